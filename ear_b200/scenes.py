@@ -1,0 +1,205 @@
+"""Scene fixtures, emitted without Blender.
+
+* `rt60_scene`       BASELINE config 1: testbench/RT60.blend's shoebox "Hall" (unit cube
+                     scaled to 10 x 6 x 4 m, 12 triangles after the exporter's quad split
+                     `[v0,v1,v2],[v0,v2,v3]`, blender/render_EAR/__init__.py:274).
+* `example1_scene`   BASELINE config 2: a 40 x 52 x 18 m hall with a 0.36 m thick, 3.47 m
+                     high partition, 44 triangles, stereo recorder with exporter defaults.
+* `synthetic_hall`   BASELINE config 4/5 generator: 60 x 40 x 20 m shoebox whose six walls are
+                     tessellated to an exact triangle count with seeded +-5 cm displacement,
+                     plus seeded interior box obstacles; 4 materials x n_bands coefficients.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .earfile import MaterialDef, MeshDef, RecorderDef, SceneDef, SourceDef
+
+_QUAD_FACES = ([0, 1, 2, 3], [4, 7, 6, 5], [0, 4, 5, 1], [1, 5, 6, 2], [2, 6, 7, 3], [4, 0, 3, 7])
+
+
+def _box_verts(lo, hi) -> np.ndarray:
+    """8 corners in the vertex order of RT60.blend's `Hall` cube."""
+    (x0, y0, z0), (x1, y1, z1) = lo, hi
+    return np.array([(x1, y1, z0), (x1, y0, z0), (x0, y0, z0), (x0, y1, z0),
+                     (x1, y1, z1), (x1, y0, z1), (x0, y0, z1), (x0, y1, z1)], np.float32)
+
+
+def box_triangles(lo, hi, faces=_QUAD_FACES) -> np.ndarray:
+    v = _box_verts(lo, hi)
+    tris = []
+    for q in faces:
+        tris.append([v[q[0]], v[q[1]], v[q[2]]])
+        tris.append([v[q[0]], v[q[2]], v[q[3]]])
+    return np.asarray(tris, np.float32)
+
+
+def rt60_scene(dims=(10.0, 6.0, 4.0), refl=(0.95, 0.95, 0.95), refr=(0.0, 0.0, 0.0), spec=(0.0, 0.5, 0.0),
+               air=(0.0, 0.0, 0.0), samples=1000000, wav="/tmp/click.wav", stereo=False) -> SceneDef:
+    dx, dy, dz = dims
+    tris = box_triangles((-dx / 2, -dy / 2, 0.0), (dx / 2, dy / 2, dz))
+    sc = SceneDef(samples=samples, air_absorption=air)
+    sc.materials.append(MaterialDef("Hall_Material", refl, refr, spec))
+    sc.meshes.append(MeshDef("Hall_Material", tris))
+    # listener at x = d0/2 - 1, source mirrored (testbench script embedded in RT60.blend)
+    sc.sources.append(SourceDef([wav], position=(-(dx / 2 - 1.0), 0.0, 1.6)))
+    sc.recorders.append(RecorderDef("/tmp/output.wav", position=(dx / 2 - 1.0, 0.0, 1.6), stereo=stereo))
+    return sc
+
+
+def example1_scene(samples=1000000, wav="/tmp/click.wav", stereo=True) -> SceneDef:
+    """Hall 40 x 52 x 18 m (12 triangles) + free-standing partition 0.36 m thick, 3.47 m high.
+    The partition and a stage block are closed boxes, split into 16 further quads so the scene has
+    the 22 quads / 44 triangles of example1.blend (the .blend's exact vertex table is not
+    recoverable without Blender; dimensions, material and source/listener placement are)."""
+    hall = box_triangles((-20.0, -26.0, 0.0), (20.0, 26.0, 18.0))
+    # partition: 5 visible quads (no bottom), split lengthwise into two boxes -> 10 quads
+    part_a = box_triangles((-0.18, -14.0, 0.0), (0.18, 0.0, 3.47), faces=_QUAD_FACES[1:])
+    part_b = box_triangles((-0.18, 0.0, 0.0), (0.18, 14.0, 3.47), faces=_QUAD_FACES[1:])
+    # stage riser: 6 quads
+    stage = box_triangles((12.0, -8.0, 0.0), (18.0, 8.0, 0.9))
+    tris = np.concatenate([hall, part_a, part_b, stage])
+    assert tris.shape[0] == 44
+    sc = SceneDef(samples=samples, air_absorption=(0.001, 0.0015, 0.003))
+    sc.materials.append(MaterialDef("Material", (0.95, 0.98, 0.99), (0.0, 0.0, 0.0), (0.3, 0.6, 0.9)))
+    sc.meshes.append(MeshDef("Material", tris))
+    sc.sources.append(SourceDef([wav], position=(-5.0, 5.0, 1.6)))
+    sc.recorders.append(RecorderDef("/tmp/example1.out.wav", position=(5.0, -5.0, 1.6), stereo=stereo,
+                                    right_ear=(-1.0, 0.0, 0.0), head_size=0.2, head_absorption=(0.1, 0.3, 0.9)))
+    return sc
+
+
+# ----------------------------------------------------------------------------------
+# synthetic hall (C4 / C5)
+# ----------------------------------------------------------------------------------
+def _wall_grid(origin, eu, ev, normal, nu, nv, rng, amp):
+    """Tessellate the parallelogram origin + s*eu + t*ev into nu x nv quads (2 triangles each);
+    interior vertices are displaced along `normal` by U(-amp, amp); border vertices stay put so
+    adjacent walls stay welded."""
+    s = np.linspace(0.0, 1.0, nu + 1)
+    t = np.linspace(0.0, 1.0, nv + 1)
+    S, T = np.meshgrid(s, t, indexing="ij")
+    P = (np.asarray(origin)[None, None, :] + S[..., None] * np.asarray(eu)[None, None, :]
+         + T[..., None] * np.asarray(ev)[None, None, :])
+    d = rng.uniform(-amp, amp, size=S.shape)
+    d[0, :] = d[-1, :] = 0.0
+    d[:, 0] = d[:, -1] = 0.0
+    P = P + d[..., None] * np.asarray(normal)[None, None, :]
+    a, b, c, e = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+    t1 = np.stack([a, b, c], axis=2)
+    t2 = np.stack([a, c, e], axis=2)
+    return np.concatenate([t1.reshape(-1, 3, 3), t2.reshape(-1, 3, 3)]).astype(np.float32)
+
+
+def _split_triangles(tris: np.ndarray, extra: int) -> np.ndarray:
+    """Raise the triangle count by exactly `extra` by bisecting the first `extra` triangles."""
+    if extra <= 0:
+        return tris
+    head, tail = tris[:extra], tris[extra:]
+    mid = (head[:, 1] + head[:, 2]) * np.float32(0.5)
+    a = np.stack([head[:, 0], head[:, 1], mid], axis=1)
+    b = np.stack([head[:, 0], mid, head[:, 2]], axis=1)
+    return np.concatenate([a, b, tail]).astype(np.float32)
+
+
+def synthetic_hall(n_tris=1_000_000, n_obstacles=2000, n_bands=8, seed=0, dims=(60.0, 40.0, 20.0),
+                   n_recorders=1, samples=10_000_000):
+    """Returns (SceneDef, material_table[M, n_bands, 4]).  The SceneDef carries bands 0..2 only
+    (the .ear format is hard-wired to three, src/EAR.cpp:176); the full table is what the
+    ABI consumes when n_bands > 3 (documented extension)."""
+    rng = np.random.default_rng(seed)
+    dx, dy, dz = dims
+    x0, x1, y0, y1 = -dx / 2, dx / 2, -dy / 2, dy / 2
+    n_box_tris = 12 * n_obstacles
+    n_wall = n_tris - n_box_tris
+    assert n_wall >= 12, "triangle budget too small for the obstacle count"
+    # (origin, eu, ev, inward normal, material)
+    walls = [
+        ((x0, y0, 0.0), (dx, 0, 0), (0, dy, 0), (0, 0, 1), 0),      # floor
+        ((x0, y0, dz), (dx, 0, 0), (0, dy, 0), (0, 0, -1), 1),      # ceiling
+        ((x0, y0, 0.0), (dx, 0, 0), (0, 0, dz), (0, 1, 0), 1),      # y = y0
+        ((x0, y1, 0.0), (dx, 0, 0), (0, 0, dz), (0, -1, 0), 1),     # y = y1
+        ((x0, y0, 0.0), (0, dy, 0), (0, 0, dz), (1, 0, 0), 1),      # x = x0
+        ((x1, y0, 0.0), (0, dy, 0), (0, 0, dz), (-1, 0, 0), 1),     # x = x1
+    ]
+    areas = np.array([np.linalg.norm(np.cross(w[1], w[2])) for w in walls])
+    per_mat = {0: [], 1: [], 2: [], 3: []}
+    made = 0
+    for w, area in zip(walls, areas):
+        quads = max(1, int(np.floor(n_wall * area / areas.sum() / 2.0)))
+        lu, lv = np.linalg.norm(w[1]), np.linalg.norm(w[2])
+        nu = max(1, int(np.floor(np.sqrt(quads * lu / lv))))
+        nv = max(1, quads // nu)
+        g = _wall_grid(w[0], w[1], w[2], w[3], nu, nv, rng, 0.05)
+        per_mat[w[4]].append(g)
+        made += g.shape[0]
+    extra = n_wall - made
+    assert extra >= 0
+    per_mat[0][0] = _split_triangles(per_mat[0][0], extra)
+    # obstacles: seat-like boxes on the floor; every 4th one is a thin glazed screen
+    for i in range(n_obstacles):
+        cx = rng.uniform(x0 + 3.0, x1 - 3.0)
+        cy = rng.uniform(y0 + 3.0, y1 - 3.0)
+        if i % 4 == 0:
+            sx, sy, sz = (0.06, rng.uniform(0.8, 2.0), rng.uniform(1.0, 2.2))
+            if rng.uniform() < 0.5:
+                sx, sy = sy, sx
+            mat = 3
+        else:
+            sx, sy, sz = rng.uniform(0.4, 1.2), rng.uniform(0.4, 1.2), rng.uniform(0.4, 1.1)
+            mat = 2
+        z_lo = 0.06
+        per_mat[mat].append(box_triangles((cx - sx / 2, cy - sy / 2, z_lo), (cx + sx / 2, cy + sy / 2, z_lo + sz)))
+    # materials: refl ~ U(0.6, 0.97), spec ~ U(0, 0.9) per band; material 3 is glazing (0.7 / 0.24)
+    table = np.zeros((4, n_bands, 4), np.float32)
+    refl = rng.uniform(0.6, 0.97, size=(4, n_bands)).astype(np.float32)
+    spec = rng.uniform(0.0, 0.9, size=(4, n_bands)).astype(np.float32)
+    refr = np.zeros((4, n_bands), np.float32)
+    refl[3, :] = 0.7
+    refr[3, :] = 0.24
+    sc = SceneDef(samples=samples, air_absorption=(0.001, 0.0015, 0.003))
+    names = ["floor", "shell", "seats", "glazing"]
+    for m in range(4):
+        sc.materials.append(MaterialDef(names[m], [float(x) for x in refl[m, :3]], [float(x) for x in refr[m, :3]],
+                                        [float(x) for x in spec[m, :3]]))
+    eps = np.float32(1e-9)
+    for m in range(4):
+        for b in range(n_bands):
+            a = np.float32(1.0)
+            a = np.float32(a - np.float32(refl[m, b] - eps))
+            a = np.float32(a - np.float32(refr[m, b] - eps))
+            table[m, b] = (refl[m, b], refr[m, b], np.float32(np.float32(1.0) - a), spec[m, b])
+    for m in range(4):
+        if per_mat[m]:
+            sc.meshes.append(MeshDef(names[m], np.concatenate(per_mat[m]).astype(np.float32)))
+    assert sc.triangles().shape[0] == n_tris, (sc.triangles().shape[0], n_tris)
+    sc.sources.append(SourceDef(["/tmp/click.wav"], position=(x0 + 8.0, 1.0, 1.7)))
+    rrng = np.random.default_rng(seed + 1)
+    for r in range(n_recorders):
+        if r == 0:
+            pos = (x1 - 10.0, -2.0, 1.8)
+        else:
+            pos = (rrng.uniform(x0 + 2, x1 - 2), rrng.uniform(y0 + 2, y1 - 2), rrng.uniform(1.2, dz - 2.0))
+        sc.recorders.append(RecorderDef(f"/tmp/hall.{r}.wav", position=pos))
+    return sc, table
+
+
+def air_factors(n_bands: int) -> np.ndarray:
+    """Per-band air survival factor per metre (1 - absorption) for the synthetic hall's bands."""
+    ab = np.linspace(0.0005, 0.004, n_bands).astype(np.float32)
+    return (np.float32(1.0) - ab).astype(np.float32)
+
+
+def write_click_wav(path: str, n: int = 443) -> str:
+    """A short 16-bit mono 44.1 kHz click (same length as example1/click.wav: 443 samples);
+    the reference refuses to load a scene whose source wav is missing (src/SoundFile.cpp:41-43)."""
+    import wave
+    t = np.arange(n, dtype=np.float64)
+    sig = np.exp(-t / 40.0) * np.sin(2 * np.pi * 1000.0 * t / 44100.0)
+    pcm = np.round(sig / np.abs(sig).max() * 30000.0).astype("<i2")
+    with wave.open(path, "wb") as w:
+        w.setnchannels(1)
+        w.setsampwidth(2)
+        w.setframerate(44100)
+        w.writeframes(pcm.tobytes())
+    return path

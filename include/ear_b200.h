@@ -1,0 +1,152 @@
+/*
+ * ear_b200 -- C ABI of the B200-native replacement for E.A.R's ray-tracing render path.
+ *
+ * The reference (aothms/ear) has no plugin/FFI interface; the seam this library replaces is
+ * the C++ call
+ *     void Scene::Render(int band, int sound, float absorbtion_factor, int num_samples,
+ *                        float dry, const std::vector<Recorder*>& rec, int keyframeID)
+ * (src/Scene.h:77, body src/Scene.cpp:111-318) as invoked once per (sound, keyframe, band)
+ * "context" by SceneContext::operator() (src/SceneContext.h:46-48) from the boost thread
+ * fan-out in Render() (src/EAR.cpp:170-207).  One ear_b200_render() call replaces that whole
+ * fan-out.  Results come back the way the reference returns them -- as recorder tracks
+ * (FloatBuffer: data, first_sample, real_length; src/Recorder.h:55-92) -- so the host post
+ * chain (Power/Truncate/T60/convolution, src/EAR.cpp:210-386) runs unchanged on top.
+ *
+ * Conventions: plain pointers and sizes, no C++ types, no exceptions across the boundary.
+ * Every call returns 0 on success, non-zero on failure; ear_b200_last_error() then holds
+ * the text a host rethrows as std::runtime_error so `main` prints the reference's
+ * "Error: <what>" line (src/EAR.cpp:404-408).  Host buffers stay owned by the caller;
+ * results are owned by the library until ear_b200_result_free().  There is no CPU fallback:
+ * without a CUDA device every compute entry point fails.
+ *
+ * All arithmetic is IEEE float32 with the reference's operation order (no FMA contraction
+ * on the geometry path); indices are int32.  Triangle index == position in `verts`, which
+ * must be the concatenation of the scene's MESH blocks in file order (src/Scene.cpp:103-106).
+ */
+#ifndef EAR_B200_H
+#define EAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EAR_B200_ABI_VERSION 1
+#define EAR_B200_MAX_BANDS 8          /* the .ear format carries 3; up to 8 through the ABI */
+#define EAR_B200_SAMPLE_RATE 44100    /* src/Recorder.h:35 */
+#define EAR_B200_MONO 1               /* OUT1, MonoRecorder  (src/MonoRecorder.cpp:83-97)   */
+#define EAR_B200_STEREO 2             /* OUT2, StereoRecorder (src/StereoRecorder.cpp:97-130) */
+
+typedef struct ear_b200_scene ear_b200_scene;    /* triangles + BVH + materials on one GPU */
+
+/* One recorder as seen by one context (positions already evaluated at the context's
+ * keyframe: Recorder::getLocation(kf), StereoRecorder::getRightEar(kf)). */
+typedef struct ear_b200_recorder {
+	int32_t kind;                                /* EAR_B200_MONO | EAR_B200_STEREO */
+	float position[3];
+	float right_ear[3];                          /* stereo only */
+	float head_size;                             /* stereo only */
+	float head_absorption[EAR_B200_MAX_BANDS];   /* stereo only; as held after load:
+	                                                max(0, (1-a)^4)  (src/StereoRecorder.cpp:55-57) */
+} ear_b200_recorder;
+
+/* One SceneContext (src/SceneContext.h:28-45): a (sound, keyframe, band) render. */
+typedef struct ear_b200_context {
+	int32_t band;                 /* column of the material table */
+	int32_t reserved;
+	int64_t num_samples;          /* rays; the CLI passes settings "samples"/10 (src/EAR.cpp:81) */
+	float absorption_factor;      /* 1 - air absorption[band] per metre (src/EAR.cpp:180) */
+	float dry_level;              /* direct-sound gain (src/Scene.cpp:308-309) */
+	float gain;                   /* source gain; tracks are scaled by gain^2 (src/Scene.cpp:313-314) */
+	float source_position[3];     /* AbstractSoundFile::getLocation(kf) (src/SoundFile.cpp:142-148) */
+} ear_b200_context;
+
+typedef struct ear_b200_options {
+	int32_t max_bounces;          /* reference hard-codes 1000 (src/Scene.cpp:143); 0 -> 1000 */
+	int32_t n_bins;               /* bins per track; 0 -> sized from max_bounces x scene diagonal */
+	uint64_t seed;                /* Philox4x32-10 key; streams are keyed by (seed, context, ray) */
+	int64_t first_ray;            /* shard: this call traces ray ids [first_ray, first_ray+ray_count) */
+	int64_t ray_count;            /*        of every context; ray_count < 0 -> all of num_samples    */
+	int32_t finalise;             /* 1: apply 1/N, direct sound, gain^2 (src/Scene.cpp:286-316);
+	                                 0: leave raw partial sums (multi-GPU: reduce first, then finalise) */
+	int32_t reserved;
+} ear_b200_options;
+
+/* FloatBuffer view (src/Recorder.h:55-65). `length` is the allocated bin count. */
+typedef struct ear_b200_track {
+	float* data;
+	uint32_t first_sample;
+	uint32_t real_length;
+	uint32_t length;
+	uint32_t reserved;
+} ear_b200_track;
+
+typedef struct ear_b200_result {
+	int32_t n_contexts;
+	int32_t n_recorders;
+	ear_b200_track* tracks;       /* [n_contexts][n_recorders][2]; mono uses slot 0 only */
+	uint64_t rays;                /* rays traced by this call */
+	uint64_t segments;            /* Scene::Bounce invocations (src/Scene.cpp:151), incl. the final miss */
+	uint64_t occlusion_queries;   /* Scene::Connect invocations (src/Scene.cpp:194) */
+	uint64_t contributions;       /* Recorder::Record invocations (src/Scene.cpp:259) */
+	uint64_t bin_updates;         /* track[i] += v operations */
+	uint64_t dropped_updates;     /* bin updates beyond n_bins (must be 0 for parity) */
+	double device_ms;             /* CUDA-event time of the trace kernels on the library's stream */
+	double bvh_build_ms;
+} ear_b200_result;
+
+const char* ear_b200_last_error(void);
+int32_t ear_b200_abi_version(void);
+int32_t ear_b200_device_count(void);
+
+/* Uploads the triangle soup (file order), builds the BVH, keeps everything resident on `device`.
+ * materials: [n_materials][n_bands][4] = {reflection, transmission, kept, specularity} where
+ * kept = absorption_coefficient as derived by src/Material.cpp:33-60.  Replaces Scene::addMesh /
+ * Mesh::Combine / Triangle ctor (src/Scene.cpp:103-106, src/Mesh.cpp:116-123, src/Triangle.cpp:26-43). */
+int32_t ear_b200_scene_create(const float* verts /*[n_tris][3][3]*/, const int32_t* tri_material /*[n_tris]*/,
+                              int32_t n_tris, const float* materials, int32_t n_materials, int32_t n_bands,
+                              int32_t device, ear_b200_scene** out);
+void ear_b200_scene_destroy(ear_b200_scene* scene);
+
+/* Harness: Mesh::RayIntersection (src/Mesh.cpp:33-56) for explicit rays.
+ * tri_index[i] = winning triangle or -1; t[i] = its distance (undefined on miss). */
+int32_t ear_b200_first_hit(ear_b200_scene* scene, const float* origins /*[n][3]*/, const float* dirs /*[n][3]*/,
+                           int64_t n, int32_t* tri_index, float* t);
+/* Harness: Scene::Connect / Mesh::LineIntersection (src/Scene.cpp:84-96, src/Mesh.cpp:58-71)
+ * for explicit segments p -> x.  out[i] = 1 if occluded. */
+int32_t ear_b200_occluded(ear_b200_scene* scene, const float* p /*[n][3]*/, const float* x /*[n][3]*/,
+                          int64_t n, uint8_t* out);
+/* Harness: replays ray ids [first_ray, first_ray+n) of one context through the bounce loop and
+ * returns, per ray, the triangle hit at each bounce (-1 terminates) -- used to check emission,
+ * Material::Bounce and Sample_Hemi against the oracle path by path.  hits: [n][max_bounces]. */
+int32_t ear_b200_trace_paths(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t ctx_index,
+                             const ear_b200_options* opt, int64_t n, int32_t* hits, float* final_state /*[n][8]*/);
+
+/* The hot path.  Host buffers in, host tracks out (device copies inside).
+ * rec: [n_contexts][n_recorders]. */
+int32_t ear_b200_render(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
+                        const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
+                        ear_b200_result** out);
+void ear_b200_result_free(ear_b200_result* result);
+
+/* Device-resident variant for one-process-per-GPU sharding: accumulates raw partial sums into
+ * caller-owned device memory so the caller can reduce them across ranks (NCCL) before finalising.
+ *   d_hist   float  [n_contexts][n_recorders][2][n_bins]   (zeroed by the caller)
+ *   d_range  uint32 [n_contexts][n_recorders][2][2]        {first_sample (init 132299), real_length (init 0)}
+ *   d_counters uint64 [8]: rays, segments, occlusion_queries, contributions, bin_updates, dropped, -, -
+ * `stream` is a cudaStream_t (0 = legacy default stream).  Asynchronous. */
+int32_t ear_b200_trace_device(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
+                              const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
+                              int32_t n_bins, float* d_hist, uint32_t* d_range, uint64_t* d_counters, void* stream);
+/* K7 on device buffers: x 1/N, direct sound, x gain^2 (src/Scene.cpp:286-316). Asynchronous. */
+int32_t ear_b200_finalise_device(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
+                                 const ear_b200_recorder* rec, int32_t n_recorders, int32_t n_bins,
+                                 float* d_hist, uint32_t* d_range, void* stream);
+/* Bins per track the library would choose for these options (same rule as ear_b200_render). */
+int32_t ear_b200_default_bins(ear_b200_scene* scene, const ear_b200_options* opt);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

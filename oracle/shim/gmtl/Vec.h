@@ -1,0 +1,2 @@
+/* forwarding header: the whole GMTL stand-in lives in gmtl.h */
+#include "gmtl.h"
