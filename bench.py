@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py -- ray-bounce segments/sec of the Scene::Render replacement on B200.
+
+Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): synthetic 1M-triangle hall
+(60 x 40 x 20 m, displaced wall tessellation + 2000 box obstacles, 4 materials), 8 frequency bands
+= 8 contexts, 1e8 rays in total (1.25e7 per band), max 50 bounces, one mono recorder, point source.
+A "step" is one full render of that ray budget.  Total work is fixed as N grows (strong scaling):
+rank g traces ray ids [g*R/N, (g+1)*R/N) of every context into its own partial histogram, then ONE
+NCCL reduce (sum) of the histograms (+ min/max of the track ranges) to rank 0, which finalises.
+
+  value : segments / second, whole job, scene + contexts already resident in HBM
+  e2e   : same metric through the C ABI with host buffers: ear_b200_scene_create (triangle upload +
+          BVH build) + ear_b200_render (context upload, trace, finalise, track download) every step
+  --impl reference : the reference's own CPU render (oracle/_ref/ref_harness, built from the
+          unmodified sources) on this host's cores, one 50-ray context per process
+          (50 is the reference's minimum: DrawProgressBar divides by samples/50).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_TRIS = int(os.environ.get("EAR_BENCH_TRIS", 1_000_000))
+N_BANDS = 8
+TOTAL_RAYS = int(float(os.environ.get("EAR_BENCH_RAYS", 1e8)))
+MAX_BOUNCES = 50
+WORKLOAD = f"synthetic {N_TRIS}-triangle hall, {N_BANDS} bands, {TOTAL_RAYS:.0e} rays, {MAX_BOUNCES} bounces, 1 mono recorder"
+
+
+def algorithmic_bytes(n_tris, segments, occlusion, bin_updates):
+    """64*S + Q(T)*(S+O) + 8*U with Q(T) = 32*ceil(log2(ceil(T/4))) + 192."""
+    depth = math.ceil(math.log2(max(2, math.ceil(n_tris / 4))))
+    q = 32 * depth + 192
+    return 64 * segments + q * (segments + occlusion) + 8 * bin_updates
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower() == "active" for r in self.rows if len(r) >= 6)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None, "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def build_workload():
+    import numpy as np
+    from ear_b200 import api, scenes
+    sc, table = scenes.synthetic_hall(n_tris=N_TRIS, n_obstacles=max(1, N_TRIS // 500), n_bands=N_BANDS, seed=0)
+    af = scenes.air_factors(N_BANDS)
+    rays_per_ctx = TOTAL_RAYS // N_BANDS
+    ctxs = [api.Context(b, rays_per_ctx, float(af[b]), sc.sources[0].position, 1.0, 1.0) for b in range(N_BANDS)]
+    recs = [api.Recorder(sc.recorders[0].position)]
+    return sc, np.ascontiguousarray(table, np.float32), ctxs, recs
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from ear_b200 import api
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (ear_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = api.load_library()
+
+    sc, table, ctxs, recs = build_workload()
+    verts, tri_mat = sc.triangles(), sc.triangle_materials()
+    scene = api.Scene(verts, tri_mat, table, device=local)
+    n_ctx, n_rec = len(ctxs), len(recs)
+    ctx_c = api.pack_contexts(ctxs)
+    rec_c, _ = api.pack_recorders(recs, n_ctx)
+    rays_per_ctx = ctxs[0].num_samples
+    lo = rays_per_ctx * rank // world
+    hi = rays_per_ctx * (rank + 1) // world
+    opt = api.make_options(max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo, finalise=False)
+    n_bins = scene.default_bins(opt)
+    n_tracks = n_ctx * n_rec * 2
+    hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
+    rng_first = torch.empty((n_tracks,), dtype=torch.int32, device=dev)
+    rng_real = torch.empty((n_tracks,), dtype=torch.int32, device=dev)
+    rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
+    counters = torch.zeros((8,), dtype=torch.int64, device=dev)
+    flush = torch.empty((64 * 1024 * 1024,), dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    launches = [0]
+
+    def step(timed_kernel=False):
+        flush.zero_()
+        hist.zero_()
+        counters.zero_()
+        rng[:, 0] = api.FIRST_SAMPLE_INIT
+        rng[:, 1] = 0
+        if timed_kernel:
+            k0.record(stream)
+        api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
+                                                  hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
+        if timed_kernel:
+            k1.record(stream)
+        launches[0] += 1
+        if world > 1:
+            # one reduce of the partial histograms over NVLink; track ranges reduce by min / max
+            dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
+            rng_first.copy_(rng[:, 0]); rng_real.copy_(rng[:, 1])
+            dist.reduce(rng_first, dst=0, op=dist.ReduceOp.MIN)
+            dist.reduce(rng_real, dst=0, op=dist.ReduceOp.MAX)
+            rng[:, 0] = rng_first; rng[:, 1] = rng_real
+        if rank == 0:
+            api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
+                                                         hist.data_ptr(), rng.data_ptr(), sp))
+            launches[0] += 3
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches[0] = 0
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    seg_total = occ_total = bins_total = 0
+    t0.record(stream)
+    for _ in range(args.steps):
+        step(timed_kernel=True)
+        k1.synchronize()
+        kernel_ms.append(k0.elapsed_time(k1))
+        c = counters.cpu().numpy()
+        seg_total += int(c[1]); occ_total += int(c[2]); bins_total += int(c[4])
+    t1.record(stream)
+    barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([seg_total, occ_total, bins_total, int(counters[5].item())], dtype=torch.int64, device=dev)
+    kms = torch.tensor([sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+    total_ms = float(ms.item())
+    segments, occl, bins, dropped = (int(x) for x in tot.tolist())
+    value = segments / (total_ms * 1e-3)
+
+    # ---- e2e: host buffers through the public C ABI, every step ----
+    e2e_ms = []
+    h2d = verts.nbytes + tri_mat.nbytes + table.nbytes + C.sizeof(ctx_c) + C.sizeof(rec_c)
+    d2h = 0
+    e2e_segments = 0
+    e2e_steps = max(1, min(args.steps, 2))
+    for _ in range(e2e_steps):
+        barrier()
+        w0 = time.perf_counter()
+        s2 = api.Scene(verts, tri_mat, table, device=local)
+        res = s2.render(ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo,
+                        finalise=(world == 1))
+        if world > 1:
+            part = torch.from_numpy(np.stack([t.data for c in res.tracks for r in c for t in r])).to(dev)
+            dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
+            part = part.cpu()
+        torch.cuda.synchronize()
+        w1 = time.perf_counter()
+        s2.close()
+        d2h = sum((t.real_length + 1) * 4 for c in res.tracks for r in c for t in r)
+        e2e_ms.append((w1 - w0) * 1e3)
+        e2e_segments += res.segments
+    e2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
+    es = torch.tensor([e2e_segments], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(es, op=dist.ReduceOp.SUM)
+    e2e_value = float(es.item()) / (float(e2.item()) * 1e-3)
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu_base = reference_sample(sc)
+        except Exception as exc:  # the baseline is reported, never required
+            cpu_base = {"error": str(exc)[:200]}
+    if rank == 0:
+        peak, which = measured_peak()
+        per_launch = algorithmic_bytes(N_TRIS, segments / args.steps / world, occl / args.steps / world,
+                                       bins / args.steps / world)
+        achieved = per_launch / (float(kms.item()) * 1e-3) / 1e9
+        line = {
+            "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
+                       "max_bounces": MAX_BOUNCES, "recorders": 1, "bins_per_track": n_bins,
+                       "sharding": f"ray ranges over {world} GPU(s), one NCCL reduce",
+                       "l2": "flushed by a 256 MiB memset before every step"},
+            "segments_per_step": segments // args.steps, "occlusion_queries_per_step": occl // args.steps,
+            "bin_updates_per_step": bins // args.steps, "dropped_updates": dropped,
+            "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "includes": "scene upload + BVH build + trace + finalise + track download"},
+            "gpu_launches": launches[0],
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "render_kernel", "kernel_ms": float(kms.item()),
+                         "peak_source": which,
+                         "bytes_model": "64*S + (32*ceil(log2(ceil(T/4)))+192)*(S+O) + 8*U per launch"},
+            "cpu_baseline": cpu_base, "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm / CPU baseline
+# ------------------------------------------------------------------------------------------
+def reference_sample(sc, procs=None):
+    """The reference's CPU render of the same scene on this host: `procs` concurrent processes, each
+    one 50-ray mid-band context through the unmodified Scene::Render (1000-bounce cap, 1e-8 cutoff)."""
+    from ear_b200 import scenes
+    harness = os.path.join(ROOT, "oracle", "_ref", "ref_harness")
+    if not os.path.exists(harness):
+        raise RuntimeError("oracle/_ref/ref_harness missing (build it where /root/reference exists)")
+    cores = os.cpu_count() or 1
+    procs = procs or cores
+    tmp = tempfile.mkdtemp(prefix="ear_ref_")
+    scenes.write_click_wav(os.path.join(tmp, "click.wav"))
+    sc.sources[0].wavs = [os.path.join(tmp, "click.wav")]
+    sc.samples = 500   # -> 50 rays per context, the reference's minimum (DrawProgressBar: samples/50)
+    path = os.path.join(tmp, "hall.ear")
+    sc.write(path)
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([harness, "render", path, str(100 + i), os.path.join(tmp, f"t{i}.bin"), "t60", "threads=1"],
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True) for i in range(procs)]
+    outs = [p.communicate()[0] for p in ps]
+    wall = time.perf_counter() - t0
+    import re
+    seg, secs = 0.0, 0.0
+    for o in outs:
+        m = re.search(r"REF_RENDER .*seconds=([0-9.]+) .*segments=([0-9.]+)", o)
+        if not m:
+            raise RuntimeError("reference run failed")
+        secs = max(secs, float(m.group(1)))
+        seg += float(m.group(2))
+    for f in os.listdir(tmp):
+        os.unlink(os.path.join(tmp, f))
+    os.rmdir(tmp)
+    return {"value": seg / secs, "unit": "segments/s", "cores": procs, "kind": "reference",
+            "sample": f"{procs} processes x 1 context x 50 rays (reference's 1000-bounce loop), {int(seg)} segments, "
+                      f"{secs:.1f} s render, {wall:.1f} s wall incl. parse"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sc, table, ctxs, recs = build_workload()
+    for _ in range(min(args.warmup, 1)):
+        reference_sample(sc, procs=max(1, (os.cpu_count() or 1)))
+    t0 = time.perf_counter()
+    seg = 0.0
+    last = None
+    for _ in range(args.steps):
+        last = reference_sample(sc)
+        seg += float(last["sample"].split("), ")[1].split(" segments")[0])
+    wall = time.perf_counter() - t0
+    value = last["value"]
+    line = {"impl": "reference", "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
+                       "max_bounces": MAX_BOUNCES, "recorders": 1},
+            "cpu_baseline": last,
+            "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

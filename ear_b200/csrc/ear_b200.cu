@@ -1,0 +1,623 @@
+// libear_b200.so -- CUDA kernels (sm_100a) + the C ABI declared in include/ear_b200.h.
+//
+// Replaces the reference's Scene::Render bounce loop (src/Scene.cpp:111-318) and what it calls.
+// Kernels (names follow SURVEY.md section 2.3):
+//   K1 emission + K2 closest hit + K3 material/resample + K4 occlusion + K5 weight/splat + K6 ray
+//   refill live in ONE persistent kernel (`render_kernel`): a ray's state never leaves registers
+//   between bounces, so the per-segment HBM traffic is BVH nodes, triangle records and histogram
+//   atomics only.  K7 (`scale_kernel`, `direct_kernel`) finalises tracks.  H1 harness kernels
+//   (`first_hit_kernel`, `occluded_kernel`, `paths_kernel`) expose K2/K4/K1-K3 for parity tests.
+// There is no CPU fallback anywhere in this file.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ear_b200.h"
+#include "bvh_build.h"
+#include "traverse.cuh"
+
+using namespace earb;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+static int32_t fail(const std::string& msg) { g_last_error = msg; return 1; }
+#define CUDA_TRY(expr)                                                                          \
+	do {                                                                                        \
+		cudaError_t err__ = (expr);                                                             \
+		if (err__ != cudaSuccess)                                                               \
+			return fail(std::string(#expr) + ": " + cudaGetErrorString(err__));                 \
+	} while (0)
+
+// ------------------------------------------------------------------------------------------
+// device-side parameter blocks
+// ------------------------------------------------------------------------------------------
+struct RenderParams {
+	const ear_b200_context* ctx;     // [n_ctx]
+	const ear_b200_recorder* rec;    // [n_ctx][n_rec]
+	const long long* work_prefix;    // [n_ctx + 1] rays of this shard, prefix-summed over contexts
+	int32_t n_ctx, n_rec, max_bounces, n_bins;
+	unsigned long long seed;
+	long long first_ray;
+	long long total_work;
+	float* hist;                     // [n_ctx][n_rec][2][n_bins]
+	uint32_t* range;                 // [n_ctx][n_rec][2][2] {first_sample, real_length}
+	unsigned long long* counters;    // [8]
+	unsigned long long* next_work;   // work-queue head
+};
+
+struct LocalCounters {
+	unsigned long long rays, segments, occlusion, contributions, bin_updates, dropped;
+};
+
+#define PI_F 3.14159265f  /* src/Distributions.h:37 */
+
+// FloatBuffer::operator[] bookkeeping (src/Recorder.cpp:52-59): first_sample = min touched index,
+// real_length = max touched index.  Read first, touch the atomic only when it would move.
+__device__ __forceinline__ void touch_range(uint32_t* range, int lo, int hi) {
+	const uint32_t cur_first = __ldcg(range), cur_real = __ldcg(range + 1);
+	if ((uint32_t)lo < cur_first) atomicMin(range, (uint32_t)lo);
+	if ((uint32_t)hi > cur_real) atomicMax(range + 1, (uint32_t)hi);
+}
+
+// One linearly decaying ramp of `w` bins starting at bin `s` (the USE_FILTER splat shared by
+// MonoRecorder::Record, src/MonoRecorder.cpp:83-97, and StereoRecorder::Record, :120-129).
+__device__ __forceinline__ void splat_ramp(float* track, uint32_t* range, int n_bins, int s, int w, float ampl,
+                                           float step, LocalCounters& lc) {
+	int lo = 0x7fffffff, hi = -1;
+	for (int i = 0; i < w; ++i) {
+		const int idx = s + i;
+		if (idx >= 0) {                         // StereoRecorder::_Sample drops negative bins (:93)
+			if (idx < n_bins) {
+				atomicAdd(track + idx, ampl);   // RED.ADD.F32 to the L2-resident histogram
+				lo = min(lo, idx); hi = max(hi, idx);
+				++lc.bin_updates;
+			} else ++lc.dropped;
+		}
+		ampl = fsub(ampl, step);
+	}
+	if (hi >= 0) touch_range(range, lo, hi);
+}
+
+__device__ __forceinline__ void record(const ear_b200_recorder& rec, float* tracks /* 2 x n_bins */, uint32_t* range,
+                                       int n_bins, V3 dir, float a, float t, float dist, int band, LocalCounters& lc) {
+	++lc.contributions;
+	const float width = fsqrt(dist);
+	const float ampl = fdiv(fmul(2.0f, a), width);
+	const int w = (int)ceilf(width);
+	if (rec.kind == EAR_B200_STEREO) {
+		const float dt = vdot(dir, mk(rec.right_ear[0], rec.right_ear[1], rec.right_ear[2]));
+		const float time_difference = fdiv(rec.head_size, 343.0f);
+		const int s_right = __double2int_rz((double)fsub(t, fmul(dt, time_difference)) * 44100.0);
+		const int s_left = __double2int_rz((double)fadd(t, fmul(dt, time_difference)) * 44100.0);
+		float ampl_left = ampl, ampl_right = ampl;
+		const float factor = powf(rec.head_absorption[band], fmul(fabsf(dt), rec.head_size));
+		if (dt < 0) ampl_right = fmul(ampl_right, fmul(factor, factor));
+		else ampl_left = fmul(ampl_left, fmul(factor, factor));
+		splat_ramp(tracks, range, n_bins, s_left, w, ampl_left, fdiv(ampl_left, (float)w), lc);
+		splat_ramp(tracks + n_bins, range + 2, n_bins, s_right, w, ampl_right, fdiv(ampl_right, (float)w), lc);
+	} else {
+		const int s = __double2int_rz((double)t * 44100.0);
+		splat_ramp(tracks, range, n_bins, s, w, ampl, fdiv(ampl, (float)w), lc);
+	}
+}
+
+// One ray of Scene::Render's outer loop (src/Scene.cpp:131-284).  PATHS = true logs the triangle
+// hit at each bounce instead of recording (parity harness).
+template <bool PATHS>
+__device__ __forceinline__ void trace_ray(const SceneDev& sc, const RenderParams& p, int c, unsigned long long ray,
+                                          LocalCounters& lc, int32_t* hits, float* final_state) {
+	const ear_b200_context cx = p.ctx[c];
+	const int band = cx.band;
+	const float af = cx.absorption_factor;
+	Rng rng;
+	rng.start(p.seed, (uint32_t)c, ray);
+	++lc.rays;
+	float intensity = 1.0f, path = 0.0f;
+	// AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226)
+	V3 o = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
+	V3 d = sample_sphere(rng);
+	V3 prev_dir = vnormalized(d);  // bounce 0 ends with prev_ray_dir = normalize(dir) (src/Scene.cpp:277)
+	// bounce 0: intensity = 1 is FP_NORMAL and >= 1e-8, nothing is recorded for point sources (:185)
+	for (int b = 1; b < p.max_bounces; ++b) {
+		// ---- Scene::Bounce (src/Scene.cpp:49-82) ----
+		++lc.segments;
+		float t; int32_t slot;
+		const int32_t idx = traverse<false>(sc, o, d, t, slot);
+		if (PATHS) hits[b] = idx;
+		if (idx < 0) break;
+		const float4 r1 = __ldg(sc.tris + 3 * (size_t)slot + 1);
+		const float4 r2 = __ldg(sc.tris + 3 * (size_t)slot + 2);
+		const V3 tri_n = vnormalized(vcross(mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z)));  // src/Triangle.cpp:41
+		const V3 pnt = vadd(o, vscale(d, t));                                              // src/Mesh.cpp:48
+		V3 n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;                      // :49-53
+		const float4 m = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
+		// Material::Bounce (src/Material.cpp:76-83); comparisons against 0.0001 are in double there
+		bool refract;
+		if ((double)m.x < 0.0001 && (double)m.y < 0.0001) refract = false;
+		else refract = !(rng.unit() <= fdiv(m.x, fadd(m.x, m.y)));
+		const float spec = m.w;
+		V3 v;
+		if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
+		else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
+		const float seg = vlength(vsub(pnt, o));
+		intensity = fmul(intensity, powf(af, seg));                                         // src/Scene.cpp:154
+		path = fadd(path, seg);
+		o = pnt; d = v;
+		intensity = fmul(intensity, m.z);                                                   // :169-171
+		if (invalid_float(intensity)) break;                                                // :175
+		if (!PATHS) {
+			for (int r = 0; r < p.n_rec; ++r) {
+				const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
+				const V3 x = mk(rec.position[0], rec.position[1], rec.position[2]);
+				const V3 segv = vsub(x, o);   // LineSeg(p, x) = Ray(p, x - p)
+				++lc.occlusion;
+				float tt; int32_t ss;
+				if (traverse<true>(sc, o, segv, tt, ss)) continue;                          // :194-197
+				const V3 lsdir = vnormalized(segv);
+				if (!(vdot(lsdir, n) > 0.0f)) continue;                                     // :205-209
+				float factor;
+				if (!refract) {                                                             // :219-235
+					const V3 rv = vreflect(prev_dir, n);
+					const float diff = -vdot(n, prev_dir);
+					const float dsp = vdot(rv, lsdir);
+					const float specf = (0.0f < dsp) ? dsp : 0.0f;
+					factor = fadd(fmul(fmul(spec, 1001.0f), powf(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+				} else {                                                                    // :236-247
+					const float diff = vdot(n, prev_dir);
+					const float dsp = vdot(prev_dir, lsdir);
+					const float specf = (0.0f < dsp) ? dsp : 0.0f;
+					factor = fadd(fmul(fmul(spec, 1001.0f), powf(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+				}
+				float contrib = fmul(intensity, factor);
+				const float l = vlength(segv);                                              // :250
+				contrib = fmul(contrib, powf(af, l));
+				contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
+				if (invalid_float(contrib)) continue;
+				if (b & 1) contrib = fmul(contrib, -1.0f);                                  // :257
+				const size_t slot2 = ((size_t)c * p.n_rec + r) * 2;
+				record(rec, p.hist + slot2 * p.n_bins, p.range + slot2 * 2, p.n_bins, lsdir, contrib,
+				       fdiv(fadd(path, l), 343.0f), fadd(path, l), band, lc);
+			}
+		}
+		if ((double)intensity < 0.00000001) break;                                          // :275
+		prev_dir = vnormalized(d);                                                          // :277
+	}
+	if (PATHS && final_state) {
+		final_state[0] = o.x; final_state[1] = o.y; final_state[2] = o.z;
+		final_state[3] = d.x; final_state[4] = d.y; final_state[5] = d.z;
+		final_state[6] = intensity; final_state[7] = path;
+	}
+}
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+// Persistent kernel: each warp pulls 32 ray ids at a time from a global queue (K6: dead lanes are
+// refilled at warp granularity), maps them to (context, ray) and runs the bounce loop.
+__global__ void __launch_bounds__(128) render_kernel(SceneDev sc, RenderParams p) {
+	const int lane = threadIdx.x & 31;
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	for (;;) {
+		unsigned long long base = 0;
+		if (lane == 0) base = atomicAdd(p.next_work, 32ull);
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if ((long long)base >= p.total_work) break;
+		const long long w = (long long)base + lane;
+		if (w < p.total_work) {
+			int c = 0;
+			while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
+			const unsigned long long ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
+			trace_ray<false>(sc, p, c, ray, lc, nullptr, nullptr);
+		}
+		__syncwarp();
+	}
+	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
+	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
+	if (lane == 0) {
+		atomicAdd(p.counters + 0, v0); atomicAdd(p.counters + 1, v1); atomicAdd(p.counters + 2, v2);
+		atomicAdd(p.counters + 3, v3); atomicAdd(p.counters + 4, v4); atomicAdd(p.counters + 5, v5);
+	}
+}
+
+__global__ void paths_kernel(SceneDev sc, RenderParams p, int c, long long n, int32_t* hits, float* final_state) {
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	int32_t* h = hits + (size_t)i * p.max_bounces;
+	for (int b = 0; b < p.max_bounces; ++b) h[b] = -2;
+	trace_ray<true>(sc, p, c, (unsigned long long)(p.first_ray + i), lc, h, final_state + 8 * (size_t)i);
+}
+
+__global__ void first_hit_kernel(SceneDev sc, const float* origins, const float* dirs, long long n, int32_t* tri_index,
+                                 float* t_out) {
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	float t; int32_t slot;
+	const int32_t idx = traverse<false>(sc, mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
+	                                    mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), t, slot);
+	tri_index[i] = idx;
+	t_out[i] = t;
+}
+
+__global__ void occluded_kernel(SceneDev sc, const float* pp, const float* xx, long long n, uint8_t* out) {
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const V3 p = mk(pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
+	const V3 x = mk(xx[3 * i], xx[3 * i + 1], xx[3 * i + 2]);
+	float t; int32_t slot;
+	out[i] = (uint8_t)traverse<true>(sc, p, vsub(x, p), t, slot);
+}
+
+// ---- K7: Scene::Render's tail, src/Scene.cpp:286-316 ----
+// FloatBuffer::Multiply over [first_sample, real_length) -- the last touched bin is NOT scaled
+// (src/Recorder.cpp:85-89).  mode 0: x 1/amount, mode 1: x gain^2.
+__global__ void scale_kernel(RenderParams p, int mode) {
+	const int track = blockIdx.y;  // (ctx * n_rec + rec) * 2 + k
+	const int c = track / (2 * p.n_rec);
+	const int r = (track / 2) % p.n_rec;
+	if ((track & 1) && p.rec[(size_t)c * p.n_rec + r].kind != EAR_B200_STEREO) return;
+	const uint32_t first = p.range[2 * track], real = p.range[2 * track + 1];
+	float f;
+	if (mode == 0) {
+		// `amount` is a float bumped by 1.0f per ray (src/Scene.cpp:122,127): it saturates at 2^24
+		const long long ns = p.ctx[c].num_samples;
+		f = fdiv(1.0f, (float)(ns < 16777216 ? ns : 16777216));
+	} else f = fmul(p.ctx[c].gain, p.ctx[c].gain);
+	float* tr = p.hist + (size_t)track * p.n_bins;
+	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < real; i += gridDim.x * blockDim.x)
+		tr[i] = fmul(tr[i], f);
+}
+// Direct sound (src/Scene.cpp:299-311): one thread per (context, recorder).
+__global__ void direct_kernel(SceneDev sc, RenderParams p) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= p.n_ctx * p.n_rec) return;
+	const int c = i / p.n_rec;
+	const ear_b200_context cx = p.ctx[c];
+	const ear_b200_recorder& rec = p.rec[i];
+	const V3 listener = mk(rec.position[0], rec.position[1], rec.position[2]);
+	const V3 source = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
+	float t; int32_t slot;
+	if (traverse<true>(sc, listener, vsub(source, listener), t, slot)) return;
+	const V3 dist = vsub(listener, source);
+	const float len = vlength(dist);
+	const V3 dir = vnormalized(dist);
+	const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), powf(cx.absorption_factor, len)),
+	                     cx.dry_level);
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	record(rec, p.hist + (size_t)i * 2 * p.n_bins, p.range + (size_t)i * 4, p.n_bins, dir, a, fdiv(len, 343.0f), len,
+	       cx.band, lc);
+}
+__global__ void init_range_kernel(uint32_t* range, int n_tracks) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_tracks) { range[2 * i] = 3 * EAR_B200_SAMPLE_RATE - 1; range[2 * i + 1] = 0; }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct ear_b200_scene {
+	int device = 0;
+	SceneDev dev{};
+	float4* d_nodes = nullptr;
+	float4* d_tris = nullptr;
+	float4* d_materials = nullptr;
+	std::vector<float> materials;
+	int32_t n_tris = 0, n_materials = 0, n_bands = 0, n_nodes = 0, depth = 0;
+	float diagonal = 0.0f;
+	double bvh_build_ms = 0.0;
+	cudaStream_t stream = nullptr;
+	int sm_count = 148;
+	// scratch reused across calls
+	ear_b200_context* d_ctx = nullptr; ear_b200_recorder* d_rec = nullptr; long long* d_prefix = nullptr;
+	unsigned long long* d_queue = nullptr;
+	size_t ctx_cap = 0, rec_cap = 0;
+};
+
+extern "C" const char* ear_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t ear_b200_abi_version(void) { return EAR_B200_ABI_VERSION; }
+extern "C" int32_t ear_b200_device_count(void) {
+	int n = 0;
+	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return n;
+}
+
+extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_material, int32_t n_tris,
+                                         const float* materials, int32_t n_materials, int32_t n_bands, int32_t device,
+                                         ear_b200_scene** out) {
+	if (!out) return fail("scene_create: out is null");
+	*out = nullptr;
+	if (n_tris < 0 || n_materials <= 0 || n_bands <= 0 || n_bands > EAR_B200_MAX_BANDS)
+		return fail("scene_create: bad sizes (need n_materials >= 1, 1 <= n_bands <= 8)");
+	if ((n_tris > 0 && !verts) || !materials) return fail("scene_create: null input");
+	if (n_tris >= (1 << 28)) return fail("scene_create: too many triangles (limit 2^28)");
+	for (int32_t i = 0; i < n_tris && tri_material; ++i)
+		if (tri_material[i] < 0 || tri_material[i] >= n_materials) return fail("scene_create: material index out of range");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail("no CUDA device: ear_b200 has no CPU fallback");
+	}
+	if (device < 0 || device >= ndev) return fail("scene_create: device index out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	ear_b200_scene* s = new ear_b200_scene();
+	s->device = device;
+	const auto t0 = std::chrono::steady_clock::now();
+	Bvh bvh;
+	build_bvh(verts, tri_material, n_tris, bvh);
+	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	s->n_tris = n_tris; s->n_materials = n_materials; s->n_bands = n_bands;
+	s->n_nodes = (int32_t)bvh.nodes.size(); s->depth = bvh.depth; s->diagonal = bvh.diagonal;
+	s->materials.assign(materials, materials + (size_t)n_materials * n_bands * 4);
+	cudaDeviceProp prop;
+	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	s->sm_count = prop.multiProcessorCount;
+	CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	CUDA_TRY(cudaMalloc(&s->d_nodes, std::max<size_t>(bvh.nodes.size(), 1) * sizeof(Node)));
+	CUDA_TRY(cudaMalloc(&s->d_tris, std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord)));
+	CUDA_TRY(cudaMalloc(&s->d_materials, s->materials.size() * sizeof(float)));
+	CUDA_TRY(cudaMemcpy(s->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+	if (!bvh.tris.empty())
+		CUDA_TRY(cudaMemcpy(s->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(s->d_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMalloc(&s->d_queue, sizeof(unsigned long long)));
+	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
+	s->dev.n_tris = n_tris; s->dev.n_materials = n_materials; s->dev.n_bands = n_bands;
+	*out = s;
+	return 0;
+}
+
+extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
+	if (!s) return;
+	cudaSetDevice(s->device);
+	cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_materials);
+	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue);
+	if (s->stream) cudaStreamDestroy(s->stream);
+	delete s;
+}
+
+extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, const float* dirs, int64_t n,
+                                      int32_t* tri_index, float* t) {
+	if (!s) return fail("first_hit: null scene");
+	if (n <= 0) return 0;
+	CUDA_TRY(cudaSetDevice(s->device));
+	float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_i = nullptr;
+	CUDA_TRY(cudaMalloc(&d_o, n * 12)); CUDA_TRY(cudaMalloc(&d_d, n * 12));
+	CUDA_TRY(cudaMalloc(&d_t, n * 4)); CUDA_TRY(cudaMalloc(&d_i, n * 4));
+	CUDA_TRY(cudaMemcpyAsync(d_o, origins, n * 12, cudaMemcpyHostToDevice, s->stream));
+	CUDA_TRY(cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, s->stream));
+	first_hit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(tri_index, d_i, n * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
+	return 0;
+}
+
+extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p, const float* x, int64_t n, uint8_t* out) {
+	if (!s) return fail("occluded: null scene");
+	if (n <= 0) return 0;
+	CUDA_TRY(cudaSetDevice(s->device));
+	float *d_p = nullptr, *d_x = nullptr; uint8_t* d_out = nullptr;
+	CUDA_TRY(cudaMalloc(&d_p, n * 12)); CUDA_TRY(cudaMalloc(&d_x, n * 12)); CUDA_TRY(cudaMalloc(&d_out, n));
+	CUDA_TRY(cudaMemcpyAsync(d_p, p, n * 12, cudaMemcpyHostToDevice, s->stream));
+	CUDA_TRY(cudaMemcpyAsync(d_x, x, n * 12, cudaMemcpyHostToDevice, s->stream));
+	occluded_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_p, d_x, n, d_out);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	cudaFree(d_p); cudaFree(d_x); cudaFree(d_out);
+	return 0;
+}
+
+// bins per track: the longest path the bounce loop can produce, in samples, plus the widest ramp
+static int32_t default_bins(const ear_b200_scene* s, int32_t max_bounces) {
+	if (max_bounces <= 0) max_bounces = 1000;
+	// energy bound: a ray dies once intensity < 1e-8 (src/Scene.cpp:275); kept <= k_max per bounce
+	float k_max = 0.0f;
+	for (size_t i = 0; i < s->materials.size() / 4; ++i) k_max = std::max(k_max, s->materials[4 * i + 2]);
+	double bounces = max_bounces;
+	if (k_max > 0.0f && k_max < 1.0f) bounces = std::min(bounces, std::ceil(std::log(1e-8) / std::log((double)k_max)) + 2.0);
+	const double reach = 2.0 * (double)s->diagonal + 1.0;  // source / recorder may sit outside the mesh bounds
+	const double path = (bounces + 1.0) * reach;
+	double bins = path / 343.0 * 44100.0 + std::sqrt(path) + 64.0;
+	bins = std::min(bins, 64.0 * 1024.0 * 1024.0);
+	bins = std::max(bins, 3.0 * 44100.0);               // FloatBuffer starts at 3 s (src/Recorder.h:36)
+	return (int32_t)bins;
+}
+extern "C" int32_t ear_b200_default_bins(ear_b200_scene* s, const ear_b200_options* opt) {
+	if (!s) return 0;
+	if (opt && opt->n_bins > 0) return opt->n_bins;
+	return default_bins(s, opt ? opt->max_bounces : 1000);
+}
+
+static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx, const ear_b200_recorder* rec,
+                             int32_t n_rec, const ear_b200_options* opt, cudaStream_t stream, RenderParams& p) {
+	if (n_ctx <= 0 || n_rec <= 0 || !ctx || !rec) return fail("render: need at least one context and one recorder");
+	for (int32_t c = 0; c < n_ctx; ++c) {
+		if (ctx[c].band < 0 || ctx[c].band >= s->n_bands) return fail("render: context band outside the material table");
+		if (ctx[c].num_samples < 0) return fail("render: negative num_samples");
+	}
+	for (int32_t i = 0; i < n_ctx * n_rec; ++i)
+		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("render: unknown recorder kind");
+	if ((size_t)n_ctx > s->ctx_cap) {
+		cudaFree(s->d_ctx); cudaFree(s->d_prefix);
+		CUDA_TRY(cudaMalloc(&s->d_ctx, sizeof(ear_b200_context) * n_ctx));
+		CUDA_TRY(cudaMalloc(&s->d_prefix, sizeof(long long) * (n_ctx + 1)));
+		s->ctx_cap = n_ctx;
+	}
+	if ((size_t)n_ctx * n_rec > s->rec_cap) {
+		cudaFree(s->d_rec);
+		CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec));
+		s->rec_cap = (size_t)n_ctx * n_rec;
+	}
+	std::vector<long long> prefix(n_ctx + 1, 0);
+	const long long first = opt ? opt->first_ray : 0;
+	for (int32_t c = 0; c < n_ctx; ++c) {
+		long long cnt = (opt && opt->ray_count >= 0) ? opt->ray_count : (long long)ctx[c].num_samples - first;
+		cnt = std::max<long long>(0, std::min<long long>(cnt, (long long)ctx[c].num_samples - first));
+		prefix[c + 1] = prefix[c] + cnt;
+	}
+	CUDA_TRY(cudaMemcpyAsync(s->d_ctx, ctx, sizeof(ear_b200_context) * n_ctx, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(s->d_prefix, prefix.data(), sizeof(long long) * (n_ctx + 1), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));  // `prefix` is a stack temporary
+	p.ctx = s->d_ctx; p.rec = s->d_rec; p.work_prefix = s->d_prefix;
+	p.n_ctx = n_ctx; p.n_rec = n_rec;
+	p.max_bounces = (opt && opt->max_bounces > 0) ? opt->max_bounces : 1000;
+	p.seed = opt ? opt->seed : 1;
+	p.first_ray = first;
+	p.total_work = prefix[n_ctx];
+	p.next_work = s->d_queue;
+	return 0;
+}
+
+static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
+	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
+	if (p.total_work > 0) {
+		int blocks_per_sm = 0;
+		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, 128, 0));
+		const long long want = (p.total_work + 127) / 128;
+		const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)s->sm_count * std::max(1, blocks_per_sm)));
+		render_kernel<<<grid, 128, 0, stream>>>(s->dev, p);
+		CUDA_TRY(cudaGetLastError());
+	}
+	return 0;
+}
+
+static int32_t launch_finalise(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
+	const int n_tracks = p.n_ctx * p.n_rec * 2;
+	dim3 grid(64, n_tracks);
+	scale_kernel<<<grid, 256, 0, stream>>>(p, 0);
+	direct_kernel<<<(p.n_ctx * p.n_rec + 63) / 64, 64, 0, stream>>>(s->dev, p);
+	scale_kernel<<<grid, 256, 0, stream>>>(p, 1);
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+extern "C" int32_t ear_b200_trace_device(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,
+                                         const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt,
+                                         int32_t n_bins, float* d_hist, uint32_t* d_range, uint64_t* d_counters,
+                                         void* stream) {
+	if (!s) return fail("trace_device: null scene");
+	if (!d_hist || !d_range || !d_counters || n_bins <= 0) return fail("trace_device: null device buffer");
+	CUDA_TRY(cudaSetDevice(s->device));
+	RenderParams p{};
+	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, (cudaStream_t)stream, p)) return rc;
+	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = (unsigned long long*)d_counters;
+	return launch_trace(s, p, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ear_b200_finalise_device(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,
+                                            const ear_b200_recorder* rec, int32_t n_rec, int32_t n_bins, float* d_hist,
+                                            uint32_t* d_range, void* stream) {
+	if (!s) return fail("finalise_device: null scene");
+	CUDA_TRY(cudaSetDevice(s->device));
+	RenderParams p{};
+	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, nullptr, (cudaStream_t)stream, p)) return rc;
+	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range;
+	return launch_finalise(s, p, (cudaStream_t)stream);
+}
+
+extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,
+                                   const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt,
+                                   ear_b200_result** out) {
+	if (!s || !out) return fail("render: null scene/out");
+	*out = nullptr;
+	CUDA_TRY(cudaSetDevice(s->device));
+	RenderParams p{};
+	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, s->stream, p)) return rc;
+	const int32_t n_bins = ear_b200_default_bins(s, opt);
+	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	float* d_hist = nullptr; uint32_t* d_range = nullptr; unsigned long long* d_counters = nullptr;
+	CUDA_TRY(cudaMalloc(&d_hist, n_tracks * n_bins * sizeof(float)));
+	CUDA_TRY(cudaMalloc(&d_range, n_tracks * 2 * sizeof(uint32_t)));
+	CUDA_TRY(cudaMalloc(&d_counters, 8 * sizeof(unsigned long long)));
+	CUDA_TRY(cudaMemsetAsync(d_hist, 0, n_tracks * n_bins * sizeof(float), s->stream));
+	CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
+	init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(d_range, (int)n_tracks);
+	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = d_counters;
+	cudaEvent_t e0, e1;
+	CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+	CUDA_TRY(cudaEventRecord(e0, s->stream));
+	if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
+	CUDA_TRY(cudaEventRecord(e1, s->stream));
+	if (!opt || opt->finalise) { if (int32_t rc = launch_finalise(s, p, s->stream)) return rc; }
+	std::vector<uint32_t> range(n_tracks * 2);
+	unsigned long long counters[8];
+	CUDA_TRY(cudaMemcpyAsync(range.data(), d_range, range.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	float ms = 0.0f;
+	CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+
+	ear_b200_result* res = (ear_b200_result*)calloc(1, sizeof(ear_b200_result));
+	res->n_contexts = n_ctx; res->n_recorders = n_rec;
+	res->tracks = (ear_b200_track*)calloc(n_tracks, sizeof(ear_b200_track));
+	for (size_t k = 0; k < n_tracks; ++k) {
+		ear_b200_track& tr = res->tracks[k];
+		const bool used = !(k & 1) || rec[k / 2].kind == EAR_B200_STEREO;
+		tr.first_sample = range[2 * k]; tr.real_length = range[2 * k + 1]; tr.length = used ? (uint32_t)n_bins : 0;
+		if (!used) continue;
+		tr.data = (float*)calloc((size_t)n_bins, sizeof(float));
+		if (!tr.data) return fail("render: out of host memory");
+		const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
+		CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + k * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+	}
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
+	res->contributions = counters[3]; res->bin_updates = counters[4]; res->dropped_updates = counters[5];
+	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;
+	cudaFree(d_hist); cudaFree(d_range); cudaFree(d_counters);
+	*out = res;
+	return 0;
+}
+
+extern "C" void ear_b200_result_free(ear_b200_result* r) {
+	if (!r) return;
+	if (r->tracks) {
+		const size_t n = (size_t)r->n_contexts * r->n_recorders * 2;
+		for (size_t k = 0; k < n; ++k) free(r->tracks[k].data);
+		free(r->tracks);
+	}
+	free(r);
+}
+
+extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_context* ctx, int32_t ctx_index,
+                                        const ear_b200_options* opt, int64_t n, int32_t* hits, float* final_state) {
+	if (!s || !ctx || !opt || !hits) return fail("trace_paths: null argument");
+	if (n <= 0) return 0;
+	CUDA_TRY(cudaSetDevice(s->device));
+	const int max_b = opt->max_bounces > 0 ? opt->max_bounces : 1000;
+	// the kernel indexes contexts by ctx_index (it keys the Philox stream): place ctx there
+	std::vector<ear_b200_context> cs(ctx_index + 1, *ctx);
+	ear_b200_recorder dummy{}; dummy.kind = EAR_B200_MONO;
+	std::vector<ear_b200_recorder> rs(ctx_index + 1, dummy);
+	ear_b200_options o2 = *opt; o2.ray_count = 0;
+	RenderParams p{};
+	if (int32_t rc = upload_params(s, cs.data(), ctx_index + 1, rs.data(), 1, &o2, s->stream, p)) return rc;
+	p.first_ray = opt->first_ray;
+	int32_t* d_hits = nullptr; float* d_state = nullptr;
+	CUDA_TRY(cudaMalloc(&d_hits, (size_t)n * max_b * 4)); CUDA_TRY(cudaMalloc(&d_state, (size_t)n * 32));
+	CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)n * 32, s->stream));
+	paths_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpyAsync(hits, d_hits, (size_t)n * max_b * 4, cudaMemcpyDeviceToHost, s->stream));
+	if (final_state) CUDA_TRY(cudaMemcpyAsync(final_state, d_state, (size_t)n * 32, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	cudaFree(d_hits); cudaFree(d_state);
+	return 0;
+}

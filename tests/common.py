@@ -1,0 +1,106 @@
+"""Shared scene / ray generators for the parity tests (seeded, deterministic)."""
+from __future__ import annotations
+
+import numpy as np
+
+from ear_b200 import scenes
+from ear_b200.earfile import MaterialDef, MeshDef, RecorderDef, SceneDef, SourceDef
+
+
+def soup_scene(n_tris=3000, seed=5, extent=10.0, size=0.8) -> SceneDef:
+    """Random triangle soup: unstructured, overlapping, many near-degenerate configurations."""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-extent, extent, (n_tris, 1, 3))
+    v = (c + rng.normal(scale=size, size=(n_tris, 3, 3))).astype(np.float32)
+    sc = SceneDef(samples=10000)
+    sc.materials.append(MaterialDef("a", (0.9, 0.8, 0.7), (0.0, 0.1, 0.2), (0.2, 0.5, 0.8)))
+    sc.materials.append(MaterialDef("b", (0.5, 0.6, 0.7), (0.3, 0.2, 0.1), (0.0, 1.0, 0.4)))
+    sc.meshes.append(MeshDef("a", v[: n_tris // 2]))
+    sc.meshes.append(MeshDef("b", v[n_tris // 2:]))
+    sc.sources.append(SourceDef(["/tmp/click.wav"], position=(0.5, 0.25, 0.1)))
+    sc.recorders.append(RecorderDef("/tmp/o.wav", position=(-1.0, 2.0, 0.5)))
+    return sc
+
+
+def small_hall(n_tris=20000, n_obstacles=200, seed=0):
+    sc, table = scenes.synthetic_hall(n_tris=n_tris, n_obstacles=n_obstacles, n_bands=3, seed=seed, samples=10000)
+    return sc
+
+
+def named_scene(name: str) -> SceneDef:
+    if name == "rt60":
+        return scenes.rt60_scene(samples=10000)
+    if name == "rt60_saved":   # material as saved in RT60.blend: refl (.95,.05,.95) spec (0,1,0)
+        return scenes.rt60_scene(refl=(0.95, 0.05, 0.95), spec=(0.0, 1.0, 0.0), samples=10000)
+    if name == "example1":
+        return scenes.example1_scene(samples=10000)
+    if name == "hall20k":
+        return small_hall()
+    if name == "soup":
+        return soup_scene()
+    raise KeyError(name)
+
+
+def make_rays(sc: SceneDef, n: int, seed: int = 1):
+    """A mix of (a) uniform rays from inside the bounds, (b) rays aimed exactly at triangle
+    vertices / edge points (shared edges, ties), (c) rays grazing a triangle's plane, (d) rays
+    leaving a surface point (the bounce case: origin on a triangle)."""
+    rng = np.random.default_rng(seed)
+    tris = sc.triangles()
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    T = tris.shape[0]
+    q = n // 4
+    o = [rng.uniform(lo, hi, (q, 3))]
+    d = [rng.normal(size=(q, 3))]
+    # (b) aimed at vertices and edge points
+    k = rng.integers(0, T, q)
+    w = rng.integers(0, 3, q)
+    a, b = tris[k, w], tris[k, (w + 1) % 3]
+    s = rng.choice([0.0, 0.25, 0.5, 1.0], q)[:, None]
+    target = a + s * (b - a)
+    ob = rng.uniform(lo, hi, (q, 3))
+    o.append(ob)
+    d.append(target - ob)
+    # (c) grazing: start just above the plane of triangle k, travel almost inside the plane
+    k = rng.integers(0, T, q)
+    v0, v1, v2 = tris[k, 0], tris[k, 1], tris[k, 2]
+    nrm = np.cross(v1 - v0, v2 - v0)
+    nrm /= np.maximum(np.linalg.norm(nrm, axis=1, keepdims=True), 1e-20)
+    cen = (v0 + v1 + v2) / 3.0
+    inplane = v1 - v0
+    inplane /= np.maximum(np.linalg.norm(inplane, axis=1, keepdims=True), 1e-20)
+    tilt = 10.0 ** rng.uniform(-6, -1, (q, 1)) * rng.choice([-1.0, 1.0], (q, 1))
+    dist = rng.uniform(0.5, 5.0, (q, 1))
+    og = cen - inplane * dist - nrm * tilt * dist
+    o.append(og)
+    d.append(inplane + nrm * tilt)
+    # (d) origin on a surface, random outgoing direction
+    k = rng.integers(0, T, n - 3 * q)
+    u = rng.uniform(0, 1, (n - 3 * q, 2))
+    flip = u.sum(1) > 1
+    u[flip] = 1 - u[flip]
+    p = tris[k, 0] + u[:, :1] * (tris[k, 1] - tris[k, 0]) + u[:, 1:] * (tris[k, 2] - tris[k, 0])
+    o.append(p)
+    d.append(rng.normal(size=(n - 3 * q, 3)))
+    o = np.concatenate(o).astype(np.float32)
+    d = np.concatenate(d)
+    d = (d / np.maximum(np.linalg.norm(d, axis=1, keepdims=True), 1e-20)).astype(np.float32)
+    return o, d
+
+
+def make_segments(sc: SceneDef, n: int, seed: int = 2):
+    """Occlusion queries: surface point -> recorder (the render case), plus random pairs."""
+    rng = np.random.default_rng(seed)
+    tris = sc.triangles()
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    T = tris.shape[0]
+    h = n // 2
+    k = rng.integers(0, T, h)
+    u = rng.uniform(0, 1, (h, 2))
+    flip = u.sum(1) > 1
+    u[flip] = 1 - u[flip]
+    p1 = tris[k, 0] + u[:, :1] * (tris[k, 1] - tris[k, 0]) + u[:, 1:] * (tris[k, 2] - tris[k, 0])
+    x1 = np.tile(np.asarray(sc.recorders[0].position, np.float64)[None, :], (h, 1))
+    p2 = rng.uniform(lo, hi, (n - h, 3))
+    x2 = rng.uniform(lo, hi, (n - h, 3))
+    return np.concatenate([p1, p2]).astype(np.float32), np.concatenate([x1, x2]).astype(np.float32)

@@ -1,0 +1,141 @@
+"""GPU parity tests: libear_b200.so (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars: first-hit triangle indices bit-exact and hit distances bit-exact (north star asks 1e-5
+relative); occlusion answers identical; bounce paths (emission, Material::Bounce, Sample_Hemi,
+reflection) identical triangle by triangle under the shared Philox streams; histograms within
+REL_TOL of the oracle's per bin (float atomics reorder the sums; powf differs by <= 2 ulp)."""
+import numpy as np
+import pytest
+
+from ear_b200 import api
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 2e-4     # per-bin |gpu - oracle| <= REL_TOL * max|oracle| over the track
+
+
+@pytest.fixture(scope="module")
+def ob():
+    from oracle import binding
+    binding.build()
+    return binding
+
+
+def _pair(ob, sc):
+    return api.Scene.from_def(sc), ob.OracleScene.from_def(sc)
+
+
+@pytest.mark.parametrize("name,n", [("rt60", 40000), ("example1", 40000), ("soup", 40000), ("hall20k", 24000)])
+def test_first_hit_bit_exact(ob, name, n):
+    sc = common.named_scene(name)
+    gpu, cpu = _pair(ob, sc)
+    o, d = common.make_rays(sc, n)
+    gi, gt = gpu.first_hit(o, d)
+    ci, ct = cpu.first_hit(o, d)
+    assert np.array_equal(gi, ci), f"{(gi != ci).sum()} of {n} first-hit indices differ"
+    hit = ci >= 0
+    assert hit.mean() > 0.3
+    assert np.array_equal(gt[hit].view(np.uint32), ct[hit].view(np.uint32))
+
+
+@pytest.mark.parametrize("name,n", [("rt60", 40000), ("example1", 40000), ("soup", 40000), ("hall20k", 24000)])
+def test_occlusion_identical(ob, name, n):
+    sc = common.named_scene(name)
+    gpu, cpu = _pair(ob, sc)
+    p, x = common.make_segments(sc, n)
+    g = gpu.occluded(p, x)
+    c = cpu.occluded(p, x)
+    assert np.array_equal(g, c), f"{(g != c).sum()} of {n} occlusion answers differ"
+
+
+def test_empty_and_tiny_scenes(ob):
+    # one triangle, and a ray batch of size 1 / 0
+    sc = common.soup_scene(n_tris=2, seed=9)
+    gpu, cpu = _pair(ob, sc)
+    o, d = common.make_rays(sc, 64)
+    assert np.array_equal(gpu.first_hit(o, d)[0], cpu.first_hit(o, d)[0])
+    gi, _ = gpu.first_hit(o[:1], d[:1])
+    assert gi.shape == (1,)
+    gi, _ = gpu.first_hit(o[:0], d[:0])
+    assert gi.shape == (0,)
+
+
+@pytest.mark.parametrize("name,band", [("rt60", 1), ("rt60_saved", 1), ("example1", 2), ("soup", 0), ("hall20k", 1)])
+def test_bounce_paths_identical(ob, name, band):
+    sc = common.named_scene(name)
+    gpu, cpu = _pair(ob, sc)
+    ctx = api.Context(band, 1000, 0.999, sc.sources[0].position)
+    n, mb = (300, 40) if name == "hall20k" else (1500, 60)
+    hg, sg = gpu.trace_paths(ctx, 3, n, mb, seed=11, first_ray=17)
+    hc, s_c = cpu.trace_paths(ctx, 3, n, mb, seed=11, first_ray=17)
+    assert np.array_equal(hg, hc), f"{(hg != hc).any(axis=1).sum()} of {n} paths differ"
+    # geometry of the final ray state is bit-exact; intensity goes through powf (<= a few ulp per bounce)
+    assert np.array_equal(sg[:, :6].view(np.uint32), s_c[:, :6].view(np.uint32))
+    assert np.allclose(sg[:, 6], s_c[:, 6], rtol=1e-4, atol=0)
+    assert np.array_equal(sg[:, 7].view(np.uint32), s_c[:, 7].view(np.uint32))
+
+
+def _compare_tracks(res, tracks):
+    worst = 0.0
+    for c in range(len(tracks)):
+        for r in range(len(tracks[c])):
+            for k in range(len(tracks[c][r])):
+                a, b = res.tracks[c][r][k], tracks[c][r][k]
+                assert (a.first_sample, a.real_length) == (b.first_sample, b.real_length)
+                n = b.real_length + 1
+                scale = np.abs(b.data[:n]).max()
+                err = np.abs(a.data[:n].astype(np.float64) - b.data[:n]).max() / scale
+                worst = max(worst, err)
+                assert not a.data[n:].any()
+    return worst
+
+
+@pytest.mark.parametrize("name,stereo", [("rt60", False), ("rt60", True), ("example1", True), ("soup", False)])
+def test_histograms_match_oracle(ob, name, stereo):
+    sc = common.named_scene(name)
+    sc.samples = 20000
+    for rec in sc.recorders:
+        rec.stereo = stereo
+    gpu, cpu = _pair(ob, sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    res = gpu.render(ctxs, recs, max_bounces=120, seed=5)
+    tracks, cnt = cpu.render(ctxs, recs, max_bounces=120, seed=5)
+    assert res.rays == cnt["rays"] and res.segments == cnt["segments"]
+    assert res.occlusion_queries == cnt["occlusion_queries"]
+    assert abs(res.contributions - cnt["contributions"]) <= max(2, cnt["contributions"] // 100000)
+    assert res.dropped_updates == 0
+    assert _compare_tracks(res, tracks) < REL_TOL
+
+
+def test_multiple_recorders_and_raw_shards_add_up(ob):
+    """Two ray shards traced without finalise sum to the unsharded raw histogram (the multi-GPU
+    contract: partial sums, one reduce, then finalise)."""
+    sc = common.named_scene("example1")
+    sc.samples = 8000
+    sc.recorders.append(type(sc.recorders[0])("/tmp/b.wav", position=(-8.0, 3.0, 2.0)))
+    gpu, cpu = _pair(ob, sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    full = gpu.render(ctxs, recs, max_bounces=60, seed=2, finalise=False)
+    a = gpu.render(ctxs, recs, max_bounces=60, seed=2, finalise=False, first_ray=0, ray_count=300)
+    b = gpu.render(ctxs, recs, max_bounces=60, seed=2, finalise=False, first_ray=300, ray_count=500)
+    assert a.rays + b.rays == full.rays and a.segments + b.segments == full.segments
+    for c in range(len(ctxs)):
+        for r in range(2):
+            for k in range(2):
+                s = a.tracks[c][r][k].data.astype(np.float64) + b.tracks[c][r][k].data
+                f = full.tracks[c][r][k].data
+                assert np.abs(s - f).max() <= 1e-4 * np.abs(f).max()
+                assert min(a.tracks[c][r][k].first_sample, b.tracks[c][r][k].first_sample) == full.tracks[c][r][k].first_sample
+                assert max(a.tracks[c][r][k].real_length, b.tracks[c][r][k].real_length) == full.tracks[c][r][k].real_length
+    tracks, _ = cpu.render(ctxs, recs, max_bounces=60, seed=2, finalise=False)
+    assert _compare_tracks(full, tracks) < REL_TOL
+
+
+def test_errors_are_reported_not_swallowed():
+    sc = common.named_scene("rt60")
+    gpu = api.Scene.from_def(sc)
+    with pytest.raises(api.EarError):
+        gpu.render([api.Context(7, 10, 1.0, (0, 0, 1))], [api.Recorder((1, 0, 1))])   # band outside the table
+    with pytest.raises(api.EarError):
+        api.Scene(sc.triangles(), np.full(12, 3, np.int32), sc.material_table())       # bad material index
