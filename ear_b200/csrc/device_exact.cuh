@@ -53,6 +53,18 @@ __device__ __forceinline__ bool invalid_float(float x) {
 	return e == 0u || e == 0xffu;
 }
 
+// powf as the reference's libm computes it (glibc powf is exp2(y*log2 x) in double, rounded once:
+// <= 0.52 ulp, subnormal results kept).  CUDA's own powf flushes subnormal results to zero, which
+// changes the FP_NORMAL classification of tiny contributions (src/Scene.cpp:254), so the same
+// double-precision route is taken here; the result equals glibc's except when the exact value sits
+// within ~1e-13 (relative) of a float32 rounding boundary.
+#ifndef EARB_HOST_EMULATION
+__device__ __forceinline__ float pow_ref(float x, float y) {
+	if (y == 0.0f || x == 1.0f) return 1.0f;
+	return __double2float_rn(exp2((double)y * log2((double)x)));
+}
+#endif
+
 // gmtl::intersectDoubleSided (Moeller-Trumbore, non-culling, EPSILON 1e-5; src/Mesh.cpp:40,65)
 // with e1 = v1 - v0 and e2 = v2 - v0 precomputed in float32 (same values the reference forms).
 __device__ __forceinline__ bool moeller_trumbore(V3 v0, V3 e1, V3 e2, V3 o, V3 d, float& t) {

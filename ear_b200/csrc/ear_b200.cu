@@ -99,7 +99,7 @@ __device__ __forceinline__ void record(const ear_b200_recorder& rec, float* trac
 		const int s_right = __double2int_rz((double)fsub(t, fmul(dt, time_difference)) * 44100.0);
 		const int s_left = __double2int_rz((double)fadd(t, fmul(dt, time_difference)) * 44100.0);
 		float ampl_left = ampl, ampl_right = ampl;
-		const float factor = powf(rec.head_absorption[band], fmul(fabsf(dt), rec.head_size));
+		const float factor = pow_ref(rec.head_absorption[band], fmul(fabsf(dt), rec.head_size));
 		if (dt < 0) ampl_right = fmul(ampl_right, fmul(factor, factor));
 		else ampl_left = fmul(ampl_left, fmul(factor, factor));
 		splat_ramp(tracks, range, n_bins, s_left, w, ampl_left, fdiv(ampl_left, (float)w), lc);
@@ -149,7 +149,7 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const RenderParams
 		if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
 		else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
 		const float seg = vlength(vsub(pnt, o));
-		intensity = fmul(intensity, powf(af, seg));                                         // src/Scene.cpp:154
+		intensity = fmul(intensity, pow_ref(af, seg));                                         // src/Scene.cpp:154
 		path = fadd(path, seg);
 		o = pnt; d = v;
 		intensity = fmul(intensity, m.z);                                                   // :169-171
@@ -170,16 +170,16 @@ __device__ __forceinline__ void trace_ray(const SceneDev& sc, const RenderParams
 					const float diff = -vdot(n, prev_dir);
 					const float dsp = vdot(rv, lsdir);
 					const float specf = (0.0f < dsp) ? dsp : 0.0f;
-					factor = fadd(fmul(fmul(spec, 1001.0f), powf(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+					factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
 				} else {                                                                    // :236-247
 					const float diff = vdot(n, prev_dir);
 					const float dsp = vdot(prev_dir, lsdir);
 					const float specf = (0.0f < dsp) ? dsp : 0.0f;
-					factor = fadd(fmul(fmul(spec, 1001.0f), powf(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+					factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
 				}
 				float contrib = fmul(intensity, factor);
 				const float l = vlength(segv);                                              // :250
-				contrib = fmul(contrib, powf(af, l));
+				contrib = fmul(contrib, pow_ref(af, l));
 				contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
 				if (invalid_float(contrib)) continue;
 				if (b & 1) contrib = fmul(contrib, -1.0f);                                  // :257
@@ -293,11 +293,15 @@ __global__ void direct_kernel(SceneDev sc, RenderParams p) {
 	const V3 dist = vsub(listener, source);
 	const float len = vlength(dist);
 	const V3 dir = vnormalized(dist);
-	const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), powf(cx.absorption_factor, len)),
+	const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), pow_ref(cx.absorption_factor, len)),
 	                     cx.dry_level);
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
 	record(rec, p.hist + (size_t)i * 2 * p.n_bins, p.range + (size_t)i * 4, p.n_bins, dir, a, fdiv(len, 343.0f), len,
 	       cx.band, lc);
+	if (p.counters) {   // the direct lobe is a Record() call like any other (src/Scene.cpp:308)
+		atomicAdd(p.counters + 3, lc.contributions); atomicAdd(p.counters + 4, lc.bin_updates);
+		atomicAdd(p.counters + 5, lc.dropped);
+	}
 }
 __global__ void init_range_kernel(uint32_t* range, int n_tracks) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -103,7 +103,7 @@ def test_histograms_match_oracle(ob, name, stereo):
     tracks, cnt = cpu.render(ctxs, recs, max_bounces=120, seed=5)
     assert res.rays == cnt["rays"] and res.segments == cnt["segments"]
     assert res.occlusion_queries == cnt["occlusion_queries"]
-    assert abs(res.contributions - cnt["contributions"]) <= max(2, cnt["contributions"] // 100000)
+    assert res.contributions == cnt["contributions"] and res.bin_updates == cnt["bin_updates"]
     assert res.dropped_updates == 0
     assert _compare_tracks(res, tracks) < REL_TOL
 
