@@ -105,6 +105,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from ear_b200 import api
+    from ear_b200.sharding import reduce_partials, shard_bounds
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -124,8 +125,7 @@ def run_ours(args):
     ctx_c = api.pack_contexts(ctxs)
     rec_c, _ = api.pack_recorders(recs, n_ctx)
     rays_per_ctx = ctxs[0].num_samples
-    lo = rays_per_ctx * rank // world
-    hi = rays_per_ctx * (rank + 1) // world
+    lo, hi = shard_bounds(rays_per_ctx, rank, world)
     opt = api.make_options(max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo, finalise=False)
     n_bins = scene.default_bins(opt)
     n_tracks = n_ctx * n_rec * 2
@@ -156,10 +156,8 @@ def run_ours(args):
         launches[0] += 1
         if world > 1:
             # one reduce of the partial histograms over NVLink; track ranges reduce by min / max
-            dist.reduce(hist, dst=0, op=dist.ReduceOp.SUM)
             rng_first.copy_(rng[:, 0]); rng_real.copy_(rng[:, 1])
-            dist.reduce(rng_first, dst=0, op=dist.ReduceOp.MIN)
-            dist.reduce(rng_real, dst=0, op=dist.ReduceOp.MAX)
+            reduce_partials(hist, rng_first, rng_real, dst=0)
             rng[:, 0] = rng_first; rng[:, 1] = rng_real
         if rank == 0:
             api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,

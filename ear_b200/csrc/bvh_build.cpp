@@ -179,12 +179,14 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 		out.lo[i] = scene.lo[i]; out.hi[i] = scene.hi[i];
 	}
 	out.diagonal = std::sqrt(diag2);
+	out.s0 = 0.0f;
 	const float eps = 5.9604645e-8f;                  // 2^-24
 	// test knob: scales pad and slack (0 = bare boxes) so the parity tests can show that the
 	// adversarial ray set actually needs them; the product never sets it
 	const char* knob = std::getenv("EAR_B200_BVH_MARGIN_SCALE");
 	const float margin_scale = knob ? (float)std::atof(knob) : 1.0f;
 	const float reach = 2.0f * out.diagonal + 1.0f;   // ray origins may sit outside the bounds
+	out.s0 = margin_scale * 64.0f * eps * (maxabs + reach);
 	b.tri_box.resize(n); b.centroid.resize(3 * (size_t)n); b.tri_slack.resize(n); b.order.resize(n);
 	for (int32_t i = 0; i < n; ++i) {
 		const float* p = verts + 9 * (size_t)i;
@@ -220,7 +222,15 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 		const float* p = verts + 9 * (size_t)t;
 		TriRecord& r = out.tris[i];
 		for (int k = 0; k < 3; ++k) { r.v0[k] = p[k]; r.e1[k] = p[3 + k] - p[k]; r.e2[k] = p[6 + k] - p[k]; }
-		r.index = t; r.material = tri_material ? tri_material[t] : 0; r.pad = 0;
+		r.index = t; r.material = tri_material ? tri_material[t] : 0; r.pad0 = 0; r.pad1 = 0;
+		// gmtl::normal(tri): cross, length, divide each component (no FMA: see the build flags)
+		const float cx = (r.e1[1] * r.e2[2]) - (r.e1[2] * r.e2[1]);
+		const float cy = (r.e1[2] * r.e2[0]) - (r.e1[0] * r.e2[2]);
+		const float cz = (r.e1[0] * r.e2[1]) - (r.e1[1] * r.e2[0]);
+		float l2 = cx * cx; l2 = l2 + cy * cy; l2 = l2 + cz * cz;
+		const float len = std::sqrt(l2);
+		r.normal[0] = cx; r.normal[1] = cy; r.normal[2] = cz;
+		if (len != 0.0f) { r.normal[0] = cx / len; r.normal[1] = cy / len; r.normal[2] = cz / len; }
 	}
 
 	// re-layout: depth-first, internal nodes only (leaves are folded into their parent's child slot)

@@ -21,15 +21,18 @@ struct Node {
 };
 static_assert(sizeof(Node) == 64, "node must be 64 bytes");
 
-// Triangle record in leaf order (48 bytes, three float4 loads):
-//   (v0.xyz, original index) (e1.xyz, material) (e2.xyz, 0)    e1 = v1 - v0, e2 = v2 - v0 in float32,
-// exactly the edge vectors gmtl::intersectDoubleSided forms per test.
+// Triangle record in leaf order (64 bytes):
+//   (v0.xyz, original index) (e1.xyz, material) (e2.xyz, 0) (unit normal, 0)
+// e1 = v1 - v0, e2 = v2 - v0 in float32, exactly the edge vectors gmtl::intersectDoubleSided forms
+// per test; normal = normalize(e1 x e2) in the reference's float32 order (Triangle ctor,
+// src/Triangle.cpp:41) -- this file must be compiled without FMA contraction.
 struct TriRecord {
 	float v0[3]; int32_t index;
 	float e1[3]; int32_t material;
-	float e2[3]; int32_t pad;
+	float e2[3]; int32_t pad0;
+	float normal[3]; int32_t pad1;
 };
-static_assert(sizeof(TriRecord) == 48, "triangle record must be 48 bytes");
+static_assert(sizeof(TriRecord) == 64, "triangle record must be 64 bytes");
 
 constexpr int32_t kEmptyChild = 0x7fffffff;
 constexpr int kMaxLeaf = 4;
@@ -39,6 +42,7 @@ struct Bvh {
 	std::vector<TriRecord> tris;     // leaf order
 	float lo[3], hi[3];              // scene bounds (unpadded)
 	float diagonal;
+	float s0;                        // absolute ray-interval margin used with the relative slack
 	int depth;
 };
 

@@ -110,119 +110,185 @@ __device__ __forceinline__ void record(const ear_b200_recorder& rec, float* trac
 	}
 }
 
-// One ray of Scene::Render's outer loop (src/Scene.cpp:131-284).  PATHS = true logs the triangle
-// hit at each bounce instead of recording (parity harness).
-template <bool PATHS>
-__device__ __forceinline__ void trace_ray(const SceneDev& sc, const RenderParams& p, int c, unsigned long long ray,
-                                          LocalCounters& lc, int32_t* hits, float* final_state) {
-	const ear_b200_context cx = p.ctx[c];
-	const int band = cx.band;
-	const float af = cx.absorption_factor;
-	Rng rng;
-	rng.start(p.seed, (uint32_t)c, ray);
-	++lc.rays;
-	float intensity = 1.0f, path = 0.0f;
-	// AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226)
-	V3 o = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
-	V3 d = sample_sphere(rng);
-	V3 prev_dir = vnormalized(d);  // bounce 0 ends with prev_ray_dir = normalize(dir) (src/Scene.cpp:277)
-	// bounce 0: intensity = 1 is FP_NORMAL and >= 1e-8, nothing is recorded for point sources (:185)
-	for (int b = 1; b < p.max_bounces; ++b) {
-		// ---- Scene::Bounce (src/Scene.cpp:49-82) ----
-		++lc.segments;
-		float t; int32_t slot;
-		const int32_t idx = traverse<false>(sc, o, d, t, slot);
-		if (PATHS) hits[b] = idx;
-		if (idx < 0) break;
-		const float4 r1 = __ldg(sc.tris + 3 * (size_t)slot + 1);
-		const float4 r2 = __ldg(sc.tris + 3 * (size_t)slot + 2);
-		const V3 tri_n = vnormalized(vcross(mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z)));  // src/Triangle.cpp:41
-		const V3 pnt = vadd(o, vscale(d, t));                                              // src/Mesh.cpp:48
-		V3 n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;                      // :49-53
-		const float4 m = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
-		// Material::Bounce (src/Material.cpp:76-83); comparisons against 0.0001 are in double there
-		bool refract;
-		if ((double)m.x < 0.0001 && (double)m.y < 0.0001) refract = false;
-		else refract = !(rng.unit() <= fdiv(m.x, fadd(m.x, m.y)));
-		const float spec = m.w;
-		V3 v;
-		if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
-		else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
-		const float seg = vlength(vsub(pnt, o));
-		intensity = fmul(intensity, pow_ref(af, seg));                                         // src/Scene.cpp:154
-		path = fadd(path, seg);
-		o = pnt; d = v;
-		intensity = fmul(intensity, m.z);                                                   // :169-171
-		if (invalid_float(intensity)) break;                                                // :175
-		if (!PATHS) {
-			for (int r = 0; r < p.n_rec; ++r) {
-				const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
-				const V3 x = mk(rec.position[0], rec.position[1], rec.position[2]);
-				const V3 segv = vsub(x, o);   // LineSeg(p, x) = Ray(p, x - p)
-				++lc.occlusion;
-				float tt; int32_t ss;
-				if (traverse<true>(sc, o, segv, tt, ss)) continue;                          // :194-197
-				const V3 lsdir = vnormalized(segv);
-				if (!(vdot(lsdir, n) > 0.0f)) continue;                                     // :205-209
-				float factor;
-				if (!refract) {                                                             // :219-235
-					const V3 rv = vreflect(prev_dir, n);
-					const float diff = -vdot(n, prev_dir);
-					const float dsp = vdot(rv, lsdir);
-					const float specf = (0.0f < dsp) ? dsp : 0.0f;
-					factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
-				} else {                                                                    // :236-247
-					const float diff = vdot(n, prev_dir);
-					const float dsp = vdot(prev_dir, lsdir);
-					const float specf = (0.0f < dsp) ? dsp : 0.0f;
-					factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
-				}
-				float contrib = fmul(intensity, factor);
-				const float l = vlength(segv);                                              // :250
-				contrib = fmul(contrib, pow_ref(af, l));
-				contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
-				if (invalid_float(contrib)) continue;
-				if (b & 1) contrib = fmul(contrib, -1.0f);                                  // :257
-				const size_t slot2 = ((size_t)c * p.n_rec + r) * 2;
-				record(rec, p.hist + slot2 * p.n_bins, p.range + slot2 * 2, p.n_bins, lsdir, contrib,
-				       fdiv(fadd(path, l), 343.0f), fadd(path, l), band, lc);
-			}
-		}
-		if ((double)intensity < 0.00000001) break;                                          // :275
-		prev_dir = vnormalized(d);                                                          // :277
-	}
-	if (PATHS && final_state) {
-		final_state[0] = o.x; final_state[1] = o.y; final_state[2] = o.z;
-		final_state[3] = d.x; final_state[4] = d.y; final_state[5] = d.z;
-		final_state[6] = intensity; final_state[7] = path;
-	}
-}
-
 __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 	return v;
 }
 
-// Persistent kernel: each warp pulls 32 ray ids at a time from a global queue (K6: dead lanes are
-// refilled at warp granularity), maps them to (context, ray) and runs the bounce loop.
-__global__ void __launch_bounds__(128) render_kernel(SceneDev sc, RenderParams p) {
+constexpr int kBlock = 128;
+
+// The bounce loop of Scene::Render (src/Scene.cpp:124-284), one ray per lane, warp-synchronous.
+// Every iteration of the outer loop advances every live lane by exactly one bounce:
+//   K6 refill    dead lanes take fresh ray ids (one ballot + one queue atomic per warp, ranks by popc)
+//   K2 closest   Scene::Bounce -> Mesh::RayIntersection            (traverse_warp<false>)
+//   K3 shade     Material::Bounce, reflect, Sample_Hemi, air + surface absorption
+//   K4 occlusion Scene::Connect per recorder                        (traverse_warp<true>)
+//   K5 splat     contribution weight + Recorder::Record
+// so lanes of one warp may be at different bounce numbers of different rays (even of different
+// contexts) but always in the same phase.  PATHS = true replays explicit ray ids and logs the
+// triangle hit at each bounce instead of recording (parity harness).
+template <bool PATHS, bool EXACT>
+__device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderParams& p, int2* stack, int stride,
+                                            LocalCounters& lc, int paths_ctx, long long paths_n, int32_t* hits,
+                                            float* final_state) {
 	const int lane = threadIdx.x & 31;
-	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	const unsigned lt_mask = (1u << lane) - 1u;
+	bool alive = false, queue_empty = false, has_ray = false;
+	int c = 0, b = 1;
+	long long ray_slot = 0;   // PATHS: index of this lane's ray in the output arrays
+	V3 o = mk(0, 0, 0), d = mk(0, 0, 0), prev_dir = mk(0, 0, 0);
+	float intensity = 1.0f, path = 0.0f, af = 1.0f;
+	int band = 0;
+	Rng rng;
+	rng.start(0, 0, 0);
 	for (;;) {
-		unsigned long long base = 0;
-		if (lane == 0) base = atomicAdd(p.next_work, 32ull);
-		base = __shfl_sync(0xffffffffu, base, 0);
-		if ((long long)base >= p.total_work) break;
-		const long long w = (long long)base + lane;
-		if (w < p.total_work) {
-			int c = 0;
-			while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
-			const unsigned long long ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
-			trace_ray<false>(sc, p, c, ray, lc, nullptr, nullptr);
+		// ---------------- K6: refill dead lanes ----------------
+		const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+		if (dead != 0u && !queue_empty) {
+			const int want = __popc(dead);
+			long long base = 0;
+			if (PATHS) {
+				// harness: thread i owns ray i, handed out once
+				base = (long long)(blockIdx.x * blockDim.x + (threadIdx.x & ~31));
+				queue_empty = true;
+			} else {
+				if (lane == 0) base = (long long)atomicAdd(p.next_work, (unsigned long long)want);
+				base = __shfl_sync(0xffffffffu, base, 0);
+				if (base + want >= p.total_work) queue_empty = true;
+			}
+			const long long w = PATHS ? base + lane : base + __popc(dead & lt_mask);
+			const long long limit = PATHS ? paths_n : p.total_work;
+			if (!alive && w < limit) {
+				unsigned long long ray;
+				if (PATHS) { c = paths_ctx; ray = (unsigned long long)(p.first_ray + w); ray_slot = w; }
+				else {
+					c = 0;
+					while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
+					ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
+				}
+				band = p.ctx[c].band;
+				af = p.ctx[c].absorption_factor;
+				rng.start(p.seed, (uint32_t)c, ray);
+				++lc.rays;
+				// bounce 0: AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226); intensity 1 is
+				// FP_NORMAL and >= 1e-8 and nothing is recorded for point sources (src/Scene.cpp:185), so the
+				// iteration only leaves prev_ray_dir = normalize(dir) behind (:277)
+				o = mk(p.ctx[c].source_position[0], p.ctx[c].source_position[1], p.ctx[c].source_position[2]);
+				d = sample_sphere(rng);
+				prev_dir = vnormalized(d);
+				intensity = 1.0f; path = 0.0f; b = 1;
+				alive = b < p.max_bounces;
+				has_ray = true;
+				if (PATHS && !alive && final_state) {
+					float* fs = final_state + 8 * ray_slot;
+					fs[0] = o.x; fs[1] = o.y; fs[2] = o.z; fs[3] = d.x; fs[4] = d.y; fs[5] = d.z; fs[6] = intensity; fs[7] = path;
+				}
+			}
 		}
 		__syncwarp();
+		if (!__any_sync(0xffffffffu, alive)) break;
+
+		// ---------------- K2: Scene::Bounce -> closest hit (src/Scene.cpp:49-58) ----------------
+		float t; int32_t idx, slot;
+		traverse_warp<false, EXACT>(sc, stack, stride, alive, o, d, t, idx, slot);
+		bool shade = alive && idx >= 0;
+		bool refract = false;
+		float spec = 0.0f;
+		V3 n = mk(0, 0, 0);
+		if (alive) {
+			++lc.segments;
+			if (PATHS) hits[ray_slot * p.max_bounces + b] = idx;
+			if (idx < 0) alive = false;
+		}
+		// ---------------- K3: material + resample (src/Scene.cpp:60-82, 154-175) ----------------
+		if (shade) {
+			const float4 r1 = __ldg(sc.tris + 4 * (size_t)slot + 1);
+			const float4 r3 = __ldg(sc.tris + 4 * (size_t)slot + 3);
+			const V3 tri_n = mk(r3.x, r3.y, r3.z);                                       // Triangle::normal
+			const V3 pnt = vadd(o, vscale(d, t));                                        // src/Mesh.cpp:48
+			n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;                  // :49-53
+			const float4 m = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
+			// Material::Bounce (src/Material.cpp:76-83); its comparisons against 0.0001 are in double
+			if ((double)m.x < 0.0001 && (double)m.y < 0.0001) refract = false;
+			else refract = !(rng.unit() <= fdiv(m.x, fadd(m.x, m.y)));
+			spec = m.w;
+			V3 v;
+			if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
+			else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
+			const float seg = vlength(vsub(pnt, o));
+			intensity = fmul(intensity, pow_ref(af, seg));                               // src/Scene.cpp:154
+			path = fadd(path, seg);
+			o = pnt; d = v;
+			intensity = fmul(intensity, m.z);                                            // :169-171
+			if (invalid_float(intensity)) { alive = false; shade = false; }              // :175
+		}
+		__syncwarp();
+		// ---------------- K4 + K5: connect to every recorder, weight, splat (src/Scene.cpp:185-268) ----------------
+		if (!PATHS) {
+			for (int r = 0; r < p.n_rec; ++r) {
+				const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
+				const V3 x = mk(rec.position[0], rec.position[1], rec.position[2]);
+				const V3 segv = vsub(x, o);   // LineSeg(p, x) = Ray(p, x - p)
+				float tt; int32_t occluded, ss;
+				traverse_warp<true, EXACT>(sc, stack, stride, shade, o, segv, tt, occluded, ss);
+				if (shade) {
+					++lc.occlusion;
+					const V3 lsdir = vnormalized(segv);
+					if (!occluded && vdot(lsdir, n) > 0.0f) {                                // :197-209
+						float factor;
+						if (!refract) {                                                      // :219-235
+							const V3 rv = vreflect(prev_dir, n);
+							const float diff = -vdot(n, prev_dir);
+							const float dsp = vdot(rv, lsdir);
+							const float specf = (0.0f < dsp) ? dsp : 0.0f;
+							factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+						} else {                                                             // :236-247
+							const float diff = vdot(n, prev_dir);
+							const float dsp = vdot(prev_dir, lsdir);
+							const float specf = (0.0f < dsp) ? dsp : 0.0f;
+							factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+						}
+						float contrib = fmul(intensity, factor);
+						const float l = vlength(segv);                                       // :250
+						contrib = fmul(contrib, pow_ref(af, l));
+						contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));   // INV_HEMI_2, :252
+						if (!invalid_float(contrib)) {
+							if (b & 1) contrib = fmul(contrib, -1.0f);                       // :257
+							const size_t slot2 = ((size_t)c * p.n_rec + r) * 2;
+							record(rec, p.hist + slot2 * p.n_bins, p.range + slot2 * 2, p.n_bins, lsdir, contrib,
+							       fdiv(fadd(path, l), 343.0f), fadd(path, l), band, lc);
+						}
+					}
+				}
+				__syncwarp();
+			}
+		}
+		// ---------------- end of this bounce (src/Scene.cpp:275-277) ----------------
+		if (shade) {
+			if ((double)intensity < 0.00000001) alive = false;
+			else {
+				prev_dir = vnormalized(d);
+				++b;
+				if (b >= p.max_bounces) alive = false;
+			}
+		}
+		if (PATHS && final_state && has_ray && !alive) {
+			// a finished ray writes its last state once (later iterations see alive == false and ray_slot unchanged,
+			// rewriting the same values is harmless)
+			float* fs = final_state + 8 * ray_slot;
+			if (ray_slot < paths_n) { fs[0] = o.x; fs[1] = o.y; fs[2] = o.z; fs[3] = d.x; fs[4] = d.y; fs[5] = d.z; fs[6] = intensity; fs[7] = path; }
+		}
 	}
+}
+
+// Persistent kernel: grid = SMs x resident blocks; warps pull ray ids from a global queue until it is dry.
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) render_kernel(SceneDev sc, RenderParams p) {
+	extern __shared__ int2 stack_smem[];
+	const int lane = threadIdx.x & 31;
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	bounce_loop<false, EXACT>(sc, p, stack_smem + threadIdx.x, blockDim.x, lc, 0, 0, nullptr, nullptr);
 	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
 	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
 	if (lane == 0) {
@@ -231,33 +297,40 @@ __global__ void __launch_bounds__(128) render_kernel(SceneDev sc, RenderParams p
 	}
 }
 
-__global__ void paths_kernel(SceneDev sc, RenderParams p, int c, long long n, int32_t* hits, float* final_state) {
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) paths_kernel(SceneDev sc, RenderParams p, int c, long long n, int32_t* hits, float* final_state) {
+	extern __shared__ int2 stack_smem[];
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
+	if (i < n) for (int b = 0; b < p.max_bounces; ++b) hits[(size_t)i * p.max_bounces + b] = -2;
+	__syncwarp();
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	int32_t* h = hits + (size_t)i * p.max_bounces;
-	for (int b = 0; b < p.max_bounces; ++b) h[b] = -2;
-	trace_ray<true>(sc, p, c, (unsigned long long)(p.first_ray + i), lc, h, final_state + 8 * (size_t)i);
+	bounce_loop<true, EXACT>(sc, p, stack_smem + threadIdx.x, blockDim.x, lc, c, n, hits, final_state);
 }
 
-__global__ void first_hit_kernel(SceneDev sc, const float* origins, const float* dirs, long long n, int32_t* tri_index,
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) first_hit_kernel(SceneDev sc, const float* origins, const float* dirs, long long n, int32_t* tri_index,
                                  float* t_out) {
+	extern __shared__ int2 stack_smem[];
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	float t; int32_t slot;
-	const int32_t idx = traverse<false>(sc, mk(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2]),
-	                                    mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), t, slot);
-	tri_index[i] = idx;
-	t_out[i] = t;
+	const bool active = i < n;
+	const long long j = active ? i : 0;
+	float t; int32_t idx, slot;
+	traverse_warp<false, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, mk(origins[3 * j], origins[3 * j + 1], origins[3 * j + 2]),
+	                            mk(dirs[3 * j], dirs[3 * j + 1], dirs[3 * j + 2]), t, idx, slot);
+	if (active) { tri_index[i] = idx; t_out[i] = t; }
 }
 
-__global__ void occluded_kernel(SceneDev sc, const float* pp, const float* xx, long long n, uint8_t* out) {
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) occluded_kernel(SceneDev sc, const float* pp, const float* xx, long long n, uint8_t* out) {
+	extern __shared__ int2 stack_smem[];
 	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) return;
-	const V3 p = mk(pp[3 * i], pp[3 * i + 1], pp[3 * i + 2]);
-	const V3 x = mk(xx[3 * i], xx[3 * i + 1], xx[3 * i + 2]);
-	float t; int32_t slot;
-	out[i] = (uint8_t)traverse<true>(sc, p, vsub(x, p), t, slot);
+	const bool active = i < n;
+	const long long j = active ? i : 0;
+	const V3 p = mk(pp[3 * j], pp[3 * j + 1], pp[3 * j + 2]);
+	const V3 x = mk(xx[3 * j], xx[3 * j + 1], xx[3 * j + 2]);
+	float t; int32_t occ, slot;
+	traverse_warp<true, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, p, vsub(x, p), t, occ, slot);
+	if (active) out[i] = (uint8_t)occ;
 }
 
 // ---- K7: Scene::Render's tail, src/Scene.cpp:286-316 ----
@@ -279,24 +352,28 @@ __global__ void scale_kernel(RenderParams p, int mode) {
 	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < real; i += gridDim.x * blockDim.x)
 		tr[i] = fmul(tr[i], f);
 }
-// Direct sound (src/Scene.cpp:299-311): one thread per (context, recorder).
-__global__ void direct_kernel(SceneDev sc, RenderParams p) {
+// Direct sound (src/Scene.cpp:299-311): one lane per (context, recorder).
+template <bool EXACT>
+__global__ void __launch_bounds__(kBlock) direct_kernel(SceneDev sc, RenderParams p) {
+	extern __shared__ int2 stack_smem[];
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= p.n_ctx * p.n_rec) return;
-	const int c = i / p.n_rec;
+	const bool active = i < p.n_ctx * p.n_rec;
+	const int j = active ? i : 0;
+	const int c = j / p.n_rec;
 	const ear_b200_context cx = p.ctx[c];
-	const ear_b200_recorder& rec = p.rec[i];
+	const ear_b200_recorder& rec = p.rec[j];
 	const V3 listener = mk(rec.position[0], rec.position[1], rec.position[2]);
 	const V3 source = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
-	float t; int32_t slot;
-	if (traverse<true>(sc, listener, vsub(source, listener), t, slot)) return;
+	float t; int32_t occ, slot;
+	traverse_warp<true, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, listener, vsub(source, listener), t, occ, slot);
+	if (!active || occ) return;
 	const V3 dist = vsub(listener, source);
 	const float len = vlength(dist);
 	const V3 dir = vnormalized(dist);
 	const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), pow_ref(cx.absorption_factor, len)),
 	                     cx.dry_level);
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	record(rec, p.hist + (size_t)i * 2 * p.n_bins, p.range + (size_t)i * 4, p.n_bins, dir, a, fdiv(len, 343.0f), len,
+	record(rec, p.hist + (size_t)j * 2 * p.n_bins, p.range + (size_t)j * 4, p.n_bins, dir, a, fdiv(len, 343.0f), len,
 	       cx.band, lc);
 	if (p.counters) {   // the direct lobe is a Record() call like any other (src/Scene.cpp:308)
 		atomicAdd(p.counters + 3, lc.contributions); atomicAdd(p.counters + 4, lc.bin_updates);
@@ -307,6 +384,8 @@ __global__ void init_range_kernel(uint32_t* range, int n_tracks) {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n_tracks) { range[2 * i] = 3 * EAR_B200_SAMPLE_RATE - 1; range[2 * i + 1] = 0; }
 }
+
+constexpr size_t kStackBytes = (size_t)kStackEntries * kBlock * sizeof(int2);
 
 // ------------------------------------------------------------------------------------------
 // host side
@@ -378,6 +457,10 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	CUDA_TRY(cudaMalloc(&s->d_queue, sizeof(unsigned long long)));
 	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
 	s->dev.n_tris = n_tris; s->dev.n_materials = n_materials; s->dev.n_bands = n_bands;
+	s->dev.s0 = bvh.s0;
+	// EAR_B200_EXACT_SLACK=1 selects the rigorous per-child interval bound (about 2x the node visits)
+	const char* ex = std::getenv("EAR_B200_EXACT_SLACK");
+	s->dev.exact = (ex && std::atoi(ex) != 0) ? 1 : 0;
 	*out = s;
 	return 0;
 }
@@ -401,7 +484,8 @@ extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, c
 	CUDA_TRY(cudaMalloc(&d_t, n * 4)); CUDA_TRY(cudaMalloc(&d_i, n * 4));
 	CUDA_TRY(cudaMemcpyAsync(d_o, origins, n * 12, cudaMemcpyHostToDevice, s->stream));
 	CUDA_TRY(cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, s->stream));
-	first_hit_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
+	if (s->dev.exact) first_hit_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
+	else first_hit_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(tri_index, d_i, n * 4, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -418,7 +502,8 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p, const fl
 	CUDA_TRY(cudaMalloc(&d_p, n * 12)); CUDA_TRY(cudaMalloc(&d_x, n * 12)); CUDA_TRY(cudaMalloc(&d_out, n));
 	CUDA_TRY(cudaMemcpyAsync(d_p, p, n * 12, cudaMemcpyHostToDevice, s->stream));
 	CUDA_TRY(cudaMemcpyAsync(d_x, x, n * 12, cudaMemcpyHostToDevice, s->stream));
-	occluded_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s->stream>>>(s->dev, d_p, d_x, n, d_out);
+	if (s->dev.exact) occluded_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, n, d_out);
+	else occluded_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, n, d_out);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -492,10 +577,12 @@ static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t str
 	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
 	if (p.total_work > 0) {
 		int blocks_per_sm = 0;
-		CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel, 128, 0));
-		const long long want = (p.total_work + 127) / 128;
+		if (s->dev.exact) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel<true>, kBlock, kStackBytes));
+		else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel<false>, kBlock, kStackBytes));
+		const long long want = (p.total_work + kBlock - 1) / kBlock;
 		const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)s->sm_count * std::max(1, blocks_per_sm)));
-		render_kernel<<<grid, 128, 0, stream>>>(s->dev, p);
+		if (s->dev.exact) render_kernel<true><<<grid, kBlock, kStackBytes, stream>>>(s->dev, p);
+		else render_kernel<false><<<grid, kBlock, kStackBytes, stream>>>(s->dev, p);
 		CUDA_TRY(cudaGetLastError());
 	}
 	return 0;
@@ -505,7 +592,8 @@ static int32_t launch_finalise(ear_b200_scene* s, RenderParams& p, cudaStream_t 
 	const int n_tracks = p.n_ctx * p.n_rec * 2;
 	dim3 grid(64, n_tracks);
 	scale_kernel<<<grid, 256, 0, stream>>>(p, 0);
-	direct_kernel<<<(p.n_ctx * p.n_rec + 63) / 64, 64, 0, stream>>>(s->dev, p);
+	if (s->dev.exact) direct_kernel<true><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
+	else direct_kernel<false><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
 	scale_kernel<<<grid, 256, 0, stream>>>(p, 1);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
@@ -617,7 +705,8 @@ extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_contex
 	int32_t* d_hits = nullptr; float* d_state = nullptr;
 	CUDA_TRY(cudaMalloc(&d_hits, (size_t)n * max_b * 4)); CUDA_TRY(cudaMalloc(&d_state, (size_t)n * 32));
 	CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)n * 32, s->stream));
-	paths_kernel<<<(unsigned)((n + 63) / 64), 64, 0, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+	if (s->dev.exact) paths_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+	else paths_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(hits, d_hits, (size_t)n * max_b * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (final_state) CUDA_TRY(cudaMemcpyAsync(final_state, d_state, (size_t)n * 32, cudaMemcpyDeviceToHost, s->stream));

@@ -1,11 +1,21 @@
 // BVH traversal: closest hit (K2, replaces Mesh::RayIntersection, src/Mesh.cpp:33-56) and any hit
 // (K4, replaces Scene::Connect / Mesh::LineIntersection, src/Scene.cpp:84-96, src/Mesh.cpp:58-71).
 //
-// One ray per thread, while-while loop, short stack in registers/local memory.  Nodes are 64 B
-// (both children's boxes, four 16-byte read-only loads), triangle records 48 B (three loads); the
-// whole structure of the 1M-triangle hall (~80 MB) is L2-resident on B200 (126 MB).
-// Box tests use FMA and are conservative (padded boxes + per-child interval slack, see
-// bvh_build.cpp); triangle tests use the reference's exact float32 expression.
+// One ray per lane, but the loop is WARP-SYNCHRONOUS: every iteration the warp votes and performs
+// either one node step (lanes sitting on an inner node) or one leaf step (lanes sitting on a leaf);
+// lanes whose turn it is not simply wait.  Leaves are postponed until enough lanes have one
+// (kLeafVote) so both kinds of step run at high lane occupancy, and there is no divergent
+// control flow for the compiler to fail to reconverge (the first version of this kernel averaged
+// 2.8 active lanes per instruction -- profiles/r1_ncu_render_v0.txt).
+//   * nodes are 64 B = two 256-bit loads (LDG.E.ENL2.256), triangle records 64 B of which the test
+//     needs 48 (one 256-bit + one 128-bit load); the 4th quarter (unit normal) is fetched for the
+//     winner only.  The whole structure of the 1M-triangle hall (~96 MB) is L2-resident on B200.
+//   * the traversal stack lives in shared memory, [entry][thread] so a warp's access is
+//     conflict-free; entries carry the child's entry distance so stale subtrees are culled on pop.
+//   * box tests use FMA and are conservative; triangle tests use the reference's exact float32
+//     expression (device_exact.cuh).  A child is culled only if the ray enters its padded box
+//     later than best_t * (1 + kKappa) + s0 [default], or later than best_t + slack(child)
+//     [EXACT: rigorous per-child bound from bvh_build.cpp, ~2x the node visits].
 #pragma once
 #include "device_exact.cuh"
 
@@ -13,17 +23,34 @@ namespace earb {
 
 struct SceneDev {
 	const float4* nodes;      // 4 float4 per node
-	const float4* tris;       // 3 float4 per triangle record (leaf order)
+	const float4* tris;       // 4 float4 per triangle record (leaf order)
 	const float4* materials;  // [M][B] {refl, refr, kept, spec}
 	int32_t n_tris, n_materials, n_bands;
+	float s0;                 // absolute interval margin (see bvh_build.cpp)
+	int32_t exact;            // 1: rigorous per-child slack
 };
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
-constexpr int kStackSize = 64;   // builder bounds depth by 30 + log2(T) (bvh_build.cpp kSahDepth)
+constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes spill to local memory
+constexpr int kStackSpill = 40;
+constexpr int kLeafVote = 12;           // do a leaf step once this many lanes wait on a leaf
+constexpr float kKappa = 1.0f / 1024.0f;
 
-struct RaySetup {
-	float idx, idy, idz, oox, ooy, ooz;
-};
+struct F8 { float4 lo, hi; };
+__device__ __forceinline__ F8 ldg256(const float4* p) {
+	F8 r;
+#ifdef EARB_HOST_EMULATION
+	r.lo = p[0]; r.hi = p[1];
+	return r;
+#else
+	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
+	             : "l"(p));
+	return r;
+#endif
+}
+
+struct RaySetup { float idx, idy, idz, oox, ooy, ooz; };
 __device__ __forceinline__ RaySetup make_setup(V3 o, V3 d) {
 	const float tiny = 1e-20f;
 	const float dx = fabsf(d.x) > tiny ? d.x : copysignf(tiny, d.x);
@@ -35,75 +62,121 @@ __device__ __forceinline__ RaySetup make_setup(V3 o, V3 d) {
 	return s;
 }
 
-// slab test of one child box against the ray interval [lo_t, hi_t]
-__device__ __forceinline__ bool slab(const RaySetup& s, float lx, float hx, float ly, float hy, float lz, float hz,
-                                     float lo_t, float hi_t, float& tnear) {
-	const float x0 = fmaf(lx, s.idx, -s.oox), x1 = fmaf(hx, s.idx, -s.oox);
-	const float y0 = fmaf(ly, s.idy, -s.ooy), y1 = fmaf(hy, s.idy, -s.ooy);
-	const float z0 = fmaf(lz, s.idz, -s.ooz), z1 = fmaf(hz, s.idz, -s.ooz);
-	const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), lo_t));
-	const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), hi_t));
-	tnear = tn;
-	return tn <= tf;
-}
+// per-lane stack: shared memory first, local memory beyond kStackEntries (never reached by SAH trees
+// of realistic scenes; the builder bounds the depth so even adversarial input cannot overflow both)
+struct LaneStack {
+	int2* smem;       // this lane's column: entry k at smem[k * stride]
+	int stride;
+	int2 spill[kStackSpill];
+	int sp;
+	__device__ __forceinline__ void push(int32_t node, float key) {
+		const int2 e = make_int2(node, __float_as_int(key));
+		if (sp < kStackEntries) smem[sp * stride] = e;
+		else if (sp < kStackEntries + kStackSpill) spill[sp - kStackEntries] = e;
+		++sp;
+	}
+	__device__ __forceinline__ int2 pop() {
+		--sp;
+		return sp < kStackEntries ? smem[sp * stride] : spill[min(sp - kStackEntries, kStackSpill - 1)];
+	}
+};
 
-// ANY_HIT = false: argmin over (t, original index) of triangles with MT hit and t > 0.001 (t < 1e6);
-//                  returns the original triangle index or -1, `best_t`, and the record slot.
-// ANY_HIT = true : d is the UNNORMALISED segment x - p; returns 1 as soon as a triangle has 1e-5 < t < 1.
-template <bool ANY_HIT>
-__device__ __forceinline__ int32_t traverse(const SceneDev& sc, V3 o, V3 d, float& best_t, int32_t& best_slot) {
+// Warp-synchronous traversal; must be called by all 32 lanes of the warp (inactive lanes pass
+// active = false).
+// ANY_HIT = false: argmin over (t, original index) of triangles with MT hit and t > 0.001 (t < 1e6):
+//                  best_idx = original triangle index or -1, best_t, best_slot = record slot.
+// ANY_HIT = true : d is the UNNORMALISED segment x - p; best_idx = 1 as soon as a triangle has 1e-5 < t < 1.
+template <bool ANY_HIT, bool EXACT>
+__device__ __forceinline__ void traverse_warp(const SceneDev& sc, int2* stack_smem, int stack_stride, bool active, V3 o,
+                                              V3 d, float& best_t, int32_t& best_idx, int32_t& best_slot) {
 	const RaySetup rs = make_setup(o, d);
-	int32_t stack[kStackSize];
-	int sp = 0;
-	int32_t node = 0;
-	int32_t best_idx = -1;
+	LaneStack st;
+	st.smem = stack_smem; st.stride = stack_stride; st.sp = 0;
+	int32_t node = active ? 0 : kEmptyChildDev;
+	best_idx = ANY_HIT ? 0 : -1;
 	best_t = ANY_HIT ? 1.0f : 1000000.0f;
 	best_slot = -1;
+	const float lo_t = -sc.s0;
 	for (;;) {
-		// ---- inner nodes ----
-		while (node >= 0 && node != kEmptyChildDev) {
-			const float4 a = __ldg(sc.nodes + 4 * (size_t)node);
-			const float4 b = __ldg(sc.nodes + 4 * (size_t)node + 1);
-			const float4 c = __ldg(sc.nodes + 4 * (size_t)node + 2);
-			const float4 dd = __ldg(sc.nodes + 4 * (size_t)node + 3);
-			const int32_t c0 = __float_as_int(dd.x), c1 = __float_as_int(dd.y);
-			const float s0 = dd.z, s1 = dd.w;
-			float t0, t1;
-			const bool h0 = c0 != kEmptyChildDev && slab(rs, a.x, a.y, a.z, a.w, c.x, c.y, -s0, best_t + s0, t0);
-			const bool h1 = c1 != kEmptyChildDev && slab(rs, b.x, b.y, b.z, b.w, c.z, c.w, -s1, best_t + s1, t1);
-			if (h0 && h1) {
-				const bool swap = t1 < t0;
-				node = swap ? c1 : c0;
-				if (sp < kStackSize) stack[sp++] = swap ? c0 : c1;
-			} else if (h0) node = c0;
-			else if (h1) node = c1;
-			else if (sp > 0) node = stack[--sp];
-			else node = kEmptyChildDev;
-		}
-		if (node == kEmptyChildDev) break;
-		// ---- leaf ----
-		const int32_t code = ~node;
-		const int32_t first = code >> 3, count = (code & 7) + 1;
-		for (int32_t i = 0; i < count; ++i) {
-			const float4 r0 = __ldg(sc.tris + 3 * (size_t)(first + i));
-			const float4 r1 = __ldg(sc.tris + 3 * (size_t)(first + i) + 1);
-			const float4 r2 = __ldg(sc.tris + 3 * (size_t)(first + i) + 2);
-			float t;
-			if (moeller_trumbore(mk(r0.x, r0.y, r0.z), mk(r1.x, r1.y, r1.z), mk(r2.x, r2.y, r2.z), o, d, t)) {
-				if (ANY_HIT) {
-					if (t > 1e-5f && t < 1.0f) return 1;
-				} else {
-					const int32_t idx = __float_as_int(r0.w);
-					// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
-					if (t > 0.001f && (t < best_t || (t == best_t && idx < best_idx))) {
-						best_t = t; best_idx = idx; best_slot = first + i;
+		const bool inner = node >= 0 && node != kEmptyChildDev;
+		const bool leaf = node < 0;
+		const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
+		const unsigned m_leaf = __ballot_sync(0xffffffffu, leaf);
+		if ((m_inner | m_leaf) == 0u) break;
+		if (m_inner != 0u && __popc(m_leaf) < kLeafVote) {
+			// ---------------- node step ----------------
+			if (inner) {
+				const F8 n0 = ldg256(sc.nodes + 4 * (size_t)node);
+				const F8 n1 = ldg256(sc.nodes + 4 * (size_t)node + 2);
+				const float4 a = n0.lo, b = n0.hi, c = n1.lo;
+				const int32_t c0 = __float_as_int(n1.hi.x), c1 = __float_as_int(n1.hi.y);
+				// interval upper ends: relative (default) or rigorous per-child slack
+				const float hi_rel = fmaf(best_t, kKappa, best_t) + sc.s0;
+				const float hi0 = EXACT ? best_t + n1.hi.z : hi_rel, hi1 = EXACT ? best_t + n1.hi.w : hi_rel;
+				const float lo0 = EXACT ? -n1.hi.z : lo_t, lo1 = EXACT ? -n1.hi.w : lo_t;
+				const float x00 = fmaf(a.x, rs.idx, -rs.oox), x01 = fmaf(a.y, rs.idx, -rs.oox);
+				const float y00 = fmaf(a.z, rs.idy, -rs.ooy), y01 = fmaf(a.w, rs.idy, -rs.ooy);
+				const float z00 = fmaf(c.x, rs.idz, -rs.ooz), z01 = fmaf(c.y, rs.idz, -rs.ooz);
+				const float x10 = fmaf(b.x, rs.idx, -rs.oox), x11 = fmaf(b.y, rs.idx, -rs.oox);
+				const float y10 = fmaf(b.z, rs.idy, -rs.ooy), y11 = fmaf(b.w, rs.idy, -rs.ooy);
+				const float z10 = fmaf(c.z, rs.idz, -rs.ooz), z11 = fmaf(c.w, rs.idz, -rs.ooz);
+				const float tn0 = fmaxf(fmaxf(fminf(x00, x01), fminf(y00, y01)), fmaxf(fminf(z00, z01), lo0));
+				const float tf0 = fminf(fminf(fmaxf(x00, x01), fmaxf(y00, y01)), fminf(fmaxf(z00, z01), hi0));
+				const float tn1 = fmaxf(fmaxf(fminf(x10, x11), fminf(y10, y11)), fmaxf(fminf(z10, z11), lo1));
+				const float tf1 = fminf(fminf(fmaxf(x10, x11), fmaxf(y10, y11)), fminf(fmaxf(z10, z11), hi1));
+				const bool h0 = c0 != kEmptyChildDev && tn0 <= tf0;
+				const bool h1 = c1 != kEmptyChildDev && tn1 <= tf1;
+				// stack key: distance at which the child stops being interesting (compared with best_t on pop)
+				const float k0 = EXACT ? tn0 - n1.hi.z : tn0, k1 = EXACT ? tn1 - n1.hi.w : tn1;
+				if (h0 && h1) {
+					const bool swap = tn1 < tn0;
+					node = swap ? c1 : c0;
+					st.push(swap ? c0 : c1, swap ? k0 : k1);
+				} else if (h0) node = c0;
+				else if (h1) node = c1;
+				else {
+					node = kEmptyChildDev;
+					const float limit = EXACT ? best_t : hi_rel;
+					while (st.sp > 0) {
+						const int2 e = st.pop();
+						if (__int_as_float(e.y) <= limit) { node = e.x; break; }
+					}
+				}
+			}
+		} else {
+			// ---------------- leaf step ----------------
+			if (leaf) {
+				const int32_t code = ~node;
+				const int32_t first = code >> 3, count = (code & 7) + 1;
+				for (int32_t i = 0; i < count; ++i) {
+					const float4* rec = sc.tris + 4 * (size_t)(first + i);
+					const F8 r01 = ldg256(rec);
+					const float4 r2 = __ldg(rec + 2);
+					float t;
+					if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z),
+					                     o, d, t)) {
+						if (ANY_HIT) {
+							if (t > 1e-5f && t < 1.0f) best_idx = 1;
+						} else {
+							const int32_t idx = __float_as_int(r01.lo.w);
+							// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
+							if (t > 0.001f && (t < best_t || (t == best_t && idx < best_idx))) {
+								best_t = t; best_idx = idx; best_slot = first + i;
+							}
+						}
+					}
+				}
+				node = kEmptyChildDev;
+				if (!(ANY_HIT && best_idx)) {
+					const float limit = EXACT ? best_t : fmaf(best_t, kKappa, best_t) + sc.s0;
+					while (st.sp > 0) {
+						const int2 e = st.pop();
+						if (__int_as_float(e.y) <= limit) { node = e.x; break; }
 					}
 				}
 			}
 		}
-		if (sp > 0) node = stack[--sp]; else break;
 	}
-	return ANY_HIT ? 0 : best_idx;
 }
 
 }  // namespace earb

@@ -20,7 +20,7 @@ def build():
 
 
 class EmulScene:
-    def __init__(self, verts, mats=None):
+    def __init__(self, verts, mats=None, exact=False):
         build()
         self.l = C.CDLL(LIB)
         self.l.emul_create.restype = C.c_void_p
@@ -31,6 +31,9 @@ class EmulScene:
         self.l.emul_occluded.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
         self.verts = np.ascontiguousarray(verts, np.float32).reshape(-1, 3, 3)
         self.h = self.l.emul_create(self.verts.ctypes.data, None, self.verts.shape[0])
+        self.l.emul_set_exact.argtypes = [C.c_void_p, C.c_int32]
+        if exact:
+            self.l.emul_set_exact(self.h, 1)
 
     def __del__(self):
         if getattr(self, "h", None):

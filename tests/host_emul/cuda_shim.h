@@ -20,4 +20,11 @@ static inline uint32_t __float_as_uint(float f) { uint32_t u; memcpy(&u, &f, 4);
 static inline int32_t __float_as_int(float f) { int32_t u; memcpy(&u, &f, 4); return u; }
 static inline uint32_t __umulhi(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+struct int2 { int x, y; };
+static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
+static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }   // a one-lane warp
+static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+using std::min;
+using std::max;
 #define EARB_HOST_EMULATION 1

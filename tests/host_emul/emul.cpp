@@ -16,26 +16,31 @@ void* emul_create(const float* verts, const int32_t* mats, int32_t n) {
 	e->dev.nodes = (const float4*)e->bvh.nodes.data();
 	e->dev.tris = (const float4*)e->bvh.tris.data();
 	e->dev.materials = nullptr; e->dev.n_tris = n; e->dev.n_materials = 0; e->dev.n_bands = 0;
+	e->dev.s0 = e->bvh.s0; e->dev.exact = 0;
 	return e;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
+void emul_set_exact(void* h, int32_t exact) { ((Emul*)h)->dev.exact = exact; }
 void emul_stats(void* h, int32_t* n_nodes, int32_t* depth, double* build_ms) {
 	Emul* e = (Emul*)h; *n_nodes = (int32_t)e->bvh.nodes.size(); *depth = e->bvh.depth; *build_ms = e->build_ms;
 }
 void emul_first_hit(void* h, const float* o, const float* d, int64_t n, int32_t* idx, float* t) {
 	Emul* e = (Emul*)h;
 	for (int64_t i = 0; i < n; ++i) {
-		float bt; int32_t slot;
-		idx[i] = traverse<false>(e->dev, mk(o[3*i], o[3*i+1], o[3*i+2]), mk(d[3*i], d[3*i+1], d[3*i+2]), bt, slot);
-		t[i] = bt;
+		float bt; int32_t slot, bi; int2 stack[kStackEntries];
+		if (e->dev.exact) traverse_warp<false, true>(e->dev, stack, 1, true, mk(o[3*i], o[3*i+1], o[3*i+2]), mk(d[3*i], d[3*i+1], d[3*i+2]), bt, bi, slot);
+		else traverse_warp<false, false>(e->dev, stack, 1, true, mk(o[3*i], o[3*i+1], o[3*i+2]), mk(d[3*i], d[3*i+1], d[3*i+2]), bt, bi, slot);
+		idx[i] = bi; t[i] = bt;
 	}
 }
 void emul_occluded(void* h, const float* p, const float* x, int64_t n, uint8_t* out) {
 	Emul* e = (Emul*)h;
 	for (int64_t i = 0; i < n; ++i) {
-		float bt; int32_t slot;
+		float bt; int32_t slot, bi; int2 stack[kStackEntries];
 		const V3 a = mk(p[3*i], p[3*i+1], p[3*i+2]), b = mk(x[3*i], x[3*i+1], x[3*i+2]);
-		out[i] = (uint8_t)traverse<true>(e->dev, a, vsub(b, a), bt, slot);
+		if (e->dev.exact) traverse_warp<true, true>(e->dev, stack, 1, true, a, vsub(b, a), bt, bi, slot);
+		else traverse_warp<true, false>(e->dev, stack, 1, true, a, vsub(b, a), bt, bi, slot);
+		out[i] = (uint8_t)bi;
 	}
 }
 }

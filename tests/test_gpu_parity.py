@@ -113,7 +113,7 @@ def test_multiple_recorders_and_raw_shards_add_up(ob):
     contract: partial sums, one reduce, then finalise)."""
     sc = common.named_scene("example1")
     sc.samples = 8000
-    sc.recorders.append(type(sc.recorders[0])("/tmp/b.wav", position=(-8.0, 3.0, 2.0)))
+    sc.recorders.append(type(sc.recorders[0])("/tmp/b.wav", position=(-8.0, 3.0, 2.0), stereo=True, right_ear=(0.0, 1.0, 0.0)))
     gpu, cpu = _pair(ob, sc)
     ctxs, recs = api.contexts_from_def(sc)
     full = gpu.render(ctxs, recs, max_bounces=60, seed=2, finalise=False)
