@@ -137,23 +137,15 @@ def run_ours(args):
     flush = torch.empty((64 * 1024 * 1024,), dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    launches = [0]
 
-    def step(timed_kernel=False):
+    def step():
         flush.zero_()
         hist.zero_()
         counters.zero_()
         rng[:, 0] = api.FIRST_SAMPLE_INIT
         rng[:, 1] = 0
-        if timed_kernel:
-            k0.record(stream)
         api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
                                                   hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
-        if timed_kernel:
-            k1.record(stream)
-        launches[0] += 1
         if world > 1:
             # one reduce of the partial histograms over NVLink; track ranges reduce by min / max
             rng_first.copy_(rng[:, 0]); rng_real.copy_(rng[:, 1])
@@ -162,7 +154,6 @@ def run_ours(args):
         if rank == 0:
             api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
                                                          hist.data_ptr(), rng.data_ptr(), sp))
-            launches[0] += 3
 
     def barrier():
         if world > 1:
@@ -175,26 +166,26 @@ def run_ours(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    launches[0] = 0
+    scene.stats(reset=True)
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     seg_total = occ_total = bins_total = 0
     t0.record(stream)
     for _ in range(args.steps):
-        step(timed_kernel=True)
-        k1.synchronize()
-        kernel_ms.append(k0.elapsed_time(k1))
+        step()
         c = counters.cpu().numpy()
         seg_total += int(c[1]); occ_total += int(c[2]); bins_total += int(c[4])
     t1.record(stream)
     barrier()
     ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=dev)
     tot = torch.tensor([seg_total, occ_total, bins_total, int(counters[5].item())], dtype=torch.int64, device=dev)
-    kms = torch.tensor([sum(kernel_ms) / len(kernel_ms)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
+    st = scene.stats()
+    n_launch = sum(st["launches"].values())
+    trav_ms = st["ms"]["closest"] + st["ms"]["anyhit"] + st["ms"]["fused"]        # dominant kernel class, this rank
+    trav_launches = st["launches"]["closest"] + st["launches"]["anyhit"] + st["launches"]["fused"]
     total_ms = float(ms.item())
     segments, occl, bins, dropped = (int(x) for x in tot.tolist())
     value = segments / (total_ms * 1e-3)
@@ -204,7 +195,7 @@ def run_ours(args):
     h2d = verts.nbytes + tri_mat.nbytes + table.nbytes + C.sizeof(ctx_c) + C.sizeof(rec_c)
     d2h = 0
     e2e_segments = 0
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
     for _ in range(e2e_steps):
         barrier()
         w0 = time.perf_counter()
@@ -226,7 +217,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
         dist.all_reduce(es, op=dist.ReduceOp.SUM)
-    e2e_value = float(es.item()) / (float(e2.item()) * 1e-3)
+    e2e_value = float(es.item()) / (float(e2.item()) * 1e-3) if e2e_steps else None
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -236,9 +227,14 @@ def run_ours(args):
             cpu_base = {"error": str(exc)[:200]}
     if rank == 0:
         peak, which = measured_peak()
-        per_launch = algorithmic_bytes(N_TRIS, segments / args.steps / world, occl / args.steps / world,
-                                       bins / args.steps / world)
-        achieved = per_launch / (float(kms.item()) * 1e-3) / 1e9
+        # dominant kernel = the BVH traversal kernels (closest-hit + any-hit launches of this rank).  Algorithmic
+        # bytes they move: Q(T) per query + 32 B ray in / 8 B hit out per query; duration: CUDA events
+        # recorded by the library around every launch on the launch stream, summed over the timed region.
+        depth = math.ceil(math.log2(max(2, math.ceil(N_TRIS / 4))))
+        q_bytes = 32 * depth + 192 + 40
+        trav_bytes = q_bytes * (segments + occl) / world
+        achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
+        whole = algorithmic_bytes(N_TRIS, segments / world, occl / world, bins / world) / (total_ms * 1e-3) / 1e9
         line = {
             "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
@@ -251,11 +247,15 @@ def run_ours(args):
             "bin_updates_per_step": bins // args.steps, "dropped_updates": dropped,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "includes": "scene upload + BVH build + trace + finalise + track download"},
-            "gpu_launches": launches[0],
+            "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
+            "launches_per_step": {k: v / args.steps for k, v in st["launches"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "render_kernel", "kernel_ms": float(kms.item()),
+                         "traffic": None, "kernel": "wf_traverse_kernel (closest + any-hit)",
+                         "kernel_ms": trav_ms / max(1, trav_launches), "kernel_launches": trav_launches,
+                         "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                          "peak_source": which,
-                         "bytes_model": "64*S + (32*ceil(log2(ceil(T/4)))+192)*(S+O) + 8*U per launch"},
+                         "bytes_model": "traversal launches: (32*ceil(log2(ceil(T/4)))+192 + 40)*(S+O); whole step: "
+                                        "64*S + (32*ceil(log2(ceil(T/4)))+192)*(S+O) + 8*U (SURVEY 8d)"},
             "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -334,6 +334,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -56,11 +56,17 @@ class ResultC(C.Structure):
                 ("device_ms", C.c_double), ("bvh_build_ms", C.c_double)]
 
 
+class StatsC(C.Structure):
+    _fields_ = [("launches", C.c_uint64 * 8), ("ms", C.c_double * 8), ("iterations", C.c_uint64), ("reserved", C.c_uint64)]
+
+
+KERNEL_CLASSES = ["shade", "closest", "anyhit", "splat", "fused", "finalise"]
+
 EXPORTS = [
     "ear_b200_last_error", "ear_b200_abi_version", "ear_b200_device_count", "ear_b200_scene_create",
     "ear_b200_scene_destroy", "ear_b200_first_hit", "ear_b200_occluded", "ear_b200_trace_paths",
     "ear_b200_render", "ear_b200_result_free", "ear_b200_trace_device", "ear_b200_finalise_device",
-    "ear_b200_default_bins",
+    "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset",
 ]
 
 _lib = None
@@ -94,6 +100,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                           C.POINTER(OptionsC), i32, vp, vp, vp, vp]
     lib.ear_b200_finalise_device.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(RecorderC), i32, i32, vp, vp, vp]
     lib.ear_b200_default_bins.argtypes = [vp, C.POINTER(OptionsC)]
+    lib.ear_b200_scene_stats.argtypes = [vp, C.POINTER(StatsC)]
+    lib.ear_b200_scene_stats_reset.argtypes = [vp]
+    lib.ear_b200_scene_stats_reset.restype = None
     if path is None:
         _lib = lib
     return lib
@@ -267,6 +276,18 @@ class Scene:
         _check(self.lib, self.lib.ear_b200_trace_paths(self.handle, C.byref(cc), ctx_index, C.byref(opt), n,
                                                         hits.ctypes.data, state.ctypes.data))
         return hits, state
+
+    def stats(self, reset: bool = False) -> dict:
+        """Launch counts and CUDA-event milliseconds per kernel class since the last reset."""
+        st = StatsC()
+        _check(self.lib, self.lib.ear_b200_scene_stats(self.handle, C.byref(st)))
+        out = {"iterations": int(st.iterations), "launches": {}, "ms": {}}
+        for i, name in enumerate(KERNEL_CLASSES):
+            out["launches"][name] = int(st.launches[i])
+            out["ms"][name] = float(st.ms[i])
+        if reset:
+            self.lib.ear_b200_scene_stats_reset(self.handle)
+        return out
 
     def default_bins(self, opt: OptionsC) -> int:
         return int(self.lib.ear_b200_default_bins(self.handle, C.byref(opt)))

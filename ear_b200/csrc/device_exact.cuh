@@ -61,7 +61,16 @@ __device__ __forceinline__ bool invalid_float(float x) {
 #ifndef EARB_HOST_EMULATION
 __device__ __forceinline__ float pow_ref(float x, float y) {
 	if (y == 0.0f || x == 1.0f) return 1.0f;
+	// results below 2^-150 round to +0: decide that from a single-precision estimate and skip the double path
+	// (x^1000 lobes underflow for x < 0.9, i.e. for ~90 % of the specular-lobe evaluations)
+	if (x > 0.0f && x < 1.0f && y > 0.0f && y * __log2f(x) < -156.0f) return 0.0f;
 	return __double2float_rn(exp2((double)y * log2((double)x)));
+}
+// pow(af, l) with log2(af) hoisted: the air-absorption base is fixed per context
+__device__ __forceinline__ double log2_ref(float x) { return log2((double)x); }
+__device__ __forceinline__ float pow_ref_hoisted(float x, double log2_x, float y) {
+	if (y == 0.0f || x == 1.0f) return 1.0f;
+	return __double2float_rn(exp2((double)y * log2_x));
 }
 #endif
 
@@ -83,17 +92,18 @@ __device__ __forceinline__ bool moeller_trumbore(V3 v0, V3 e1, V3 e2, V3 o, V3 d
 	return t >= 0.0f;
 }
 
-// ---------------- Philox4x32-10, keyed (seed) / counter (ray_lo, ray_hi, block, context) ----------------
+// ---------------- Philox4x32-10 ----------------
+// key = seed, counter = (ray id lo, ray id hi, draw index, context).  Every draw is one block: a
+// Sample_Sphere try takes its three uniforms from words 0..2, Material::Bounce takes word 0.  The only
+// per-ray state is the 32-bit draw index, so a ray can be parked in memory between kernels.
 struct Rng {
 	uint32_t k0, k1, ray_lo, ray_hi, ctx, block;
-	uint32_t b0, b1, b2, b3;
-	int pos;
-	__device__ __forceinline__ void start(uint64_t seed, uint32_t context, uint64_t ray) {
+	__device__ __forceinline__ void start(uint64_t seed, uint32_t context, uint64_t ray, uint32_t first_block = 0) {
 		k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32);
 		ray_lo = (uint32_t)ray; ray_hi = (uint32_t)(ray >> 32);
-		ctx = context; block = 0; pos = 4;
+		ctx = context; block = first_block;
 	}
-	__device__ __forceinline__ void refill() {
+	__device__ __forceinline__ void draw(uint32_t& w0, uint32_t& w1, uint32_t& w2) {
 		uint32_t c0 = ray_lo, c1 = ray_hi, c2 = block++, c3 = ctx, ka = k0, kb = k1;
 #pragma unroll
 		for (int r = 0; r < 10; ++r) {
@@ -103,23 +113,30 @@ struct Rng {
 			c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
 			ka += 0x9E3779B9u; kb += 0xBB67AE85u;
 		}
-		b0 = c0; b1 = c1; b2 = c2; b3 = c3; pos = 0;
+		w0 = c0; w1 = c1; w2 = c2;
 	}
-	// 24-bit uniform in [0,1); stands in for gmtl::Math::unitRandom = rand()/RAND_MAX
-	__device__ __forceinline__ float unit() {
-		if (pos == 4) refill();
-		const uint32_t x = pos == 0 ? b0 : pos == 1 ? b1 : pos == 2 ? b2 : b3;
-		++pos;
-		return fmul((float)(x >> 8), 1.0f / 16777216.0f);
+	// 24-bit uniforms in [0,1); stand in for gmtl::Math::unitRandom = rand()/RAND_MAX
+	static __device__ __forceinline__ float to_unit(uint32_t x) { return fmul((float)(x >> 8), 1.0f / 16777216.0f); }
+	__device__ __forceinline__ void unit3(float& a, float& b, float& c) {
+		uint32_t w0, w1, w2;
+		draw(w0, w1, w2);
+		a = to_unit(w0); b = to_unit(w1); c = to_unit(w2);
+	}
+	__device__ __forceinline__ float unit1() {
+		uint32_t w0, w1, w2;
+		draw(w0, w1, w2);
+		return to_unit(w0);
 	}
 };
 
 // Sample_Sphere, src/Distributions.h:48-58 (cube rejection, 0.001 <= |v|^2 <= 1)
 __device__ __forceinline__ V3 sample_sphere(Rng& rng) {
 	for (;;) {
-		const float f1 = fsub(fmul(rng.unit(), 2.0f), 1.0f);
-		const float f2 = fsub(fmul(rng.unit(), 2.0f), 1.0f);
-		const float f3 = fsub(fmul(rng.unit(), 2.0f), 1.0f);
+		float u1, u2, u3;
+		rng.unit3(u1, u2, u3);
+		const float f1 = fsub(fmul(u1, 2.0f), 1.0f);
+		const float f2 = fsub(fmul(u2, 2.0f), 1.0f);
+		const float f3 = fsub(fmul(u3, 2.0f), 1.0f);
 		V3 v = mk(f1, f2, f3);
 		const float l = vdot(v, v);
 		if (l < 0.001f || l > 1.0f) continue;

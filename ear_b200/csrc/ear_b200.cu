@@ -52,6 +52,8 @@ struct RenderParams {
 	uint32_t* range;                 // [n_ctx][n_rec][2][2] {first_sample, real_length}
 	unsigned long long* counters;    // [8]
 	unsigned long long* next_work;   // work-queue head
+	int32_t* hits;                   // parity harness: [rays][max_bounces] triangle hit per bounce (or null)
+	float* final_state;              // parity harness: [rays][8] (or null)
 };
 
 struct LocalCounters {
@@ -139,6 +141,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 	long long ray_slot = 0;   // PATHS: index of this lane's ray in the output arrays
 	V3 o = mk(0, 0, 0), d = mk(0, 0, 0), prev_dir = mk(0, 0, 0);
 	float intensity = 1.0f, path = 0.0f, af = 1.0f;
+	double log2_af = 0.0;
 	int band = 0;
 	Rng rng;
 	rng.start(0, 0, 0);
@@ -169,6 +172,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 				}
 				band = p.ctx[c].band;
 				af = p.ctx[c].absorption_factor;
+				log2_af = log2_ref(af);
 				rng.start(p.seed, (uint32_t)c, ray);
 				++lc.rays;
 				// bounce 0: AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226); intensity 1 is
@@ -211,13 +215,13 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 			const float4 m = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
 			// Material::Bounce (src/Material.cpp:76-83); its comparisons against 0.0001 are in double
 			if ((double)m.x < 0.0001 && (double)m.y < 0.0001) refract = false;
-			else refract = !(rng.unit() <= fdiv(m.x, fadd(m.x, m.y)));
+			else refract = !(rng.unit1() <= fdiv(m.x, fadd(m.x, m.y)));
 			spec = m.w;
 			V3 v;
 			if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
 			else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
 			const float seg = vlength(vsub(pnt, o));
-			intensity = fmul(intensity, pow_ref(af, seg));                               // src/Scene.cpp:154
+			intensity = fmul(intensity, pow_ref_hoisted(af, log2_af, seg));                               // src/Scene.cpp:154
 			path = fadd(path, seg);
 			o = pnt; d = v;
 			intensity = fmul(intensity, m.z);                                            // :169-171
@@ -230,12 +234,15 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 				const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
 				const V3 x = mk(rec.position[0], rec.position[1], rec.position[2]);
 				const V3 segv = vsub(x, o);   // LineSeg(p, x) = Ray(p, x - p)
+				// Scene::Connect is evaluated for every live lane in the reference (:194); its answer is only used
+				// when dot(lsdir, n) > 0 (:209), so lanes failing that test skip the traversal (same result)
+				const V3 lsdir = vnormalized(segv);
+				const bool facing = shade && vdot(lsdir, n) > 0.0f;
 				float tt; int32_t occluded, ss;
-				traverse_warp<true, EXACT>(sc, stack, stride, shade, o, segv, tt, occluded, ss);
+				traverse_warp<true, EXACT>(sc, stack, stride, facing, o, segv, tt, occluded, ss);
 				if (shade) {
 					++lc.occlusion;
-					const V3 lsdir = vnormalized(segv);
-					if (!occluded && vdot(lsdir, n) > 0.0f) {                                // :197-209
+					if (facing && !occluded) {                                               // :197-209
 						float factor;
 						if (!refract) {                                                      // :219-235
 							const V3 rv = vreflect(prev_dir, n);
@@ -251,7 +258,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 						}
 						float contrib = fmul(intensity, factor);
 						const float l = vlength(segv);                                       // :250
-						contrib = fmul(contrib, pow_ref(af, l));
+						contrib = fmul(contrib, pow_ref_hoisted(af, log2_af, l));
 						contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));   // INV_HEMI_2, :252
 						if (!invalid_float(contrib)) {
 							if (b & 1) contrib = fmul(contrib, -1.0f);                       // :257
@@ -282,9 +289,12 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 	}
 }
 
-// Persistent kernel: grid = SMs x resident blocks; warps pull ray ids from a global queue until it is dry.
-template <bool EXACT>
-__global__ void __launch_bounds__(kBlock) render_kernel(SceneDev sc, RenderParams p) {
+#include "wavefront.cuh"
+
+// Fused single-kernel engine (EAR_B200_ENGINE=mega): grid = SMs x resident blocks; warps pull ray ids from a
+// global queue until it is dry.
+template <bool EXACT, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) render_kernel(SceneDev sc, RenderParams p) {
 	extern __shared__ int2 stack_smem[];
 	const int lane = threadIdx.x & 31;
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
@@ -402,6 +412,20 @@ struct ear_b200_scene {
 	double bvh_build_ms = 0.0;
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
+	int min_blocks = 4;
+	int engine = 0;                 // 0 = wavefront (default), 1 = fused kernel (EAR_B200_ENGINE=mega)
+	int max_slots = 1 << 20;        // rays in flight in the wavefront pool (EAR_B200_SLOTS)
+	int check_every = 8;            // iterations between host checks for completion
+	WfPool pool{};
+	size_t pool_slots = 0, pool_queries = 0;
+	int* h_counts = nullptr;        // pinned
+	unsigned long long* d_scratch_counters = nullptr;
+	ear_b200_stats stats{};
+	// event pairs recorded around every engine launch, harvested at the engine's sync points
+	struct Timed { cudaEvent_t a, b; int cls; };
+	std::vector<Timed> ev_pool;
+	size_t ev_used = 0;
+	cudaStream_t last_stream = nullptr;
 	// scratch reused across calls
 	ear_b200_context* d_ctx = nullptr; ear_b200_recorder* d_rec = nullptr; long long* d_prefix = nullptr;
 	unsigned long long* d_queue = nullptr;
@@ -461,6 +485,21 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	// EAR_B200_EXACT_SLACK=1 selects the rigorous per-child interval bound (about 2x the node visits)
 	const char* ex = std::getenv("EAR_B200_EXACT_SLACK");
 	s->dev.exact = (ex && std::atoi(ex) != 0) ? 1 : 0;
+	// tuning knobs (defaults are the measured best, see profiles/)
+	const char* lv = std::getenv("EAR_B200_LEAF_VOTE");
+	s->dev.leaf_vote = lv ? std::max(1, std::min(32, std::atoi(lv))) : kLeafVote;
+	const char* mb = std::getenv("EAR_B200_MIN_BLOCKS");
+	s->min_blocks = mb ? std::atoi(mb) : 5;
+	const char* fv = std::getenv("EAR_B200_FETCH_VOTE");
+	s->dev.fetch_vote = fv ? std::max(1, std::min(32, std::atoi(fv))) : 8;
+	const char* en = std::getenv("EAR_B200_ENGINE");
+	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
+	const char* sl = std::getenv("EAR_B200_SLOTS");
+	if (sl) s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl)));
+	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
+	if (ce) s->check_every = std::max(1, std::atoi(ce));
+	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
+	CUDA_TRY(cudaMalloc(&s->d_scratch_counters, 8 * sizeof(unsigned long long)));
 	*out = s;
 	return 0;
 }
@@ -470,44 +509,85 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaSetDevice(s->device);
 	cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_materials);
 	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue);
+	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
+	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
+	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
+	cudaFree(s->d_scratch_counters);
+	if (s->h_counts) cudaFreeHost(s->h_counts);
+	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
+
+static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries);
 
 extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, const float* dirs, int64_t n,
                                       int32_t* tri_index, float* t) {
 	if (!s) return fail("first_hit: null scene");
 	if (n <= 0) return 0;
 	CUDA_TRY(cudaSetDevice(s->device));
+	const int64_t chunk = std::min<int64_t>(n, s->max_slots);
 	float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_i = nullptr;
-	CUDA_TRY(cudaMalloc(&d_o, n * 12)); CUDA_TRY(cudaMalloc(&d_d, n * 12));
-	CUDA_TRY(cudaMalloc(&d_t, n * 4)); CUDA_TRY(cudaMalloc(&d_i, n * 4));
-	CUDA_TRY(cudaMemcpyAsync(d_o, origins, n * 12, cudaMemcpyHostToDevice, s->stream));
-	CUDA_TRY(cudaMemcpyAsync(d_d, dirs, n * 12, cudaMemcpyHostToDevice, s->stream));
-	if (s->dev.exact) first_hit_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
-	else first_hit_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, n, d_i, d_t);
-	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpyAsync(tri_index, d_i, n * 4, cudaMemcpyDeviceToHost, s->stream));
-	CUDA_TRY(cudaMemcpyAsync(t, d_t, n * 4, cudaMemcpyDeviceToHost, s->stream));
-	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	CUDA_TRY(cudaMalloc(&d_o, chunk * 12)); CUDA_TRY(cudaMalloc(&d_d, chunk * 12));
+	CUDA_TRY(cudaMalloc(&d_t, chunk * 4)); CUDA_TRY(cudaMalloc(&d_i, chunk * 4));
+	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, 1)) return rc; }
+	RenderParams p{};
+	for (int64_t at = 0; at < n; at += chunk) {
+		const int m = (int)std::min<int64_t>(chunk, n - at);
+		const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+		CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
+		if (s->engine == 0) {
+			// the production closest-hit kernel (persistent, dynamic fetch) over an explicit ray list
+			WfPool pl = s->pool;
+			wf_load_rays_kernel<<<grid, kBlock, 0, s->stream>>>(pl, d_o, d_d, m);
+			int bps = 0;
+			void (*closest)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<false, true> : wf_traverse_kernel<false, false>;
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, closest, kBlock, kStackBytes));
+			closest<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
+			wf_store_hits_kernel<<<grid, kBlock, 0, s->stream>>>(s->dev, pl, m, d_i, d_t);
+		} else if (s->dev.exact) first_hit_kernel<true><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, m, d_i, d_t);
+		else first_hit_kernel<false><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, m, d_i, d_t);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(tri_index + at, d_i, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaMemcpyAsync(t + at, d_t, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+	}
 	cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
 	return 0;
 }
 
-extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p, const float* x, int64_t n, uint8_t* out) {
+extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const float* x, int64_t n, uint8_t* out) {
 	if (!s) return fail("occluded: null scene");
 	if (n <= 0) return 0;
 	CUDA_TRY(cudaSetDevice(s->device));
-	float *d_p = nullptr, *d_x = nullptr; uint8_t* d_out = nullptr;
-	CUDA_TRY(cudaMalloc(&d_p, n * 12)); CUDA_TRY(cudaMalloc(&d_x, n * 12)); CUDA_TRY(cudaMalloc(&d_out, n));
-	CUDA_TRY(cudaMemcpyAsync(d_p, p, n * 12, cudaMemcpyHostToDevice, s->stream));
-	CUDA_TRY(cudaMemcpyAsync(d_x, x, n * 12, cudaMemcpyHostToDevice, s->stream));
-	if (s->dev.exact) occluded_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, n, d_out);
-	else occluded_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, n, d_out);
-	CUDA_TRY(cudaGetLastError());
-	CUDA_TRY(cudaMemcpyAsync(out, d_out, n, cudaMemcpyDeviceToHost, s->stream));
-	CUDA_TRY(cudaStreamSynchronize(s->stream));
-	cudaFree(d_p); cudaFree(d_x); cudaFree(d_out);
+	const int64_t chunk = std::min<int64_t>(n, s->max_slots);
+	float *d_p = nullptr, *d_x = nullptr; uint8_t* d_out = nullptr; float4* d_qx = nullptr;
+	CUDA_TRY(cudaMalloc(&d_p, chunk * 12)); CUDA_TRY(cudaMalloc(&d_x, chunk * 12)); CUDA_TRY(cudaMalloc(&d_out, chunk));
+	CUDA_TRY(cudaMalloc(&d_qx, chunk * sizeof(float4)));
+	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, (size_t)chunk)) return rc; }
+	RenderParams p{};
+	for (int64_t at = 0; at < n; at += chunk) {
+		const int m = (int)std::min<int64_t>(chunk, n - at);
+		const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
+		CUDA_TRY(cudaMemcpyAsync(d_p, p_in + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
+		CUDA_TRY(cudaMemcpyAsync(d_x, x + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
+		if (s->engine == 0) {
+			WfPool pl = s->pool;
+			pl.qx = d_qx;
+			wf_load_segments_kernel<<<grid, kBlock, 0, s->stream>>>(pl, d_qx, d_p, d_x, m, d_out);
+			int bps = 0;
+			void (*anyhit)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<true, true> : wf_traverse_kernel<true, false>;
+			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, anyhit, kBlock, kStackBytes));
+			anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
+			wf_mark_visible_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(pl, d_out);
+		} else if (s->dev.exact) occluded_kernel<true><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
+		else occluded_kernel<false><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(out + at, d_out, (size_t)m, cudaMemcpyDeviceToHost, s->stream));
+		CUDA_TRY(cudaStreamSynchronize(s->stream));
+	}
+	cudaFree(d_p); cudaFree(d_x); cudaFree(d_out); cudaFree(d_qx);
 	return 0;
 }
 
@@ -533,7 +613,8 @@ extern "C" int32_t ear_b200_default_bins(ear_b200_scene* s, const ear_b200_optio
 }
 
 static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx, const ear_b200_recorder* rec,
-                             int32_t n_rec, const ear_b200_options* opt, cudaStream_t stream, RenderParams& p) {
+                             int32_t n_rec, const ear_b200_options* opt, cudaStream_t stream, RenderParams& p,
+                             const long long* prefix_override = nullptr) {
 	if (n_ctx <= 0 || n_rec <= 0 || !ctx || !rec) return fail("render: need at least one context and one recorder");
 	for (int32_t c = 0; c < n_ctx; ++c) {
 		if (ctx[c].band < 0 || ctx[c].band >= s->n_bands) return fail("render: context band outside the material table");
@@ -559,6 +640,7 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 		cnt = std::max<long long>(0, std::min<long long>(cnt, (long long)ctx[c].num_samples - first));
 		prefix[c + 1] = prefix[c] + cnt;
 	}
+	if (prefix_override) for (int32_t c = 0; c <= n_ctx; ++c) prefix[c] = prefix_override[c];
 	CUDA_TRY(cudaMemcpyAsync(s->d_ctx, ctx, sizeof(ear_b200_context) * n_ctx, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_prefix, prefix.data(), sizeof(long long) * (n_ctx + 1), cudaMemcpyHostToDevice, stream));
@@ -573,24 +655,115 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	return 0;
 }
 
-static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
-	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
-	if (p.total_work > 0) {
-		int blocks_per_sm = 0;
-		if (s->dev.exact) CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel<true>, kBlock, kStackBytes));
-		else CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, render_kernel<false>, kBlock, kStackBytes));
-		const long long want = (p.total_work + kBlock - 1) / kBlock;
-		const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)s->sm_count * std::max(1, blocks_per_sm)));
-		if (s->dev.exact) render_kernel<true><<<grid, kBlock, kStackBytes, stream>>>(s->dev, p);
-		else render_kernel<false><<<grid, kBlock, kStackBytes, stream>>>(s->dev, p);
+static void harvest_events(ear_b200_scene* s) {
+	for (size_t i = 0; i < s->ev_used; ++i) {
+		float ms = 0.0f;
+		if (cudaEventElapsedTime(&ms, s->ev_pool[i].a, s->ev_pool[i].b) == cudaSuccess) s->stats.ms[s->ev_pool[i].cls] += ms;
+	}
+	s->ev_used = 0;
+}
+struct LaunchTimer {   // records an event pair around one launch
+	ear_b200_scene* s; cudaStream_t stream; size_t slot;
+	LaunchTimer(ear_b200_scene* sc, cudaStream_t st, int cls) : s(sc), stream(st) {
+		if (s->ev_used == s->ev_pool.size()) {
+			ear_b200_scene::Timed t; cudaEventCreate(&t.a); cudaEventCreate(&t.b); t.cls = cls; s->ev_pool.push_back(t);
+		}
+		slot = s->ev_used++;
+		s->ev_pool[slot].cls = cls;
+		++s->stats.launches[cls];
+		s->last_stream = stream;
+		cudaEventRecord(s->ev_pool[slot].a, stream);
+	}
+	~LaunchTimer() { cudaEventRecord(s->ev_pool[slot].b, stream); }
+};
+
+// Fused single-kernel engine.
+static int32_t launch_mega(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
+	void (*kern)(SceneDev, RenderParams) = nullptr;
+	if (s->dev.exact) kern = render_kernel<true, 4>;
+	else if (s->min_blocks == 4) kern = render_kernel<false, 4>;
+	else if (s->min_blocks == 6) kern = render_kernel<false, 6>;
+	else kern = render_kernel<false, 5>;
+	int blocks_per_sm = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, kStackBytes));
+	const long long want = (p.total_work + kBlock - 1) / kBlock;
+	const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)s->sm_count * std::max(1, blocks_per_sm)));
+	{ LaunchTimer t(s, stream, 4); kern<<<grid, kBlock, kStackBytes, stream>>>(s->dev, p); }
+	CUDA_TRY(cudaGetLastError());
+	return 0;
+}
+
+static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
+	WfPool& pl = s->pool;
+	if (slots > s->pool_slots) {
+		cudaFree(pl.ro); cudaFree(pl.rd); cudaFree(pl.rm); cudaFree(pl.hit); cudaFree(pl.sh0); cudaFree(pl.sh1); cudaFree(pl.sh2);
+		cudaFree(pl.trav_list);
+		CUDA_TRY(cudaMalloc(&pl.ro, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.rd, slots * sizeof(float4)));
+		CUDA_TRY(cudaMalloc(&pl.rm, slots * sizeof(uint4))); CUDA_TRY(cudaMalloc(&pl.hit, slots * sizeof(int2)));
+		CUDA_TRY(cudaMalloc(&pl.sh0, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.sh1, slots * sizeof(float4)));
+		CUDA_TRY(cudaMalloc(&pl.sh2, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.trav_list, slots * sizeof(int)));
+		s->pool_slots = slots;
+	}
+	if (queries > s->pool_queries) {
+		cudaFree(pl.q_list); cudaFree(pl.vis_list);
+		CUDA_TRY(cudaMalloc(&pl.q_list, queries * sizeof(uint2))); CUDA_TRY(cudaMalloc(&pl.vis_list, queries * sizeof(uint2)));
+		s->pool_queries = queries;
+	}
+	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
+	return 0;
+}
+
+// Wavefront engine: shade -> closest -> any-hit -> splat per iteration until no ray is left.
+// Asynchronous except for one tiny host read every `check_every` iterations (the loop must know when to stop).
+static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
+	if (p.n_rec > 255) return fail("render: more than 255 recorders per context are not supported");
+	if (p.n_ctx > 65535) return fail("render: more than 65535 contexts per call are not supported");
+	long long slots = std::min<long long>(std::max<long long>(p.total_work, 1), s->max_slots);
+	slots = (slots + 255) / 256 * 256;
+	if (int32_t rc = ensure_pool(s, (size_t)slots, (size_t)slots * std::max(1, p.n_rec))) return rc;
+	WfPool pl = s->pool;
+	pl.n_slots = (int)slots;
+	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
+	void (*closest)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<false, true> : wf_traverse_kernel<false, false>;
+	void (*anyhit)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<true, true> : wf_traverse_kernel<true, false>;
+	int bps = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, closest, kBlock, kStackBytes));
+	const int trav_grid = s->sm_count * std::max(1, bps);
+	const int shade_grid = (int)(slots / 256);
+	const int splat_grid = s->sm_count * 8;
+	// upper bound on iterations: every slot hosts ceil(work/slots) rays of at most max_bounces iterations each
+	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 1) + 2;
+	for (long long it = 0; it < max_iter;) {
+		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
+			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
+			{ LaunchTimer t(s, stream, 0); wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p); }
+			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
+			if (p.n_rec > 0) {
+				{ LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
+				{ LaunchTimer t(s, stream, 3); wf_splat_kernel<<<splat_grid, 256, 0, stream>>>(pl, p); }
+			}
+			++s->stats.iterations;
+		}
 		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaMemcpyAsync(s->h_counts, pl.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		harvest_events(s);
+		if (s->h_counts[0] == 0) break;   // nothing left to trace after the last shade
 	}
 	return 0;
+}
+
+static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
+	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
+	if (p.total_work <= 0) return 0;
+	return s->engine == 1 ? launch_mega(s, p, stream) : launch_wavefront(s, p, stream);
 }
 
 static int32_t launch_finalise(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
 	const int n_tracks = p.n_ctx * p.n_rec * 2;
 	dim3 grid(64, n_tracks);
+	LaunchTimer t(s, stream, 5);
+	s->stats.launches[5] += 2;
 	scale_kernel<<<grid, 256, 0, stream>>>(p, 0);
 	if (s->dev.exact) direct_kernel<true><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
 	else direct_kernel<false><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
@@ -678,6 +851,20 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	return 0;
 }
 
+extern "C" int32_t ear_b200_scene_stats(ear_b200_scene* s, ear_b200_stats* out) {
+	if (!s || !out) return fail("scene_stats: null argument");
+	CUDA_TRY(cudaSetDevice(s->device));
+	if (s->ev_used) { CUDA_TRY(cudaStreamSynchronize(s->last_stream)); harvest_events(s); }
+	*out = s->stats;
+	return 0;
+}
+extern "C" void ear_b200_scene_stats_reset(ear_b200_scene* s) {
+	if (!s) return;
+	cudaSetDevice(s->device);
+	if (s->ev_used) { cudaStreamSynchronize(s->last_stream); harvest_events(s); }
+	s->stats = ear_b200_stats{};
+}
+
 extern "C" void ear_b200_result_free(ear_b200_result* r) {
 	if (!r) return;
 	if (r->tracks) {
@@ -692,21 +879,32 @@ extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_contex
                                         const ear_b200_options* opt, int64_t n, int32_t* hits, float* final_state) {
 	if (!s || !ctx || !opt || !hits) return fail("trace_paths: null argument");
 	if (n <= 0) return 0;
+	if (ctx_index < 0 || ctx_index > 65535) return fail("trace_paths: context index out of range");
 	CUDA_TRY(cudaSetDevice(s->device));
 	const int max_b = opt->max_bounces > 0 ? opt->max_bounces : 1000;
-	// the kernel indexes contexts by ctx_index (it keys the Philox stream): place ctx there
+	// the Philox stream is keyed by the context's index: place ctx there, give it all the work
 	std::vector<ear_b200_context> cs(ctx_index + 1, *ctx);
 	ear_b200_recorder dummy{}; dummy.kind = EAR_B200_MONO;
 	std::vector<ear_b200_recorder> rs(ctx_index + 1, dummy);
-	ear_b200_options o2 = *opt; o2.ray_count = 0;
+	std::vector<long long> prefix(ctx_index + 2, 0);
+	prefix[ctx_index + 1] = n;
 	RenderParams p{};
-	if (int32_t rc = upload_params(s, cs.data(), ctx_index + 1, rs.data(), 1, &o2, s->stream, p)) return rc;
+	if (int32_t rc = upload_params(s, cs.data(), ctx_index + 1, rs.data(), 1, opt, s->stream, p, prefix.data())) return rc;
 	p.first_ray = opt->first_ray;
 	int32_t* d_hits = nullptr; float* d_state = nullptr;
 	CUDA_TRY(cudaMalloc(&d_hits, (size_t)n * max_b * 4)); CUDA_TRY(cudaMalloc(&d_state, (size_t)n * 32));
 	CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)n * 32, s->stream));
-	if (s->dev.exact) paths_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
-	else paths_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+	if (s->engine == 0) {
+		wf_fill_int_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(d_hits, (long long)n * max_b, -2);
+		CUDA_TRY(cudaMemsetAsync(s->d_scratch_counters, 0, 8 * sizeof(unsigned long long), s->stream));
+		p.n_rec = 0;   // paths only: no occlusion queries, nothing recorded
+		p.hits = d_hits; p.final_state = d_state; p.counters = s->d_scratch_counters;
+		if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
+	} else {
+		CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), s->stream));
+		if (s->dev.exact) paths_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+		else paths_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
+	}
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(hits, d_hits, (size_t)n * max_b * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (final_state) CUDA_TRY(cudaMemcpyAsync(final_state, d_state, (size_t)n * 32, cudaMemcpyDeviceToHost, s->stream));

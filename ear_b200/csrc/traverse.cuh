@@ -28,12 +28,14 @@ struct SceneDev {
 	int32_t n_tris, n_materials, n_bands;
 	float s0;                 // absolute interval margin (see bvh_build.cpp)
 	int32_t exact;            // 1: rigorous per-child slack
+	int32_t leaf_vote;        // lanes that must wait on a leaf before the warp runs a leaf step
+	int32_t fetch_vote;       // idle lanes that trigger a fetch of new work in the persistent kernels
 };
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
 constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes spill to local memory
 constexpr int kStackSpill = 40;
-constexpr int kLeafVote = 12;           // do a leaf step once this many lanes wait on a leaf
+constexpr int kLeafVote = 8;           // do a leaf step once this many lanes wait on a leaf
 constexpr float kKappa = 1.0f / 1024.0f;
 
 struct F8 { float4 lo, hi; };
@@ -81,102 +83,122 @@ struct LaneStack {
 	}
 };
 
-// Warp-synchronous traversal; must be called by all 32 lanes of the warp (inactive lanes pass
-// active = false).
+// Per-lane traversal state shared by the warp-synchronous drivers (traverse_warp below and the
+// persistent wavefront kernels in wavefront.cuh).
+struct TravState {
+	int32_t node;        // >= 0 inner node, < 0 leaf, kEmptyChildDev: nothing (left) to do
+	float best_t;
+	int32_t best_idx;    // closest: original triangle index or -1; any-hit: 1 once occluded
+	int32_t best_slot;   // closest: triangle record slot of the winner
+	V3 o, d;
+	RaySetup rs;
+	LaneStack st;
+	template <bool ANY_HIT>
+	__device__ __forceinline__ void begin(V3 origin, V3 dir) {
+		o = origin; d = dir; rs = make_setup(origin, dir);
+		node = 0; st.sp = 0;
+		best_idx = ANY_HIT ? 0 : -1;
+		best_t = ANY_HIT ? 1.0f : 1000000.0f;
+		best_slot = -1;
+	}
+};
+
+template <bool EXACT>
+__device__ __forceinline__ void pop_next(const SceneDev& sc, TravState& ts) {
+	ts.node = kEmptyChildDev;
+	const float limit = EXACT ? ts.best_t : fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
+	while (ts.st.sp > 0) {
+		const int2 e = ts.st.pop();
+		if (__int_as_float(e.y) <= limit) { ts.node = e.x; break; }
+	}
+}
+
+// one inner-node step for a lane sitting on an inner node
+template <bool EXACT>
+__device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
+	const F8 n0 = ldg256(sc.nodes + 4 * (size_t)ts.node);
+	const F8 n1 = ldg256(sc.nodes + 4 * (size_t)ts.node + 2);
+	const float4 a = n0.lo, b = n0.hi, c = n1.lo;
+	const int32_t c0 = __float_as_int(n1.hi.x), c1 = __float_as_int(n1.hi.y);
+	const RaySetup& rs = ts.rs;
+	// ray interval: relative margin (default) or rigorous per-child slack
+	const float hi_rel = fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
+	const float hi0 = EXACT ? ts.best_t + n1.hi.z : hi_rel, hi1 = EXACT ? ts.best_t + n1.hi.w : hi_rel;
+	const float lo0 = EXACT ? -n1.hi.z : -sc.s0, lo1 = EXACT ? -n1.hi.w : -sc.s0;
+	const float x00 = fmaf(a.x, rs.idx, -rs.oox), x01 = fmaf(a.y, rs.idx, -rs.oox);
+	const float y00 = fmaf(a.z, rs.idy, -rs.ooy), y01 = fmaf(a.w, rs.idy, -rs.ooy);
+	const float z00 = fmaf(c.x, rs.idz, -rs.ooz), z01 = fmaf(c.y, rs.idz, -rs.ooz);
+	const float x10 = fmaf(b.x, rs.idx, -rs.oox), x11 = fmaf(b.y, rs.idx, -rs.oox);
+	const float y10 = fmaf(b.z, rs.idy, -rs.ooy), y11 = fmaf(b.w, rs.idy, -rs.ooy);
+	const float z10 = fmaf(c.z, rs.idz, -rs.ooz), z11 = fmaf(c.w, rs.idz, -rs.ooz);
+	const float tn0 = fmaxf(fmaxf(fminf(x00, x01), fminf(y00, y01)), fmaxf(fminf(z00, z01), lo0));
+	const float tf0 = fminf(fminf(fmaxf(x00, x01), fmaxf(y00, y01)), fminf(fmaxf(z00, z01), hi0));
+	const float tn1 = fmaxf(fmaxf(fminf(x10, x11), fminf(y10, y11)), fmaxf(fminf(z10, z11), lo1));
+	const float tf1 = fminf(fminf(fmaxf(x10, x11), fmaxf(y10, y11)), fminf(fmaxf(z10, z11), hi1));
+	const bool h0 = c0 != kEmptyChildDev && tn0 <= tf0;
+	const bool h1 = c1 != kEmptyChildDev && tn1 <= tf1;
+	// stack key: entry distance (minus the child's slack in EXACT mode), compared with the limit on pop
+	const float k0 = EXACT ? tn0 - n1.hi.z : tn0, k1 = EXACT ? tn1 - n1.hi.w : tn1;
+	if (h0 && h1) {
+		const bool swap = tn1 < tn0;
+		ts.node = swap ? c1 : c0;
+		ts.st.push(swap ? c0 : c1, swap ? k0 : k1);
+	} else if (h0) ts.node = c0;
+	else if (h1) ts.node = c1;
+	else pop_next<EXACT>(sc, ts);
+}
+
+// one leaf step (all triangles of the leaf) for a lane sitting on a leaf
+template <bool ANY_HIT, bool EXACT>
+__device__ __forceinline__ void leaf_step(const SceneDev& sc, TravState& ts) {
+	const int32_t code = ~ts.node;
+	const int32_t first = code >> 3, count = (code & 7) + 1;
+	for (int32_t i = 0; i < count; ++i) {
+		const float4* rec = sc.tris + 4 * (size_t)(first + i);
+		const F8 r01 = ldg256(rec);
+		const float4 r2 = __ldg(rec + 2);
+		float t;
+		if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
+			if (ANY_HIT) {
+				if (t > 1e-5f && t < 1.0f) ts.best_idx = 1;
+			} else {
+				const int32_t idx = __float_as_int(r01.lo.w);
+				// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
+				if (t > 0.001f && (t < ts.best_t || (t == ts.best_t && idx < ts.best_idx))) {
+					ts.best_t = t; ts.best_idx = idx; ts.best_slot = first + i;
+				}
+			}
+		}
+	}
+	if (ANY_HIT && ts.best_idx) ts.node = kEmptyChildDev;
+	else pop_next<EXACT>(sc, ts);
+}
+
+// Warp-synchronous traversal of one ray per lane; must be called by all 32 lanes of the warp
+// (inactive lanes pass active = false).
 // ANY_HIT = false: argmin over (t, original index) of triangles with MT hit and t > 0.001 (t < 1e6):
 //                  best_idx = original triangle index or -1, best_t, best_slot = record slot.
 // ANY_HIT = true : d is the UNNORMALISED segment x - p; best_idx = 1 as soon as a triangle has 1e-5 < t < 1.
 template <bool ANY_HIT, bool EXACT>
 __device__ __forceinline__ void traverse_warp(const SceneDev& sc, int2* stack_smem, int stack_stride, bool active, V3 o,
                                               V3 d, float& best_t, int32_t& best_idx, int32_t& best_slot) {
-	const RaySetup rs = make_setup(o, d);
-	LaneStack st;
-	st.smem = stack_smem; st.stride = stack_stride; st.sp = 0;
-	int32_t node = active ? 0 : kEmptyChildDev;
-	best_idx = ANY_HIT ? 0 : -1;
-	best_t = ANY_HIT ? 1.0f : 1000000.0f;
-	best_slot = -1;
-	const float lo_t = -sc.s0;
+	TravState ts;
+	ts.st.smem = stack_smem; ts.st.stride = stack_stride;
+	ts.begin<ANY_HIT>(o, d);
+	if (!active) ts.node = kEmptyChildDev;
 	for (;;) {
-		const bool inner = node >= 0 && node != kEmptyChildDev;
-		const bool leaf = node < 0;
+		const bool inner = ts.node >= 0 && ts.node != kEmptyChildDev;
+		const bool leaf = ts.node < 0;
 		const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
 		const unsigned m_leaf = __ballot_sync(0xffffffffu, leaf);
 		if ((m_inner | m_leaf) == 0u) break;
-		if (m_inner != 0u && __popc(m_leaf) < kLeafVote) {
-			// ---------------- node step ----------------
-			if (inner) {
-				const F8 n0 = ldg256(sc.nodes + 4 * (size_t)node);
-				const F8 n1 = ldg256(sc.nodes + 4 * (size_t)node + 2);
-				const float4 a = n0.lo, b = n0.hi, c = n1.lo;
-				const int32_t c0 = __float_as_int(n1.hi.x), c1 = __float_as_int(n1.hi.y);
-				// interval upper ends: relative (default) or rigorous per-child slack
-				const float hi_rel = fmaf(best_t, kKappa, best_t) + sc.s0;
-				const float hi0 = EXACT ? best_t + n1.hi.z : hi_rel, hi1 = EXACT ? best_t + n1.hi.w : hi_rel;
-				const float lo0 = EXACT ? -n1.hi.z : lo_t, lo1 = EXACT ? -n1.hi.w : lo_t;
-				const float x00 = fmaf(a.x, rs.idx, -rs.oox), x01 = fmaf(a.y, rs.idx, -rs.oox);
-				const float y00 = fmaf(a.z, rs.idy, -rs.ooy), y01 = fmaf(a.w, rs.idy, -rs.ooy);
-				const float z00 = fmaf(c.x, rs.idz, -rs.ooz), z01 = fmaf(c.y, rs.idz, -rs.ooz);
-				const float x10 = fmaf(b.x, rs.idx, -rs.oox), x11 = fmaf(b.y, rs.idx, -rs.oox);
-				const float y10 = fmaf(b.z, rs.idy, -rs.ooy), y11 = fmaf(b.w, rs.idy, -rs.ooy);
-				const float z10 = fmaf(c.z, rs.idz, -rs.ooz), z11 = fmaf(c.w, rs.idz, -rs.ooz);
-				const float tn0 = fmaxf(fmaxf(fminf(x00, x01), fminf(y00, y01)), fmaxf(fminf(z00, z01), lo0));
-				const float tf0 = fminf(fminf(fmaxf(x00, x01), fmaxf(y00, y01)), fminf(fmaxf(z00, z01), hi0));
-				const float tn1 = fmaxf(fmaxf(fminf(x10, x11), fminf(y10, y11)), fmaxf(fminf(z10, z11), lo1));
-				const float tf1 = fminf(fminf(fmaxf(x10, x11), fmaxf(y10, y11)), fminf(fmaxf(z10, z11), hi1));
-				const bool h0 = c0 != kEmptyChildDev && tn0 <= tf0;
-				const bool h1 = c1 != kEmptyChildDev && tn1 <= tf1;
-				// stack key: distance at which the child stops being interesting (compared with best_t on pop)
-				const float k0 = EXACT ? tn0 - n1.hi.z : tn0, k1 = EXACT ? tn1 - n1.hi.w : tn1;
-				if (h0 && h1) {
-					const bool swap = tn1 < tn0;
-					node = swap ? c1 : c0;
-					st.push(swap ? c0 : c1, swap ? k0 : k1);
-				} else if (h0) node = c0;
-				else if (h1) node = c1;
-				else {
-					node = kEmptyChildDev;
-					const float limit = EXACT ? best_t : hi_rel;
-					while (st.sp > 0) {
-						const int2 e = st.pop();
-						if (__int_as_float(e.y) <= limit) { node = e.x; break; }
-					}
-				}
-			}
+		if (m_inner != 0u && __popc(m_leaf) < sc.leaf_vote) {
+			if (inner) node_step<EXACT>(sc, ts);
 		} else {
-			// ---------------- leaf step ----------------
-			if (leaf) {
-				const int32_t code = ~node;
-				const int32_t first = code >> 3, count = (code & 7) + 1;
-				for (int32_t i = 0; i < count; ++i) {
-					const float4* rec = sc.tris + 4 * (size_t)(first + i);
-					const F8 r01 = ldg256(rec);
-					const float4 r2 = __ldg(rec + 2);
-					float t;
-					if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z),
-					                     o, d, t)) {
-						if (ANY_HIT) {
-							if (t > 1e-5f && t < 1.0f) best_idx = 1;
-						} else {
-							const int32_t idx = __float_as_int(r01.lo.w);
-							// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
-							if (t > 0.001f && (t < best_t || (t == best_t && idx < best_idx))) {
-								best_t = t; best_idx = idx; best_slot = first + i;
-							}
-						}
-					}
-				}
-				node = kEmptyChildDev;
-				if (!(ANY_HIT && best_idx)) {
-					const float limit = EXACT ? best_t : fmaf(best_t, kKappa, best_t) + sc.s0;
-					while (st.sp > 0) {
-						const int2 e = st.pop();
-						if (__int_as_float(e.y) <= limit) { node = e.x; break; }
-					}
-				}
-			}
+			if (leaf) leaf_step<ANY_HIT, EXACT>(sc, ts);
 		}
 	}
+	best_t = ts.best_t; best_idx = ts.best_idx; best_slot = ts.best_slot;
 }
 
 }  // namespace earb

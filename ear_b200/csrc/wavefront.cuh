@@ -1,0 +1,368 @@
+// Wavefront engine for Scene::Render's bounce loop (src/Scene.cpp:124-284).
+//
+// Rays live in a pool of N slots in global memory (SoA, 16-byte vectors).  One ITERATION advances every
+// live ray by one bounce through four kernels; all hand-offs are device-side lists built with warp
+// ballots + one atomic per warp, so nothing returns to the host between bounces:
+//
+//   wf_shade_kernel     K3 + K6 + K1: consume last iteration's hit (material, reflect / transmit, resample,
+//                       air + surface absorption, cut-offs), write the shading record, enqueue one
+//                       occlusion query per facing recorder, REFILL dead slots from the global ray queue
+//                       (emission), and compact the slots that still need a closest-hit query into trav_list
+//   wf_traverse<false>  K2: persistent closest-hit traversal over trav_list  (Mesh::RayIntersection)
+//   wf_traverse<true>   K4: persistent any-hit traversal over q_list        (Scene::Connect); visible
+//                       queries are compacted into vis_list
+//   wf_splat_kernel     K5: contribution weight + Recorder::Record for every visible query
+//
+// The traversal kernels carry ONLY traversal state (about 56 registers), so many warps are
+// resident to hide the L2 latency of the node fetches, and lanes that finish early fetch the next ray from
+// the list instead of waiting for the slowest lane of their warp (vote-driven: node step / leaf step /
+// fetch, whichever the warp needs).  The fused single-kernel version this replaces held the whole ray
+// state in registers (120 regs, 16 warps/SM) and averaged 11 of 32 lanes per instruction.
+#pragma once
+#include "traverse.cuh"
+
+namespace earb {
+
+struct WfPool {
+	float4* ro;         // [N] origin.xyz, intensity
+	float4* rd;         // [N] direction.xyz, path length
+	uint4* rm;          // [N] ray id lo, ray id hi, context | bounce << 16 (bounce 0 = empty slot), Philox draw index
+	int2* hit;          // [N] (t bits, triangle record slot or -1), written by the closest-hit kernel
+	float4* sh0;        // [N] hit point.xyz, intensity after the surface            } shading record of the bounce
+	float4* sh1;        // [N] facing normal.xyz, path length up to the hit point    } whose occlusion queries are
+	float4* sh2;        // [N] incoming unit direction.xyz, specularity (sign bit set: transmitted)  } in flight
+	int* trav_list;     // [N] slots that need a closest-hit query
+	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
+	uint2* vis_list;    // [N*R] the unoccluded ones
+	int* counts;        // 0 trav_count, 1 q_count, 2 vis_count, 3 trav_cursor, 4 q_cursor
+	const float4* qx;   // harness only: explicit segment end point per query (else the recorder position)
+	int n_slots;
+};
+
+constexpr int kSlotBits = 24;
+constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
+
+// ---------------------------------------------------------------------------------------------------
+// K2 / K4: persistent traversal with dynamic fetch
+// ---------------------------------------------------------------------------------------------------
+template <bool ANY_HIT, bool EXACT>
+__global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+	extern __shared__ int2 stack_smem[];
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const int total = ANY_HIT ? pool.counts[1] : pool.counts[0];
+	int* cursor = pool.counts + (ANY_HIT ? 4 : 3);
+	TravState ts;
+	ts.st.smem = stack_smem + threadIdx.x; ts.st.stride = blockDim.x; ts.st.sp = 0;
+	ts.node = kEmptyChildDev;
+	ts.best_t = 0.0f; ts.best_idx = 0; ts.best_slot = -1;
+	ts.o = mk(0, 0, 0); ts.d = mk(0, 0, 0); ts.rs = make_setup(ts.o, ts.d);
+	bool has_job = false, exhausted = total <= 0;
+	uint2 job = make_uint2(0u, 0u);   // closest: x = slot; any-hit: the query
+	for (;;) {
+		const bool inner = ts.node >= 0 && ts.node != kEmptyChildDev;
+		const bool leaf = ts.node < 0;
+		const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
+		const unsigned m_leaf = __ballot_sync(0xffffffffu, leaf);
+		const unsigned m_idle = ~(m_inner | m_leaf);
+		const bool busy = (m_inner | m_leaf) != 0u;
+		if (!exhausted && (__popc(m_idle) >= sc.fetch_vote || !busy)) {
+			// ---------------- retire finished lanes, fetch new work ----------------
+			const bool idle = !inner && !leaf;
+			if (ANY_HIT) {
+				const bool visible = idle && has_job && ts.best_idx == 0;
+				const unsigned m_vis = __ballot_sync(0xffffffffu, visible);
+				if (m_vis) {
+					int base = 0;
+					if (lane == 0) base = atomicAdd(pool.counts + 2, __popc(m_vis));
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (visible) pool.vis_list[base + __popc(m_vis & lt_mask)] = job;
+				}
+			} else if (idle && has_job) {
+				pool.hit[job.x] = make_int2(__float_as_int(ts.best_t), ts.best_slot);
+			}
+			int base = 0;
+			const int want = __popc(m_idle);
+			if (lane == 0) base = atomicAdd(cursor, want);
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (base + want >= total) exhausted = true;
+			if (idle) {
+				const int my = base + __popc(m_idle & lt_mask);
+				has_job = my < total;
+				if (has_job) {
+					if (ANY_HIT) {
+						job = pool.q_list[my];
+						const uint32_t slot = job.x & kSlotMask, r = job.x >> kSlotBits, c = job.y & 0xffffu;
+						const float4 s0 = pool.sh0[slot];
+						V3 x;
+						if (pool.qx) { const float4 e = pool.qx[my]; x = mk(e.x, e.y, e.z); }
+						else { const float* rp = p.rec[(size_t)c * p.n_rec + r].position; x = mk(rp[0], rp[1], rp[2]); }
+						const V3 pnt = mk(s0.x, s0.y, s0.z);
+						ts.begin<true>(pnt, vsub(x, pnt));   // LineSeg(p, x) = Ray(p, x - p)
+					} else {
+						job.x = (uint32_t)pool.trav_list[my];
+						const float4 o4 = pool.ro[job.x], d4 = pool.rd[job.x];
+						ts.begin<false>(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
+					}
+				}
+			}
+			continue;
+		}
+		if (!busy) {
+			// exhausted and nothing in flight: retire what is left and leave
+			if (ANY_HIT) {
+				const bool visible = has_job && ts.best_idx == 0;
+				const unsigned m_vis = __ballot_sync(0xffffffffu, visible);
+				if (m_vis) {
+					int base = 0;
+					if (lane == 0) base = atomicAdd(pool.counts + 2, __popc(m_vis));
+					base = __shfl_sync(0xffffffffu, base, 0);
+					if (visible) pool.vis_list[base + __popc(m_vis & lt_mask)] = job;
+				}
+			} else if (has_job) {
+				pool.hit[job.x] = make_int2(__float_as_int(ts.best_t), ts.best_slot);
+			}
+			break;
+		}
+		if (m_inner != 0u && __popc(m_leaf) < sc.leaf_vote) {
+			if (inner) node_step<EXACT>(sc, ts);
+		} else {
+			if (leaf) leaf_step<ANY_HIT, EXACT>(sc, ts);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K3 + K6 + K1: shade, refill, enqueue
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+	const int slot = blockIdx.x * blockDim.x + threadIdx.x;   // n_slots is a multiple of the block size
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	uint4 m = pool.rm[slot];
+	int bounce = (int)(m.z >> 16);
+	int c = (int)(m.z & 0xffffu);
+	bool alive = bounce != 0;
+	float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
+	bool shaded = false;
+	V3 n = mk(0, 0, 0), pnt = mk(0, 0, 0);
+	if (alive) {
+		ro = pool.ro[slot]; rd = pool.rd[slot];
+		const int2 h = pool.hit[slot];
+		const unsigned long long ray = ((unsigned long long)m.y << 32) | m.x;
+		const long long w = (long long)(ray - (unsigned long long)p.first_ray);   // PATHS: output row
+		++lc.segments;                                                            // one Scene::Bounce call
+		V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
+		float intensity = ro.w, path = rd.w;
+		if (p.hits) p.hits[w * p.max_bounces + bounce] = h.y >= 0 ? __float_as_int(__ldg(sc.tris + 4 * (size_t)h.y).w) : -1;
+		if (h.y < 0) alive = false;                                               // escaped (src/Scene.cpp:166)
+		else {
+			// ---- Scene::Bounce after the hit (src/Scene.cpp:60-82), then :154-175 ----
+			const float t = __int_as_float(h.x);
+			const float4 r1 = __ldg(sc.tris + 4 * (size_t)h.y + 1);
+			const float4 r3 = __ldg(sc.tris + 4 * (size_t)h.y + 3);
+			const V3 prev_dir = vnormalized(d);                                   // prev_ray_dir (:277) of this bounce
+			const V3 tri_n = mk(r3.x, r3.y, r3.z);
+			pnt = vadd(o, vscale(d, t));                                          // src/Mesh.cpp:48
+			n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;           // :49-53
+			const int band = p.ctx[c].band;
+			const float af = p.ctx[c].absorption_factor;
+			const float4 mat = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
+			Rng rng;
+			rng.start(p.seed, (uint32_t)c, ray, m.w);
+			// Material::Bounce (src/Material.cpp:76-83); its comparisons against 0.0001 are in double
+			bool refract;
+			if ((double)mat.x < 0.0001 && (double)mat.y < 0.0001) refract = false;
+			else refract = !(rng.unit1() <= fdiv(mat.x, fadd(mat.x, mat.y)));
+			const float spec = mat.w;
+			V3 v;
+			if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
+			else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
+			m.w = rng.block;
+			const float seg = vlength(vsub(pnt, o));
+			intensity = fmul(intensity, pow_ref(af, seg));                        // src/Scene.cpp:154
+			path = fadd(path, seg);
+			intensity = fmul(intensity, mat.z);                                   // :169-171
+			ro = make_float4(pnt.x, pnt.y, pnt.z, intensity);
+			rd = make_float4(v.x, v.y, v.z, path);
+			if (invalid_float(intensity)) alive = false;                          // :175
+			else {
+				shaded = p.n_rec > 0;
+				if (shaded) {
+					pool.sh0[slot] = ro;
+					pool.sh1[slot] = make_float4(n.x, n.y, n.z, path);
+					pool.sh2[slot] = make_float4(prev_dir.x, prev_dir.y, prev_dir.z,
+					                             refract ? __int_as_float(__float_as_int(spec) | (int)0x80000000) : spec);
+				}
+				if ((double)intensity < 0.00000001) alive = false;                // :275
+				else if (bounce + 1 >= p.max_bounces) alive = false;              // loop bound (:143)
+			}
+		}
+		if (!alive && p.final_state) {
+			float* fs = p.final_state + 8 * w;
+			fs[0] = ro.x; fs[1] = ro.y; fs[2] = ro.z; fs[3] = rd.x; fs[4] = rd.y; fs[5] = rd.z; fs[6] = ro.w; fs[7] = rd.w;
+		}
+	}
+	// ---- K4 enqueue: Scene::Connect is called for every recorder (src/Scene.cpp:188-195); its answer is only
+	// used when dot(lsdir, n) > 0 (:209), so only those queries are traced ----
+	for (int r = 0; r < p.n_rec; ++r) {
+		bool facing = false;
+		if (shaded) {
+			++lc.occlusion;
+			const float* x = p.rec[(size_t)c * p.n_rec + r].position;
+			const V3 lsdir = vnormalized(vsub(mk(x[0], x[1], x[2]), pnt));
+			facing = vdot(lsdir, n) > 0.0f;
+		}
+		const unsigned mq = __ballot_sync(0xffffffffu, facing);
+		if (mq) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (facing)
+				pool.q_list[base + __popc(mq & lt_mask)] =
+				    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
+		}
+	}
+	if (alive) ++bounce;
+	// ---- K6 + K1: dead slots take the next ray id of the shard and emit (AbstractSoundFile::SoundRay) ----
+	const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+	if (dead) {
+		unsigned long long base = 0;
+		const int want = __popc(dead);
+		if (lane == 0) {
+			base = *(volatile unsigned long long*)p.next_work;
+			if ((long long)base < p.total_work) base = atomicAdd(p.next_work, (unsigned long long)want);
+		}
+		base = __shfl_sync(0xffffffffu, base, 0);
+		const long long w = (long long)base + __popc(dead & lt_mask);
+		if (!alive) {
+			bounce = 0;
+			if (w < p.total_work) {
+				c = 0;
+				while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
+				const unsigned long long ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
+				Rng rng;
+				rng.start(p.seed, (uint32_t)c, ray, 0);
+				++lc.rays;
+				const float* sp = p.ctx[c].source_position;
+				const V3 d = sample_sphere(rng);
+				ro = make_float4(sp[0], sp[1], sp[2], 1.0f);
+				rd = make_float4(d.x, d.y, d.z, 0.0f);
+				m.x = (uint32_t)ray; m.y = (uint32_t)(ray >> 32); m.w = rng.block;
+				// bounce 0 of the reference loop records nothing for point sources (src/Scene.cpp:185)
+				bounce = 1;
+				alive = bounce < p.max_bounces;
+				if (!alive) {
+					bounce = 0;
+					if (p.final_state) {
+						float* fs = p.final_state + 8 * (long long)(ray - (unsigned long long)p.first_ray);
+						fs[0] = ro.x; fs[1] = ro.y; fs[2] = ro.z; fs[3] = rd.x; fs[4] = rd.y; fs[5] = rd.z; fs[6] = ro.w; fs[7] = rd.w;
+					}
+				}
+			}
+		}
+	}
+	m.z = (uint32_t)c | ((uint32_t)bounce << 16);
+	pool.rm[slot] = m;
+	if (alive) { pool.ro[slot] = ro; pool.rd[slot] = rd; }
+	// ---- compaction: slots that need a closest-hit query next ----
+	const unsigned live = __ballot_sync(0xffffffffu, alive);
+	if (live) {
+		int base = 0;
+		if (lane == 0) base = atomicAdd(pool.counts + 0, __popc(live));
+		base = __shfl_sync(0xffffffffu, base, 0);
+		if (alive) pool.trav_list[base + __popc(live & lt_mask)] = slot;
+	}
+	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
+	if (lane == 0 && (v0 | v1 | v2)) {
+		if (v0) atomicAdd(p.counters + 0, v0);
+		if (v1) atomicAdd(p.counters + 1, v1);
+		if (v2) atomicAdd(p.counters + 2, v2);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5: contribution weight (src/Scene.cpp:197-263) + Recorder::Record for every visible query
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) wf_splat_kernel(WfPool pool, RenderParams p) {
+	const int total = pool.counts[2];
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const uint2 q = pool.vis_list[i];
+		const uint32_t slot = q.x & kSlotMask, r = q.x >> kSlotBits, c = q.y & 0xffffu;
+		const float4 s0 = pool.sh0[slot], s1 = pool.sh1[slot], s2 = pool.sh2[slot];
+		const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
+		const V3 pnt = mk(s0.x, s0.y, s0.z), n = mk(s1.x, s1.y, s1.z), prev_dir = mk(s2.x, s2.y, s2.z);
+		const bool refract = (__float_as_uint(s2.w) >> 31) != 0u;   // sign bit carries the bounce type
+		const float spec = fabsf(s2.w);
+		const float intensity = s0.w, path = s1.w;
+		const float af = p.ctx[c].absorption_factor;
+		const V3 segv = vsub(mk(rec.position[0], rec.position[1], rec.position[2]), pnt);
+		const V3 lsdir = vnormalized(segv);
+		float factor;
+		if (!refract) {                                                              // :219-235
+			const V3 rv = vreflect(prev_dir, n);
+			const float diff = -vdot(n, prev_dir);
+			const float dsp = vdot(rv, lsdir);
+			const float specf = (0.0f < dsp) ? dsp : 0.0f;
+			factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+		} else {                                                                     // :236-247
+			const float diff = vdot(n, prev_dir);
+			const float dsp = vdot(prev_dir, lsdir);
+			const float specf = (0.0f < dsp) ? dsp : 0.0f;
+			factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+		}
+		float contrib = fmul(intensity, factor);
+		const float l = vlength(segv);                                               // :250
+		contrib = fmul(contrib, pow_ref(af, l));
+		contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
+		if (invalid_float(contrib)) continue;
+		if (q.y >> 31) contrib = fmul(contrib, -1.0f);                               // odd bounce (:257)
+		const size_t track = ((size_t)c * p.n_rec + r) * 2;
+		record(rec, p.hist + track * p.n_bins, p.range + track * 2, p.n_bins, lsdir, contrib, fdiv(fadd(path, l), 343.0f),
+		       fadd(path, l), p.ctx[c].band, lc);
+	}
+	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
+	if ((threadIdx.x & 31) == 0 && (v3 | v4 | v5)) {
+		atomicAdd(p.counters + 3, v3); atomicAdd(p.counters + 4, v4);
+		if (v5) atomicAdd(p.counters + 5, v5);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// H1 harness glue: explicit rays / segments through the same persistent traversal kernels
+// ---------------------------------------------------------------------------------------------------
+__global__ void wf_load_rays_kernel(WfPool pool, const float* origins, const float* dirs, int n) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	pool.ro[i] = make_float4(origins[3 * i], origins[3 * i + 1], origins[3 * i + 2], 1.0f);
+	pool.rd[i] = make_float4(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2], 0.0f);
+	pool.trav_list[i] = i;
+	if (i == 0) { pool.counts[0] = n; pool.counts[3] = 0; }
+}
+__global__ void wf_store_hits_kernel(SceneDev sc, WfPool pool, int n, int32_t* tri_index, float* t_out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const int2 h = pool.hit[i];
+	tri_index[i] = h.y >= 0 ? __float_as_int(__ldg(sc.tris + 4 * (size_t)h.y).w) : -1;
+	t_out[i] = __int_as_float(h.x);
+}
+__global__ void wf_load_segments_kernel(WfPool pool, float4* qx, const float* pp, const float* xx, int n, uint8_t* out) {
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	pool.sh0[i] = make_float4(pp[3 * i], pp[3 * i + 1], pp[3 * i + 2], 0.0f);
+	qx[i] = make_float4(xx[3 * i], xx[3 * i + 1], xx[3 * i + 2], 0.0f);
+	pool.q_list[i] = make_uint2((uint32_t)i, 0u);
+	out[i] = 1;   // occluded unless the traversal reports the query visible
+	if (i == 0) { pool.counts[1] = n; pool.counts[2] = 0; pool.counts[4] = 0; }
+}
+__global__ void wf_mark_visible_kernel(WfPool pool, uint8_t* out) {
+	const int total = pool.counts[2];
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[pool.vis_list[i].x & kSlotMask] = 0;
+}
+__global__ void wf_fill_int_kernel(int32_t* dst, long long n, int32_t v) {
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
+}
+
+}  // namespace earb

@@ -96,6 +96,16 @@ typedef struct ear_b200_result {
 	double bvh_build_ms;
 } ear_b200_result;
 
+/* Cumulative per-scene launch statistics of the trace engine (reset by ear_b200_scene_stats_reset).
+ * Kernel classes: 0 shade/refill/enqueue, 1 closest-hit traversal, 2 any-hit traversal, 3 splat,
+ * 4 fused single-kernel engine, 5 finalise (scale, direct).  ms[] are CUDA-event times on the launch stream. */
+typedef struct ear_b200_stats {
+	uint64_t launches[8];
+	double ms[8];
+	uint64_t iterations;
+	uint64_t reserved;
+} ear_b200_stats;
+
 const char* ear_b200_last_error(void);
 int32_t ear_b200_abi_version(void);
 int32_t ear_b200_device_count(void);
@@ -145,6 +155,9 @@ int32_t ear_b200_finalise_device(ear_b200_scene* scene, const ear_b200_context* 
                                  float* d_hist, uint32_t* d_range, void* stream);
 /* Bins per track the library would choose for these options (same rule as ear_b200_render). */
 int32_t ear_b200_default_bins(ear_b200_scene* scene, const ear_b200_options* opt);
+/* Launch counts and device time per kernel class since the last reset (synchronises the scene's last stream). */
+int32_t ear_b200_scene_stats(ear_b200_scene* scene, ear_b200_stats* out);
+void ear_b200_scene_stats_reset(ear_b200_scene* scene);
 
 #ifdef __cplusplus
 }
