@@ -233,59 +233,102 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 		if (len != 0.0f) { r.normal[0] = cx / len; r.normal[1] = cy / len; r.normal[2] = cz / len; }
 	}
 
-	// re-layout: depth-first, internal nodes only (leaves are folded into their parent's child slot)
+	// collapse to 4-wide nodes, quantise, lay out depth-first
 	out.nodes.clear();
-	out.nodes.reserve(std::max<int32_t>(n, 1));
+	out.nodes.reserve(std::max<int32_t>(n / 2, 1));
 	out.depth = 0;
-	struct Item { int32_t build_id, out_id, slot, depth; };
-	std::vector<Item> stack;
-	auto child_ref = [&](const BuildNode& c) -> int32_t {
-		if (c.count == 0) return kEmptyChild;
-		return encode_leaf(c.first, c.count);
+	auto half_up = [](float f) -> uint16_t {   // smallest fp16 >= f (f >= 0)
+		if (!(f > 0.0f)) return 0;
+		if (f >= 65504.0f) return 0x7bff;
+		uint32_t bits; std::memcpy(&bits, &f, 4);
+		int e = (int)((bits >> 23) & 0xff) - 127;
+		if (e < -14) {   // subnormal half: step 2^-24
+			const uint32_t q = (uint32_t)std::ceil(f * 16777216.0f);
+			return (uint16_t)std::min<uint32_t>(q, 0x400);
+		}
+		uint32_t man = bits & 0x7fffffu;
+		uint32_t h = (uint32_t)((e + 15) << 10) | (man >> 13);
+		if (man & 0x1fffu) ++h;   // round up; a carry walks into the exponent correctly
+		return (uint16_t)std::min<uint32_t>(h, 0x7bff);
 	};
-	auto set_box = [&](Node& nd, int slot, const BuildNode& c) {
-		Box bx = c.box;
-		if (c.left < 0 && c.count == 0) { for (int k = 0; k < 3; ++k) { bx.lo[k] = INFINITY; bx.hi[k] = -INFINITY; } }
-		float* xy = slot == 0 ? nd.a : nd.b;
-		xy[0] = bx.lo[0]; xy[1] = bx.hi[0]; xy[2] = bx.lo[1]; xy[3] = bx.hi[1];
-		nd.c[2 * slot] = bx.lo[2]; nd.c[2 * slot + 1] = bx.hi[2];
-		nd.slack[slot] = c.slack;
-	};
-	// the root is always internal so that traversal can start with a node fetch
-	BuildNode fake_root;
-	const BuildNode* root_node = &b.nodes[root];
-	BuildNode empty; empty.left = empty.right = -1; empty.first = 0; empty.count = 0; empty.slack = 0; empty.box.reset();
-	if (root_node->left < 0) {
-		// single-leaf (or empty) scene: wrap it
-		out.nodes.push_back(Node());
-		Node& nd = out.nodes[0];
+	auto emit_node = [&](int32_t out_id, const Box& bounds, const BuildNode* const* kids, int n_kids, const int32_t* refs) {
+		Node nd;
 		std::memset(&nd, 0, sizeof(nd));
-		set_box(nd, 0, *root_node); nd.child[0] = child_ref(*root_node);
-		set_box(nd, 1, empty); nd.child[1] = kEmptyChild;
+		double step[3];
+		for (int a = 0; a < 3; ++a) {
+			nd.lo[a] = bounds.lo[a];
+			const double ext = (double)bounds.hi[a] - (double)bounds.lo[a];
+			int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 255.0)) : -126;
+			e = std::max(-126, std::min(127, e));
+			while (e < 127 && std::ldexp(255.0, e) < ext) ++e;   // guard against log2 rounding
+			nd.ex[a] = (uint8_t)(e + 127);
+			step[a] = std::ldexp(1.0, e);
+		}
+		for (int k = 0; k < 4; ++k) {
+			if (k >= n_kids || refs[k] == kEmptyChild) {
+				nd.child[k] = kEmptyChild;
+				for (int a = 0; a < 3; ++a) { nd.q[a][k] = 255; nd.q[3 + a][k] = 0; }
+				nd.slack[k] = 0;
+				continue;
+			}
+			nd.child[k] = refs[k];
+			nd.slack[k] = half_up(kids[k]->slack);
+			for (int a = 0; a < 3; ++a) {
+				const double l = ((double)kids[k]->box.lo[a] - (double)nd.lo[a]) / step[a];
+				const double h = ((double)kids[k]->box.hi[a] - (double)nd.lo[a]) / step[a];
+				nd.q[a][k] = (uint8_t)std::max(0.0, std::min(255.0, std::floor(l)));
+				nd.q[3 + a][k] = (uint8_t)std::max(0.0, std::min(255.0, std::ceil(h)));
+			}
+		}
+		out.nodes[out_id] = nd;
+	};
+	BuildNode empty; empty.left = empty.right = -1; empty.first = 0; empty.count = 0; empty.slack = 0; empty.box.reset();
+	const BuildNode* root_node = &b.nodes[root];
+	out.nodes.push_back(Node());
+	if (root_node->left < 0) {
+		// single-leaf (or empty) scene: one node, one child, so traversal can always start with a node fetch
+		const BuildNode* kids[1] = {root_node};
+		const int32_t refs[1] = {root_node->count ? encode_leaf(root_node->first, root_node->count) : kEmptyChild};
+		Box bx = root_node->box;
+		if (!root_node->count) { for (int k = 0; k < 3; ++k) { bx.lo[k] = 0; bx.hi[k] = 0; } }
+		emit_node(0, bx, kids, 1, refs);
 		out.depth = 1;
-		(void)fake_root;
 		return;
 	}
-	out.nodes.push_back(Node());
-	stack.push_back({root, 0, -1, 1});
+	struct Item { int32_t build_id, out_id, depth; };
+	std::vector<Item> stack;
+	stack.push_back({root, 0, 1});
 	while (!stack.empty()) {
 		const Item it = stack.back();
 		stack.pop_back();
 		out.depth = std::max(out.depth, it.depth);
 		const BuildNode& bn = b.nodes[it.build_id];
-		const int32_t kids[2] = {bn.left, bn.right};
-		for (int s = 0; s < 2; ++s) {
-			const BuildNode& c = b.nodes[kids[s]];
-			Node& nd = out.nodes[it.out_id];
-			set_box(nd, s, c);
-			if (c.left < 0) nd.child[s] = child_ref(c);
+		// expand the inner child with the largest surface area until there are four children
+		int32_t kid_ids[4] = {bn.left, bn.right, -1, -1};
+		int n_kids = 2;
+		while (n_kids < 4) {
+			int best = -1; float best_area = -1.0f;
+			for (int k = 0; k < n_kids; ++k) {
+				const BuildNode& c = b.nodes[kid_ids[k]];
+				if (c.left >= 0 && c.box.half_area() > best_area) { best_area = c.box.half_area(); best = k; }
+			}
+			if (best < 0) break;
+			const BuildNode& c = b.nodes[kid_ids[best]];
+			kid_ids[best] = c.left;
+			kid_ids[n_kids++] = c.right;
+		}
+		const BuildNode* kids[4]; int32_t refs[4];
+		for (int k = 0; k < n_kids; ++k) {
+			const BuildNode& c = b.nodes[kid_ids[k]];
+			kids[k] = &c;
+			if (c.left < 0) refs[k] = c.count ? encode_leaf(c.first, c.count) : kEmptyChild;
 			else {
-				const int32_t id = (int32_t)out.nodes.size();
-				out.nodes[it.out_id].child[s] = id;
+				refs[k] = (int32_t)out.nodes.size();
 				out.nodes.push_back(Node());
-				stack.push_back({kids[s], id, s, it.depth + 1});
+				stack.push_back({kid_ids[k], refs[k], it.depth + 1});
 			}
 		}
+		emit_node(it.out_id, bn.box, kids, n_kids, refs);
 	}
 }
 

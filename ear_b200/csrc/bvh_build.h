@@ -7,17 +7,21 @@
 
 namespace earb {
 
-// One binary node, both children's boxes inline (64 bytes, four float4 loads):
-//   a = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-//   b = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   c = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-//   d = (child0, child1, slack0, slack1)   child >= 0: node index; child < 0: leaf, ~child = first*8 + (count-1)
-//                                          kEmptyChild: nothing there
-// slackN (float bits) widens the ray interval used to cull that child; see DESIGN.md "exactness".
+// One 4-wide node (64 bytes = two 256-bit loads).  The SAH tree is built binary and collapsed (largest-area
+// child expanded first); each child's padded box is quantised to 8 bits per plane inside the node's own
+// bounds, rounded OUTWARD, so a decoded box always contains the float box it came from:
+//   plane(q) = lo[a] + q * 2^(ex[a]-127)
+//   lo[3]      node bounds, low corner (float32)
+//   ex[3]      biased float exponents of the per-axis grid step (255 steps cover the extent)
+//   child[4]   >= 0: node index; < 0: leaf, ~child = first*8 + (count-1); kEmptyChild: nothing there
+//   q[p][k]    plane p (lo.x, lo.y, lo.z, hi.x, hi.y, hi.z) of child k; empty children are inverted (255 / 0)
+//   slack[4]   fp16, rounded up: per-child ray-interval widening of the EXACT mode (DESIGN.md "exactness")
 struct Node {
-	float a[4], b[4], c[4];
-	int32_t child[2];
-	float slack[2];
+	float lo[3];
+	uint8_t ex[3], pad;
+	int32_t child[4];
+	uint8_t q[6][4];
+	uint16_t slack[4];
 };
 static_assert(sizeof(Node) == 64, "node must be 64 bytes");
 

@@ -409,6 +409,7 @@ struct ear_b200_scene {
 	std::vector<float> materials;
 	int32_t n_tris = 0, n_materials = 0, n_bands = 0, n_nodes = 0, depth = 0;
 	float diagonal = 0.0f;
+	float lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0};
 	double bvh_build_ms = 0.0;
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
@@ -466,6 +467,7 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	s->n_tris = n_tris; s->n_materials = n_materials; s->n_bands = n_bands;
 	s->n_nodes = (int32_t)bvh.nodes.size(); s->depth = bvh.depth; s->diagonal = bvh.diagonal;
+	for (int k = 0; k < 3; ++k) { s->lo[k] = bvh.lo[k]; s->hi[k] = bvh.hi[k]; }
 	s->materials.assign(materials, materials + (size_t)n_materials * n_bands * 4);
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
@@ -512,6 +514,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
 	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
+	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins);
 	cudaFree(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -697,19 +700,27 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	WfPool& pl = s->pool;
 	if (slots > s->pool_slots) {
 		cudaFree(pl.ro); cudaFree(pl.rd); cudaFree(pl.rm); cudaFree(pl.hit); cudaFree(pl.sh0); cudaFree(pl.sh1); cudaFree(pl.sh2);
-		cudaFree(pl.trav_list);
+		cudaFree(pl.trav_list); cudaFree(pl.trav_tmp);
 		CUDA_TRY(cudaMalloc(&pl.ro, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.rd, slots * sizeof(float4)));
 		CUDA_TRY(cudaMalloc(&pl.rm, slots * sizeof(uint4))); CUDA_TRY(cudaMalloc(&pl.hit, slots * sizeof(int2)));
 		CUDA_TRY(cudaMalloc(&pl.sh0, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.sh1, slots * sizeof(float4)));
 		CUDA_TRY(cudaMalloc(&pl.sh2, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.trav_list, slots * sizeof(int)));
+		CUDA_TRY(cudaMalloc(&pl.trav_tmp, slots * sizeof(uint2)));
 		s->pool_slots = slots;
 	}
 	if (queries > s->pool_queries) {
-		cudaFree(pl.q_list); cudaFree(pl.vis_list);
+		cudaFree(pl.q_list); cudaFree(pl.vis_list); cudaFree(pl.q_tmp);
 		CUDA_TRY(cudaMalloc(&pl.q_list, queries * sizeof(uint2))); CUDA_TRY(cudaMalloc(&pl.vis_list, queries * sizeof(uint2)));
+		CUDA_TRY(cudaMalloc(&pl.q_tmp, queries * sizeof(uint2)));
 		s->pool_queries = queries;
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
+	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, 2 * kSortBins * sizeof(int)));
+	for (int k = 0; k < 3; ++k) {
+		pl.cell_origin[k] = s->lo[k];
+		const float ext = s->hi[k] - s->lo[k];
+		pl.cell_scale[k] = ext > 0.0f ? 16.0f / ext : 0.0f;
+	}
 	return 0;
 }
 
@@ -736,7 +747,14 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	for (long long it = 0; it < max_iter;) {
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
 			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
-			{ LaunchTimer t(s, stream, 0); wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p); }
+			CUDA_TRY(cudaMemsetAsync(pl.bins, 0, 2 * kSortBins * sizeof(int), stream));
+			{
+				LaunchTimer t(s, stream, 0);
+				s->stats.launches[0] += 2;
+				wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p);
+				wf_scan_kernel<<<2, 1024, 0, stream>>>(pl);
+				wf_scatter_kernel<<<s->sm_count * 8, 256, 0, stream>>>(pl);
+			}
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 			if (p.n_rec > 0) {
 				{ LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }

@@ -113,39 +113,62 @@ __device__ __forceinline__ void pop_next(const SceneDev& sc, TravState& ts) {
 	}
 }
 
-// one inner-node step for a lane sitting on an inner node
+__device__ __forceinline__ float half_bits_to_float(uint32_t h) {   // fp16 bits -> float (no inf/nan in the table)
+	const uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+	if (e == 0u) return (float)m * 5.9604645e-8f;                      // subnormal: m * 2^-24
+	return __int_as_float((int)(((e + 112u) << 23) | (m << 13)));
+}
+__device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) { const uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+__device__ __forceinline__ int32_t pick4(int32_t c0, int32_t c1, int32_t c2, int32_t c3, uint32_t k) {
+	return k == 0u ? c0 : k == 1u ? c1 : k == 2u ? c2 : c3;
+}
+
+// one inner-node step for a lane sitting on an inner (4-wide, 8-bit quantised) node
 template <bool EXACT>
 __device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
 	const F8 n0 = ldg256(sc.nodes + 4 * (size_t)ts.node);
 	const F8 n1 = ldg256(sc.nodes + 4 * (size_t)ts.node + 2);
-	const float4 a = n0.lo, b = n0.hi, c = n1.lo;
-	const int32_t c0 = __float_as_int(n1.hi.x), c1 = __float_as_int(n1.hi.y);
 	const RaySetup& rs = ts.rs;
-	// ray interval: relative margin (default) or rigorous per-child slack
+	const uint32_t ex = __float_as_uint(n0.lo.w);
+	// plane(q) = lo + q * 2^e  ->  t(q) = q * (2^e * idir) + (lo - o) * idir
+	const float ax = __int_as_float((int)((ex & 0xffu) << 23)) * rs.idx;
+	const float ay = __int_as_float((int)(((ex >> 8) & 0xffu) << 23)) * rs.idy;
+	const float az = __int_as_float((int)(((ex >> 16) & 0xffu) << 23)) * rs.idz;
+	const float bx = fmaf(n0.lo.x, rs.idx, -rs.oox), by = fmaf(n0.lo.y, rs.idy, -rs.ooy), bz = fmaf(n0.lo.z, rs.idz, -rs.ooz);
+	// entry / exit planes by direction sign (one select per axis per node instead of min/max per child)
+	const uint32_t qlx = __float_as_uint(n1.lo.x), qly = __float_as_uint(n1.lo.y), qlz = __float_as_uint(n1.lo.z);
+	const uint32_t qhx = __float_as_uint(n1.lo.w), qhy = __float_as_uint(n1.hi.x), qhz = __float_as_uint(n1.hi.y);
+	const bool ngx = rs.idx < 0.0f, ngy = rs.idy < 0.0f, ngz = rs.idz < 0.0f;
+	const uint32_t nx = ngx ? qhx : qlx, fx = ngx ? qlx : qhx;
+	const uint32_t ny = ngy ? qhy : qly, fy = ngy ? qly : qhy;
+	const uint32_t nz = ngz ? qhz : qlz, fz = ngz ? qlz : qhz;
 	const float hi_rel = fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
-	const float hi0 = EXACT ? ts.best_t + n1.hi.z : hi_rel, hi1 = EXACT ? ts.best_t + n1.hi.w : hi_rel;
-	const float lo0 = EXACT ? -n1.hi.z : -sc.s0, lo1 = EXACT ? -n1.hi.w : -sc.s0;
-	const float x00 = fmaf(a.x, rs.idx, -rs.oox), x01 = fmaf(a.y, rs.idx, -rs.oox);
-	const float y00 = fmaf(a.z, rs.idy, -rs.ooy), y01 = fmaf(a.w, rs.idy, -rs.ooy);
-	const float z00 = fmaf(c.x, rs.idz, -rs.ooz), z01 = fmaf(c.y, rs.idz, -rs.ooz);
-	const float x10 = fmaf(b.x, rs.idx, -rs.oox), x11 = fmaf(b.y, rs.idx, -rs.oox);
-	const float y10 = fmaf(b.z, rs.idy, -rs.ooy), y11 = fmaf(b.w, rs.idy, -rs.ooy);
-	const float z10 = fmaf(c.z, rs.idz, -rs.ooz), z11 = fmaf(c.w, rs.idz, -rs.ooz);
-	const float tn0 = fmaxf(fmaxf(fminf(x00, x01), fminf(y00, y01)), fmaxf(fminf(z00, z01), lo0));
-	const float tf0 = fminf(fminf(fmaxf(x00, x01), fmaxf(y00, y01)), fminf(fmaxf(z00, z01), hi0));
-	const float tn1 = fmaxf(fmaxf(fminf(x10, x11), fminf(y10, y11)), fmaxf(fminf(z10, z11), lo1));
-	const float tf1 = fminf(fminf(fmaxf(x10, x11), fmaxf(y10, y11)), fminf(fmaxf(z10, z11), hi1));
-	const bool h0 = c0 != kEmptyChildDev && tn0 <= tf0;
-	const bool h1 = c1 != kEmptyChildDev && tn1 <= tf1;
-	// stack key: entry distance (minus the child's slack in EXACT mode), compared with the limit on pop
-	const float k0 = EXACT ? tn0 - n1.hi.z : tn0, k1 = EXACT ? tn1 - n1.hi.w : tn1;
-	if (h0 && h1) {
-		const bool swap = tn1 < tn0;
-		ts.node = swap ? c1 : c0;
-		ts.st.push(swap ? c0 : c1, swap ? k0 : k1);
-	} else if (h0) ts.node = c0;
-	else if (h1) ts.node = c1;
-	else pop_next<EXACT>(sc, ts);
+	const uint32_t sl01 = __float_as_uint(n1.hi.z), sl23 = __float_as_uint(n1.hi.w);
+	uint32_t key[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int sh = 8 * k;
+		const float tnx = fmaf((float)((nx >> sh) & 0xffu), ax, bx), tfx = fmaf((float)((fx >> sh) & 0xffu), ax, bx);
+		const float tny = fmaf((float)((ny >> sh) & 0xffu), ay, by), tfy = fmaf((float)((fy >> sh) & 0xffu), ay, by);
+		const float tnz = fmaf((float)((nz >> sh) & 0xffu), az, bz), tfz = fmaf((float)((fz >> sh) & 0xffu), az, bz);
+		float slack = 0.0f;
+		if (EXACT) slack = half_bits_to_float(((k < 2 ? sl01 : sl23) >> (16 * (k & 1))) & 0xffffu);
+		const float lo_t = EXACT ? -slack : -sc.s0;
+		const float hi_t = EXACT ? ts.best_t + slack : hi_rel;
+		const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, lo_t));
+		const float tf = fminf(fminf(tfx, tfy), fminf(tfz, hi_t));
+		// sort key: entry distance (minus slack in EXACT mode), clamped at 0, low two mantissa bits = child slot;
+		// it only ever under-estimates the entry distance, so culling by it on pop stays conservative
+		const float kd = fmaxf(EXACT ? tn - slack : tn, 0.0f);
+		key[k] = (tn <= tf) ? ((__float_as_uint(kd) & ~3u) | (uint32_t)k) : 0xffffffffu;
+	}
+	cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
+	const int32_t c0 = __float_as_int(n0.hi.x), c1 = __float_as_int(n0.hi.y), c2 = __float_as_int(n0.hi.z), c3 = __float_as_int(n0.hi.w);
+	if (key[0] == 0xffffffffu) { pop_next<EXACT>(sc, ts); return; }
+	if (key[3] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[3] & 3u), __uint_as_float(key[3] & ~3u));
+	if (key[2] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[2] & 3u), __uint_as_float(key[2] & ~3u));
+	if (key[1] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[1] & 3u), __uint_as_float(key[1] & ~3u));
+	ts.node = pick4(c0, c1, c2, c3, key[0] & 3u);
 }
 
 // one leaf step (all triangles of the leaf) for a lane sitting on a leaf

@@ -31,7 +31,11 @@ struct WfPool {
 	float4* sh0;        // [N] hit point.xyz, intensity after the surface            } shading record of the bounce
 	float4* sh1;        // [N] facing normal.xyz, path length up to the hit point    } whose occlusion queries are
 	float4* sh2;        // [N] incoming unit direction.xyz, specularity (sign bit set: transmitted)  } in flight
-	int* trav_list;     // [N] slots that need a closest-hit query
+	int* trav_list;     // [N] slots that need a closest-hit query, binned by (direction octant, origin cell)
+	uint2* trav_tmp;    // [N] (slot, bin) as appended by the shade kernel, before binning
+	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
+	int* bins;          // [2][kSortBins] histogram -> offsets of the two counting sorts (closest rays, queries)
+	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
 	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
 	uint2* vis_list;    // [N*R] the unoccluded ones
 	int* counts;        // 0 trav_count, 1 q_count, 2 vis_count, 3 trav_cursor, 4 q_cursor
@@ -39,6 +43,7 @@ struct WfPool {
 	int n_slots;
 };
 
+constexpr int kSortBins = 32768;   // 15-bit keys: 3 octant bits (closest) or 3 recorder bits (queries) + 12 Morton cell bits
 constexpr int kSlotBits = 24;
 constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
 
@@ -133,6 +138,57 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K6 compaction with binning: the ray / query lists are counting-sorted by a 15-bit key so that lanes of a
+// warp (which fetch consecutive list entries) start in the same ~4 m cell and walk the same top of the BVH:
+// identical node addresses coalesce into one L1 wavefront, and all resident warps work on a narrow spatial
+// window of the scene at any time.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread4(uint32_t v) {   // 4 bits -> every third bit
+	return (v & 1u) | ((v & 2u) << 2) | ((v & 4u) << 4) | ((v & 8u) << 6);
+}
+__device__ __forceinline__ uint32_t cell_key(const WfPool& pool, float x, float y, float z) {
+	const int cx = min(15, max(0, (int)((x - pool.cell_origin[0]) * pool.cell_scale[0])));
+	const int cy = min(15, max(0, (int)((y - pool.cell_origin[1]) * pool.cell_scale[1])));
+	const int cz = min(15, max(0, (int)((z - pool.cell_origin[2]) * pool.cell_scale[2])));
+	return spread4((uint32_t)cx) | (spread4((uint32_t)cy) << 1) | (spread4((uint32_t)cz) << 2);   // 12-bit Morton code
+}
+// exclusive scan of the two histograms (block 0: closest rays, block 1: queries), in place
+__global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
+	__shared__ int warp_tot[32];
+	int* h = pool.bins + blockIdx.x * kSortBins;
+	constexpr int kPer = kSortBins / 1024;
+	int v[kPer];
+	int sum = 0;
+	for (int i = 0; i < kPer; ++i) { v[i] = h[threadIdx.x * kPer + i]; sum += v[i]; }
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	int inc = sum;
+	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) warp_tot[wid] = inc;
+	__syncthreads();
+	if (wid == 0) {
+		int w = warp_tot[lane];
+		for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+		warp_tot[lane] = w;
+	}
+	__syncthreads();
+	int run = inc - sum + (wid ? warp_tot[wid - 1] : 0);
+	for (int i = 0; i < kPer; ++i) { h[threadIdx.x * kPer + i] = run; run += v[i]; }
+}
+// scatter the appended entries to their bins (order inside a bin is arbitrary)
+__global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
+	const int n_trav = pool.counts[0], n_q = pool.counts[1];
+	const int stride = gridDim.x * blockDim.x;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_trav; i += stride) {
+		const uint2 e = pool.trav_tmp[i];
+		pool.trav_list[atomicAdd(pool.bins + e.y, 1)] = (int)e.x;
+	}
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += stride) {
+		const uint2 e = pool.q_tmp[i];
+		pool.q_list[atomicAdd(pool.bins + kSortBins + ((e.y >> 16) & 0x7fffu), 1)] = e;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K3 + K6 + K1: shade, refill, enqueue
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
@@ -219,9 +275,12 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool,
 			int base = 0;
 			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
 			base = __shfl_sync(0xffffffffu, base, 0);
-			if (facing)
-				pool.q_list[base + __popc(mq & lt_mask)] =
-				    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
+			if (facing) {
+				const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
+				atomicAdd(pool.bins + kSortBins + bin, 1);
+				pool.q_tmp[base + __popc(mq & lt_mask)] =
+				    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
+			}
 		}
 	}
 	if (alive) ++bounce;
@@ -272,7 +331,12 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool,
 		int base = 0;
 		if (lane == 0) base = atomicAdd(pool.counts + 0, __popc(live));
 		base = __shfl_sync(0xffffffffu, base, 0);
-		if (alive) pool.trav_list[base + __popc(live & lt_mask)] = slot;
+		if (alive) {
+			const uint32_t oct = (rd.x < 0.0f ? 1u : 0u) | (rd.y < 0.0f ? 2u : 0u) | (rd.z < 0.0f ? 4u : 0u);
+			const uint32_t bin = (oct << 12) | cell_key(pool, ro.x, ro.y, ro.z);
+			atomicAdd(pool.bins + bin, 1);
+			pool.trav_tmp[base + __popc(live & lt_mask)] = make_uint2((uint32_t)slot, bin);
+		}
 	}
 	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
 	if (lane == 0 && (v0 | v1 | v2)) {
