@@ -418,7 +418,7 @@ struct ear_b200_scene {
 	int max_slots = 1 << 20;        // rays in flight in the wavefront pool (EAR_B200_SLOTS)
 	int check_every = 8;            // iterations between host checks for completion
 	WfPool pool{};
-	size_t pool_slots = 0, pool_queries = 0;
+	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
 	int* h_counts = nullptr;        // pinned
 	unsigned long long* d_scratch_counters = nullptr;
 	ear_b200_stats stats{};
@@ -514,7 +514,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
 	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
-	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins);
+	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins); cudaFree(s->pool.ctx_log2af);
 	cudaFree(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -735,6 +735,13 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	WfPool pl = s->pool;
 	pl.n_slots = (int)slots;
 	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
+	if ((size_t)p.n_ctx > s->log2af_cap) {
+		cudaFree(s->pool.ctx_log2af);
+		CUDA_TRY(cudaMalloc(&s->pool.ctx_log2af, sizeof(double) * p.n_ctx));
+		s->log2af_cap = p.n_ctx;
+		pl.ctx_log2af = s->pool.ctx_log2af;
+	}
+	wf_ctx_table_kernel<<<(p.n_ctx + 127) / 128, 128, 0, stream>>>(pl, p);
 	void (*closest)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<false, true> : wf_traverse_kernel<false, false>;
 	void (*anyhit)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<true, true> : wf_traverse_kernel<true, false>;
 	int bps = 0;
@@ -743,7 +750,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	const int shade_grid = (int)(slots / 256);
 	const int splat_grid = s->sm_count * 8;
 	// upper bound on iterations: every slot hosts ceil(work/slots) rays of at most max_bounces iterations each
-	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 1) + 2;
+	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 2) + 4;
 	for (long long it = 0; it < max_iter;) {
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
 			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));

@@ -35,7 +35,7 @@ struct SceneDev {
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
 constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes spill to local memory
 constexpr int kStackSpill = 40;
-constexpr int kLeafVote = 8;           // do a leaf step once this many lanes wait on a leaf
+constexpr int kLeafVote = 12;           // do a leaf step once this many lanes wait on a leaf
 constexpr float kKappa = 1.0f / 1024.0f;
 
 struct F8 { float4 lo, hi; };
@@ -171,29 +171,30 @@ __device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
 	ts.node = pick4(c0, c1, c2, c3, key[0] & 3u);
 }
 
-// one leaf step (all triangles of the leaf) for a lane sitting on a leaf
+// one leaf step for a lane sitting on a leaf: tests ONE triangle and stays on the leaf while it has more, so a
+// warp's leaf round costs one triangle test whatever the leaf sizes are (a per-leaf loop idles the lanes with
+// short leaves while the longest one finishes)
 template <bool ANY_HIT, bool EXACT>
 __device__ __forceinline__ void leaf_step(const SceneDev& sc, TravState& ts) {
 	const int32_t code = ~ts.node;
-	const int32_t first = code >> 3, count = (code & 7) + 1;
-	for (int32_t i = 0; i < count; ++i) {
-		const float4* rec = sc.tris + 4 * (size_t)(first + i);
-		const F8 r01 = ldg256(rec);
-		const float4 r2 = __ldg(rec + 2);
-		float t;
-		if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
-			if (ANY_HIT) {
-				if (t > 1e-5f && t < 1.0f) ts.best_idx = 1;
-			} else {
-				const int32_t idx = __float_as_int(r01.lo.w);
-				// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
-				if (t > 0.001f && (t < ts.best_t || (t == ts.best_t && idx < ts.best_idx))) {
-					ts.best_t = t; ts.best_idx = idx; ts.best_slot = first + i;
-				}
+	const int32_t first = code >> 3, rest = code & 7;
+	const float4* rec = sc.tris + 4 * (size_t)first;
+	const F8 r01 = ldg256(rec);
+	const float4 r2 = __ldg(rec + 2);
+	float t;
+	if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
+		if (ANY_HIT) {
+			if (t > 1e-5f && t < 1.0f) ts.best_idx = 1;
+		} else {
+			const int32_t idx = __float_as_int(r01.lo.w);
+			// strict t < d in file order == lowest original index among equal t (src/Mesh.cpp:40)
+			if (t > 0.001f && (t < ts.best_t || (t == ts.best_t && idx < ts.best_idx))) {
+				ts.best_t = t; ts.best_idx = idx; ts.best_slot = first;
 			}
 		}
 	}
 	if (ANY_HIT && ts.best_idx) ts.node = kEmptyChildDev;
+	else if (rest > 0) ts.node = ~(((first + 1) << 3) | (rest - 1));
 	else pop_next<EXACT>(sc, ts);
 }
 

@@ -36,6 +36,7 @@ struct WfPool {
 	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
 	int* bins;          // [2][kSortBins] histogram -> offsets of the two counting sorts (closest rays, queries)
 	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
+	double* ctx_log2af; // [n_ctx] log2(absorption_factor), hoisted out of pow(af, length)
 	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
 	uint2* vis_list;    // [N*R] the unoccluded ones
 	int* counts;        // 0 trav_count, 1 q_count, 2 vis_count, 3 trav_cursor, 4 q_cursor
@@ -178,20 +179,32 @@ __global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
 __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 	const int n_trav = pool.counts[0], n_q = pool.counts[1];
 	const int stride = gridDim.x * blockDim.x;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_trav; i += stride) {
-		const uint2 e = pool.trav_tmp[i];
-		pool.trav_list[atomicAdd(pool.bins + e.y, 1)] = (int)e.x;
+	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+	// four independent atomics in flight per thread: the returning atomic's round trip is the whole cost here
+	for (int i = tid; i < n_trav; i += 4 * stride) {
+		uint2 e[4]; int pos[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) e[k] = pool.trav_tmp[i + k * stride];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pos[k] = atomicAdd(pool.bins + e[k].y, 1);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pool.trav_list[pos[k]] = (int)e[k].x;
 	}
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_q; i += stride) {
-		const uint2 e = pool.q_tmp[i];
-		pool.q_list[atomicAdd(pool.bins + kSortBins + ((e.y >> 16) & 0x7fffu), 1)] = e;
+	for (int i = tid; i < n_q; i += 4 * stride) {
+		uint2 e[4]; int pos[4];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = pool.q_tmp[i + k * stride];
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kSortBins + ((e[k].y >> 16) & 0x7fffu), 1);
+#pragma unroll
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pool.q_list[pos[k]] = e[k];
 	}
 }
 
 // ---------------------------------------------------------------------------------------------------
 // K3 + K6 + K1: shade, refill, enqueue
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+__global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;   // n_slots is a multiple of the block size
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -200,66 +213,129 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool,
 	int bounce = (int)(m.z >> 16);
 	int c = (int)(m.z & 0xffffu);
 	bool alive = bounce != 0;
+	const bool had_ray = alive;
 	float4 ro = make_float4(0, 0, 0, 0), rd = make_float4(0, 0, 0, 0);
-	bool shaded = false;
-	V3 n = mk(0, 0, 0), pnt = mk(0, 0, 0);
+	// what this lane needs from the shared sampling loop below
+	enum { kNone = 0, kBounce = 1, kEmit = 2 };
+	int mode = kNone;
+	V3 n = mk(0, 0, 0), pnt = mk(0, 0, 0), blend = mk(0, 0, 0), prev_dir = mk(0, 0, 0), o = mk(0, 0, 0);
+	float intensity = 0.0f, path = 0.0f, spec = 0.0f, kept = 0.0f, t = 0.0f;
+	bool refract = false;
+	unsigned long long ray = ((unsigned long long)m.y << 32) | m.x;
+	Rng rng;
+	rng.start(p.seed, (uint32_t)c, ray, m.w);
+
+	// ---- K6 + K1 (first half): slots that are empty on entry take the next ray id of the shard.  (A ray that ends in
+	// this launch frees its slot for the NEXT launch: one idle iteration per ~50, and emission shares the sampling
+	// loop with the bounces instead of running on one lane of the warp.) ----
+	const unsigned dead = __ballot_sync(0xffffffffu, !alive);
+	if (dead) {
+		unsigned long long base = 0;
+		const int want = __popc(dead);
+		if (lane == 0) {
+			base = *(volatile unsigned long long*)p.next_work;
+			if ((long long)base < p.total_work) base = atomicAdd(p.next_work, (unsigned long long)want);
+		}
+		base = __shfl_sync(0xffffffffu, base, 0);
+		const long long w = (long long)base + __popc(dead & lt_mask);
+		if (!alive && w < p.total_work) {
+			c = 0;
+			while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
+			ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
+			rng.start(p.seed, (uint32_t)c, ray, 0);
+			m.x = (uint32_t)ray; m.y = (uint32_t)(ray >> 32);
+			++lc.rays;
+			mode = kEmit;
+		}
+	}
+	const long long out_row = (long long)(ray - (unsigned long long)p.first_ray);   // parity harness: output row
+
+	// ---- K3 (first half): consume the hit of the previous launch (Scene::Bounce, src/Scene.cpp:49-63) ----
 	if (alive) {
 		ro = pool.ro[slot]; rd = pool.rd[slot];
 		const int2 h = pool.hit[slot];
-		const unsigned long long ray = ((unsigned long long)m.y << 32) | m.x;
-		const long long w = (long long)(ray - (unsigned long long)p.first_ray);   // PATHS: output row
 		++lc.segments;                                                            // one Scene::Bounce call
-		V3 o = mk(ro.x, ro.y, ro.z), d = mk(rd.x, rd.y, rd.z);
-		float intensity = ro.w, path = rd.w;
-		if (p.hits) p.hits[w * p.max_bounces + bounce] = h.y >= 0 ? __float_as_int(__ldg(sc.tris + 4 * (size_t)h.y).w) : -1;
+		o = mk(ro.x, ro.y, ro.z);
+		const V3 d = mk(rd.x, rd.y, rd.z);
+		intensity = ro.w; path = rd.w;
+		if (p.hits) p.hits[out_row * p.max_bounces + bounce] = h.y >= 0 ? __float_as_int(__ldg(sc.tris + 4 * (size_t)h.y).w) : -1;
 		if (h.y < 0) alive = false;                                               // escaped (src/Scene.cpp:166)
 		else {
-			// ---- Scene::Bounce after the hit (src/Scene.cpp:60-82), then :154-175 ----
-			const float t = __int_as_float(h.x);
+			t = __int_as_float(h.x);
 			const float4 r1 = __ldg(sc.tris + 4 * (size_t)h.y + 1);
 			const float4 r3 = __ldg(sc.tris + 4 * (size_t)h.y + 3);
-			const V3 prev_dir = vnormalized(d);                                   // prev_ray_dir (:277) of this bounce
+			prev_dir = vnormalized(d);                                            // prev_ray_dir (:277) of this bounce
 			const V3 tri_n = mk(r3.x, r3.y, r3.z);
 			pnt = vadd(o, vscale(d, t));                                          // src/Mesh.cpp:48
 			n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;           // :49-53
-			const int band = p.ctx[c].band;
-			const float af = p.ctx[c].absorption_factor;
-			const float4 mat = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
-			Rng rng;
-			rng.start(p.seed, (uint32_t)c, ray, m.w);
+			const float4 mat = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + p.ctx[c].band);
 			// Material::Bounce (src/Material.cpp:76-83); its comparisons against 0.0001 are in double
-			bool refract;
 			if ((double)mat.x < 0.0001 && (double)mat.y < 0.0001) refract = false;
 			else refract = !(rng.unit1() <= fdiv(mat.x, fadd(mat.x, mat.y)));
-			const float spec = mat.w;
-			V3 v;
-			if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
-			else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
-			m.w = rng.block;
-			const float seg = vlength(vsub(pnt, o));
-			intensity = fmul(intensity, pow_ref(af, seg));                        // src/Scene.cpp:154
-			path = fadd(path, seg);
-			intensity = fmul(intensity, mat.z);                                   // :169-171
-			ro = make_float4(pnt.x, pnt.y, pnt.z, intensity);
-			rd = make_float4(v.x, v.y, v.z, path);
-			if (invalid_float(intensity)) alive = false;                          // :175
-			else {
-				shaded = p.n_rec > 0;
-				if (shaded) {
-					pool.sh0[slot] = ro;
-					pool.sh1[slot] = make_float4(n.x, n.y, n.z, path);
-					pool.sh2[slot] = make_float4(prev_dir.x, prev_dir.y, prev_dir.z,
-					                             refract ? __int_as_float(__float_as_int(spec) | (int)0x80000000) : spec);
-				}
-				if ((double)intensity < 0.00000001) alive = false;                // :275
-				else if (bounce + 1 >= p.max_bounces) alive = false;              // loop bound (:143)
-			}
-		}
-		if (!alive && p.final_state) {
-			float* fs = p.final_state + 8 * w;
-			fs[0] = ro.x; fs[1] = ro.y; fs[2] = ro.z; fs[3] = rd.x; fs[4] = rd.y; fs[5] = rd.z; fs[6] = ro.w; fs[7] = rd.w;
+			spec = mat.w; kept = mat.z;
+			if (refract) { n = vneg(n); blend = d; }                              // src/Scene.cpp:65-69
+			else blend = vreflect(d, n);                                          // :71-73
+			mode = kBounce;
 		}
 	}
+
+	// ---- Sample_Sphere / Sample_Hemi (src/Distributions.h:48-67) for every lane that needs a direction: ONE flat
+	// rejection loop (a try = one Philox block; sphere: 0.001 <= |v|^2 <= 1; hemisphere: n.v >= 0), so that a warp
+	// runs max-over-lanes tries once instead of nesting the two rejections ----
+	V3 v = mk(0, 0, 0);
+	{
+		bool pending = mode != kNone;
+		while (pending) {
+			float u1, u2, u3;
+			rng.unit3(u1, u2, u3);
+			const V3 cand = mk(fsub(fmul(u1, 2.0f), 1.0f), fsub(fmul(u2, 2.0f), 1.0f), fsub(fmul(u3, 2.0f), 1.0f));
+			const float l = vdot(cand, cand);
+			if (!(l < 0.001f || l > 1.0f)) {
+				const float s = fsqrt(l);
+				v = mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s));
+				pending = (mode == kBounce) && (vdot(n, v) < 0.0f);
+			}
+		}
+	}
+	__syncwarp();
+
+	bool shaded = false;
+	if (mode == kBounce) {
+		// Sample_Hemi(v, n, reflection, factor), src/Distributions.h:71-75, then src/Scene.cpp:76-78, 154-175
+		v = vnormalized(vadd(vscale(v, fsub(1.0f, spec)), vscale(blend, spec)));
+		const float seg = vlength(vsub(pnt, o));
+		intensity = fmul(intensity, pow_ref_hoisted(p.ctx[c].absorption_factor, pool.ctx_log2af[c], seg));   // :154
+		path = fadd(path, seg);
+		intensity = fmul(intensity, kept);                                        // :169-171
+		ro = make_float4(pnt.x, pnt.y, pnt.z, intensity);
+		rd = make_float4(v.x, v.y, v.z, path);
+		if (invalid_float(intensity)) alive = false;                              // :175
+		else {
+			shaded = p.n_rec > 0;
+			if (shaded) {
+				pool.sh0[slot] = ro;
+				pool.sh1[slot] = make_float4(n.x, n.y, n.z, path);
+				pool.sh2[slot] = make_float4(prev_dir.x, prev_dir.y, prev_dir.z,
+				                             refract ? __int_as_float(__float_as_int(spec) | (int)0x80000000) : spec);
+			}
+			if ((double)intensity < 0.00000001) alive = false;                    // :275
+			else if (bounce + 1 >= p.max_bounces) alive = false;                  // loop bound (:143)
+		}
+	} else if (mode == kEmit) {
+		// AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226).  Bounce 0 of the reference loop
+		// records nothing for point sources (src/Scene.cpp:185) and leaves intensity 1, path 0.
+		const float* sp = p.ctx[c].source_position;
+		ro = make_float4(sp[0], sp[1], sp[2], 1.0f);
+		rd = make_float4(v.x, v.y, v.z, 0.0f);
+		bounce = 0;
+		alive = 1 < p.max_bounces;
+	}
+	m.w = rng.block;
+	if (!alive && (had_ray || mode == kEmit) && p.final_state) {   // parity harness: state the ray ended with
+		float* fs = p.final_state + 8 * out_row;
+		fs[0] = ro.x; fs[1] = ro.y; fs[2] = ro.z; fs[3] = rd.x; fs[4] = rd.y; fs[5] = rd.z; fs[6] = ro.w; fs[7] = rd.w;
+	}
+
 	// ---- K4 enqueue: Scene::Connect is called for every recorder (src/Scene.cpp:188-195); its answer is only
 	// used when dot(lsdir, n) > 0 (:209), so only those queries are traced ----
 	for (int r = 0; r < p.n_rec; ++r) {
@@ -283,49 +359,11 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool,
 			}
 		}
 	}
-	if (alive) ++bounce;
-	// ---- K6 + K1: dead slots take the next ray id of the shard and emit (AbstractSoundFile::SoundRay) ----
-	const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-	if (dead) {
-		unsigned long long base = 0;
-		const int want = __popc(dead);
-		if (lane == 0) {
-			base = *(volatile unsigned long long*)p.next_work;
-			if ((long long)base < p.total_work) base = atomicAdd(p.next_work, (unsigned long long)want);
-		}
-		base = __shfl_sync(0xffffffffu, base, 0);
-		const long long w = (long long)base + __popc(dead & lt_mask);
-		if (!alive) {
-			bounce = 0;
-			if (w < p.total_work) {
-				c = 0;
-				while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
-				const unsigned long long ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
-				Rng rng;
-				rng.start(p.seed, (uint32_t)c, ray, 0);
-				++lc.rays;
-				const float* sp = p.ctx[c].source_position;
-				const V3 d = sample_sphere(rng);
-				ro = make_float4(sp[0], sp[1], sp[2], 1.0f);
-				rd = make_float4(d.x, d.y, d.z, 0.0f);
-				m.x = (uint32_t)ray; m.y = (uint32_t)(ray >> 32); m.w = rng.block;
-				// bounce 0 of the reference loop records nothing for point sources (src/Scene.cpp:185)
-				bounce = 1;
-				alive = bounce < p.max_bounces;
-				if (!alive) {
-					bounce = 0;
-					if (p.final_state) {
-						float* fs = p.final_state + 8 * (long long)(ray - (unsigned long long)p.first_ray);
-						fs[0] = ro.x; fs[1] = ro.y; fs[2] = ro.z; fs[3] = rd.x; fs[4] = rd.y; fs[5] = rd.z; fs[6] = ro.w; fs[7] = rd.w;
-					}
-				}
-			}
-		}
-	}
+	bounce = alive ? bounce + 1 : 0;
 	m.z = (uint32_t)c | ((uint32_t)bounce << 16);
 	pool.rm[slot] = m;
 	if (alive) { pool.ro[slot] = ro; pool.rd[slot] = rd; }
-	// ---- compaction: slots that need a closest-hit query next ----
+	// ---- K6 compaction: slots that need a closest-hit query next, binned by (direction octant, origin cell) ----
 	const unsigned live = __ballot_sync(0xffffffffu, alive);
 	if (live) {
 		int base = 0;
@@ -338,6 +376,7 @@ __global__ void __launch_bounds__(256) wf_shade_kernel(SceneDev sc, WfPool pool,
 			pool.trav_tmp[base + __popc(live & lt_mask)] = make_uint2((uint32_t)slot, bin);
 		}
 	}
+	// the launch loop stops when no slot holds a ray and the shard's queue is dry
 	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
 	if (lane == 0 && (v0 | v1 | v2)) {
 		if (v0) atomicAdd(p.counters + 0, v0);
@@ -379,7 +418,7 @@ __global__ void __launch_bounds__(256) wf_splat_kernel(WfPool pool, RenderParams
 		}
 		float contrib = fmul(intensity, factor);
 		const float l = vlength(segv);                                               // :250
-		contrib = fmul(contrib, pow_ref(af, l));
+		contrib = fmul(contrib, pow_ref_hoisted(af, pool.ctx_log2af[c], l));
 		contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
 		if (invalid_float(contrib)) continue;
 		if (q.y >> 31) contrib = fmul(contrib, -1.0f);                               // odd bounce (:257)
@@ -424,6 +463,10 @@ __global__ void wf_load_segments_kernel(WfPool pool, float4* qx, const float* pp
 __global__ void wf_mark_visible_kernel(WfPool pool, uint8_t* out) {
 	const int total = pool.counts[2];
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[pool.vis_list[i].x & kSlotMask] = 0;
+}
+__global__ void wf_ctx_table_kernel(WfPool pool, RenderParams p) {
+	const int c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c < p.n_ctx) pool.ctx_log2af[c] = log2_ref(p.ctx[c].absorption_factor);
 }
 __global__ void wf_fill_int_kernel(int32_t* dst, long long n, int32_t v) {
 	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = v;
