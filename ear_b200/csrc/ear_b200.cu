@@ -415,7 +415,7 @@ struct ear_b200_scene {
 	int sm_count = 148;
 	int min_blocks = 4;
 	int engine = 0;                 // 0 = wavefront (default), 1 = fused kernel (EAR_B200_ENGINE=mega)
-	int max_slots = 1 << 20;        // rays in flight in the wavefront pool (EAR_B200_SLOTS)
+	int max_slots = 1 << 22;        // rays in flight in the wavefront pool (EAR_B200_SLOTS)
 	int check_every = 8;            // iterations between host checks for completion
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;

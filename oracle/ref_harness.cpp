@@ -15,9 +15,13 @@
  *   firsthit <scene.ear> <rays.bin> <out.bin>   rays: n x {ox,oy,oz,dx,dy,dz} f32
  *            out: n x {int32 tri, f32 t, f32 p[3], f32 n[3]} via Mesh::RayIntersection
  *   occluded <scene.ear> <segs.bin> <out.bin>   segs: n x {px,py,pz,xx,xy,xz} f32; out: n x u8
- *   render   <scene.ear> <seed> <out.bin> [t60] [threads=N]
+ *   render   <scene.ear> <seed> <out.bin> [t60] [threads=N] [budget=SECONDS]
  *            runs every SceneContext the CLI would create (EAR.cpp:170-191; with
  *            `t60` only the single calc-T60 context) and dumps the raw tracks.
+ *            budget=S (single-threaded runs): after S seconds of Scene::Render the process
+ *            prints the REF_RENDER line for the work done so far and exits -- a bounded
+ *            throughput sample for scenes where 50 rays (the reference's minimum:
+ *            DrawProgressBar divides by samples/50) take minutes of brute force.
  * rand() is seeded through a time() override: both srand(time) call sites
  * (src/EAR.cpp:58, src/Scene.cpp:116) see the requested seed.
  */
@@ -27,6 +31,8 @@
 #include <stdint.h>
 #include <time.h>
 #include <sys/time.h>
+#include <signal.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -53,6 +59,23 @@ static double wall_seconds() {
 	struct timeval tv;
 	gettimeofday(&tv, 0);
 	return (double)tv.tv_sec + 1e-6 * (double)tv.tv_usec;
+}
+
+/* budgeted runs: SIGALRM reports what Scene::Render has done so far and ends the process */
+static double g_t0 = 0.0;
+static size_t g_triangles = 0;
+static int g_contexts = 0, g_recorders = 0, g_rays = 0;
+static void on_budget(int) {
+	const gmtl::ShimCounters& c = gmtl::shim_counters();
+	const double secs = wall_seconds() - g_t0;
+	char line[512];
+	const int n = snprintf(line, sizeof(line),
+	    "\nREF_RENDER contexts=%d recorders=%d triangles=%zu rays_per_context=%d threads=1 seconds=%.6f "
+	    "ray_tests=%llu seg_tests=%llu segments=%.0f budget=1\n",
+	    g_contexts, g_recorders, g_triangles, g_rays, secs, c.ray_tests, c.seg_tests,
+	    g_triangles ? (double)c.ray_tests / (double)g_triangles : 0.0);
+	if (write(1, line, n) < 0) {}
+	_exit(0);
 }
 
 struct LoadedScene {
@@ -165,7 +188,7 @@ static int cmd_occluded(const char* scene_path, const char* in_path, const char*
 	return 0;
 }
 
-static int cmd_render(const char* scene_path, long seed, const char* out_path, bool t60_only, int threads) {
+static int cmd_render(const char* scene_path, long seed, const char* out_path, bool t60_only, int threads, int budget) {
 	g_fake_time = seed;
 	gmtl::Math::seedRandom((unsigned int)time(0)); /* src/EAR.cpp:58 */
 	LoadedScene ls;
@@ -187,7 +210,11 @@ static int cmd_render(const char* scene_path, long seed, const char* out_path, b
 		if (t60_only) break;
 	}
 	const size_t T = scene->meshes[0]->tris.size();
+	g_triangles = T; g_contexts = (int)ctxs.size(); g_recorders = (int)scene->listeners.size(); g_rays = ls.samples;
+	fflush(stdout);
 	const double t0 = wall_seconds();
+	g_t0 = t0;
+	if (budget > 0 && threads <= 1) { signal(SIGALRM, on_budget); alarm((unsigned)budget); }
 	if (threads <= 1) {
 		for (size_t i = 0; i < ctxs.size(); ++i) ctxs[i]();
 		boost::shim_totals::fold();
@@ -200,6 +227,7 @@ static int cmd_render(const char* scene_path, long seed, const char* out_path, b
 		}
 	}
 	const double t1 = wall_seconds();
+	alarm(0);
 	const unsigned long long ray_tests = boost::shim_totals::ray_tests();
 	const unsigned long long seg_tests = boost::shim_totals::seg_tests();
 	FILE* out = fopen(out_path, "wb");
@@ -240,12 +268,13 @@ int main(int argc, char** argv) {
 	if (argc >= 5 && !strcmp(argv[1], "occluded")) return cmd_occluded(argv[2], argv[3], argv[4]);
 	if (argc >= 5 && !strcmp(argv[1], "render")) {
 		bool t60 = false;
-		int threads = 1;
+		int threads = 1, budget = 0;
 		for (int i = 5; i < argc; ++i) {
 			if (!strcmp(argv[i], "t60")) t60 = true;
 			else if (!strncmp(argv[i], "threads=", 8)) threads = atoi(argv[i] + 8);
+			else if (!strncmp(argv[i], "budget=", 7)) budget = atoi(argv[i] + 7);
 		}
-		return cmd_render(argv[2], atol(argv[3]), argv[4], t60, threads);
+		return cmd_render(argv[2], atol(argv[3]), argv[4], t60, threads, budget);
 	}
 	fprintf(stderr, "usage: ref_harness firsthit|occluded|render ...\n");
 	return 64;
