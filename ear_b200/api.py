@@ -66,7 +66,7 @@ EXPORTS = [
     "ear_b200_last_error", "ear_b200_abi_version", "ear_b200_device_count", "ear_b200_scene_create",
     "ear_b200_scene_destroy", "ear_b200_first_hit", "ear_b200_occluded", "ear_b200_trace_paths",
     "ear_b200_render", "ear_b200_result_free", "ear_b200_trace_device", "ear_b200_finalise_device",
-    "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset",
+    "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset", "ear_b200_convolve",
 ]
 
 _lib = None
@@ -103,6 +103,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.ear_b200_scene_stats.argtypes = [vp, C.POINTER(StatsC)]
     lib.ear_b200_scene_stats_reset.argtypes = [vp]
     lib.ear_b200_scene_stats_reset.restype = None
+    u32 = C.c_uint32
+    lib.ear_b200_convolve.argtypes = [i32, vp, u32, u32, u32, vp, u32, u32, u32, vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
     if path is None:
         _lib = lib
     return lib
@@ -216,6 +218,28 @@ class RenderResult:
     bin_updates: int
     dropped_updates: int
     device_ms: float
+
+
+def convolve(response: "Track", dry: np.ndarray, offset: int = 0, response2: Optional["Track"] = None, device: int = 0) -> "Track":
+    """RecorderTrack::Process (src/Recorder.cpp:247-292) on the GPU: direct convolution of a dry signal with a
+    response track (cross-faded into `response2` for keyframed scenes).  Returns the result track."""
+    lib = load_library()
+    dry = np.ascontiguousarray(dry, np.float32)
+    r1 = np.ascontiguousarray(response.data, np.float32)
+    first, length = response.first_sample, response.real_length
+    r2 = None
+    if response2 is not None:
+        r2 = np.ascontiguousarray(response2.data, np.float32)
+        first, length = min(first, response2.first_sample), max(length, response2.real_length)
+    out_len = max(3 * SAMPLE_RATE, dry.shape[0] + offset + length)
+    out = np.zeros(out_len, np.float32)
+    of, orl = C.c_uint32(), C.c_uint32()
+    _check(lib, lib.ear_b200_convolve(
+        device, r1.ctypes.data, r1.shape[0], response.first_sample, response.real_length,
+        r2.ctypes.data if r2 is not None else None, r2.shape[0] if r2 is not None else 0,
+        response2.first_sample if response2 is not None else 0, response2.real_length if response2 is not None else 0,
+        dry.ctypes.data, dry.shape[0], offset, out.ctypes.data, out_len, C.byref(of), C.byref(orl)))
+    return Track(out, int(of.value), int(orl.value))
 
 
 class Scene:

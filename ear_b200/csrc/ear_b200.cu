@@ -415,7 +415,8 @@ struct ear_b200_scene {
 	int sm_count = 148;
 	int min_blocks = 4;
 	int engine = 0;                 // 0 = wavefront (default), 1 = fused kernel (EAR_B200_ENGINE=mega)
-	int max_slots = 1 << 22;        // rays in flight in the wavefront pool (EAR_B200_SLOTS)
+	int max_slots = 1 << 23;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS)
+	bool slots_forced = false;
 	int check_every = 8;            // iterations between host checks for completion
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
@@ -497,7 +498,7 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	const char* en = std::getenv("EAR_B200_ENGINE");
 	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
 	const char* sl = std::getenv("EAR_B200_SLOTS");
-	if (sl) s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl)));
+	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
 	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
@@ -729,7 +730,10 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
 	if (p.n_rec > 255) return fail("render: more than 255 recorders per context are not supported");
 	if (p.n_ctx > 65535) return fail("render: more than 65535 contexts per call are not supported");
+	// pool size: large launches amortise the persistent kernels' tails (8 Mi slots: +4 % over 4 Mi), but every slot
+	// should host several rays in turn or the run ends in a long half-empty decay: a quarter of the shard's rays
 	long long slots = std::min<long long>(std::max<long long>(p.total_work, 1), s->max_slots);
+	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / 4));
 	slots = (slots + 255) / 256 * 256;
 	if (int32_t rc = ensure_pool(s, (size_t)slots, (size_t)slots * std::max(1, p.n_rec))) return rc;
 	WfPool pl = s->pool;
@@ -873,6 +877,98 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;
 	cudaFree(d_hist); cudaFree(d_range); cudaFree(d_counters);
 	*out = res;
+	return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// impulse-response convolution (RecorderTrack::Process, src/Recorder.cpp:247-292)
+// ------------------------------------------------------------------------------------------
+// One thread per output sample k; the dry signal is walked in increasing i (the reference's outer loop), so
+// each sample sees its terms in the reference's order.  Tiles of 256 dry samples and the matching 511-sample
+// response window are staged through shared memory; global loads are coalesced, the inner loop reads a broadcast
+// dry value and a stride-1 response value (conflict-free).
+constexpr int kConvTile = 256;
+template <bool FADE>
+__global__ void __launch_bounds__(kConvTile) convolve_kernel(const float* __restrict__ r1, uint32_t len1, const float* __restrict__ r2,
+                                                             uint32_t len2, uint32_t first, uint32_t len, const float* __restrict__ dry,
+                                                             uint32_t n_dry, uint32_t offset, float* __restrict__ out, uint32_t out_len) {
+	__shared__ float s_dry[kConvTile];
+	__shared__ float s_r1[2 * kConvTile];
+	__shared__ float s_r2[FADE ? 2 * kConvTile : 1];
+	const long long k0 = (long long)blockIdx.x * kConvTile;          // first output sample of this block
+	const long long k = k0 + threadIdx.x;
+	const float inv_n = FADE ? fdiv(1.0f, (float)n_dry) : 0.0f;
+	float acc = 0.0f;
+	// i contributes to k iff first <= k - offset - i < len  <=>  k - offset - len < i <= k - offset - first
+	long long i_lo = k0 - (long long)offset - (long long)len + 1;                       // lowest i any thread of the block needs
+	long long i_hi = k0 + kConvTile - 1 - (long long)offset - (long long)first;         // highest
+	if (i_lo < 0) i_lo = 0;
+	if (i_hi > (long long)n_dry - 1) i_hi = (long long)n_dry - 1;
+	for (long long ib = i_lo; ib <= i_hi; ib += kConvTile) {
+		__syncthreads();
+		const long long i_load = ib + threadIdx.x;
+		s_dry[threadIdx.x] = i_load <= i_hi ? dry[i_load] : 0.0f;
+		// response window: j = k - offset - i for k in [k0, k0+255], i in [ib, ib+255]  ->  j in [jb, jb + 510]
+		const long long jb = k0 - (long long)offset - (ib + kConvTile - 1);
+		for (int w = threadIdx.x; w < 2 * kConvTile; w += kConvTile) {
+			const long long j = jb + w;
+			const bool in = j >= (long long)first && j < (long long)len;
+			s_r1[w] = (in && j < (long long)len1) ? r1[j] : 0.0f;
+			if (FADE) s_r2[w] = (in && j < (long long)len2) ? r2[j] : 0.0f;
+		}
+		__syncthreads();
+		const int n_i = (int)((i_hi - ib + 1 < kConvTile) ? (i_hi - ib + 1) : kConvTile);
+		for (int ii = 0; ii < n_i; ++ii) {
+			// j - jb = (k - offset - (ib + ii)) - jb = threadIdx.x + 255 - ii
+			const int w = (int)threadIdx.x + kConvTile - 1 - ii;
+			const long long j = jb + w;
+			if (j >= (long long)first && j < (long long)len) {
+				float p = s_r1[w];
+				if (FADE) {
+					const float i1 = fmul((float)(uint32_t)(ib + ii), inv_n), i2 = fsub(1.0f, i1);
+					p = fadd(fmul(i2, s_r1[w]), fmul(i1, s_r2[w]));
+				}
+				acc = fadd(acc, fmul(s_dry[ii], p));
+			}
+		}
+	}
+	if (k < (long long)out_len) out[k] = acc;
+}
+
+extern "C" int32_t ear_b200_convolve(int32_t device, const float* response, uint32_t length, uint32_t first_sample,
+                                     uint32_t real_length, const float* response2, uint32_t length2, uint32_t first_sample2,
+                                     uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
+                                     uint32_t out_len, uint32_t* out_first, uint32_t* out_real) {
+	if (!response || !out || (n_dry && !dry)) return fail("convolve: null argument");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: ear_b200 has no CPU fallback"); }
+	if (device < 0 || device >= ndev) return fail("convolve: device index out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	const bool fade = response2 != nullptr;
+	const uint32_t first = fade ? std::min(first_sample, first_sample2) : first_sample;
+	const uint32_t len = fade ? std::max(real_length, real_length2) : real_length;
+	const uint32_t init_first = 3 * EAR_B200_SAMPLE_RATE - 1;
+	if (out_first) *out_first = init_first;
+	if (out_real) *out_real = 0;
+	if (out_len) std::memset(out, 0, (size_t)out_len * sizeof(float));
+	if (n_dry == 0 || len <= first) return 0;       // the reference's loops do not run
+	const unsigned long long last = (unsigned long long)(n_dry - 1) + offset + (len - 1);
+	if (out_first) *out_first = std::min<uint32_t>(init_first, offset + first);
+	if (out_real) *out_real = (uint32_t)last;
+	if (last + 1 > out_len) return fail("convolve: output buffer shorter than n_dry - 1 + offset + real_length");
+	float *d_r1 = nullptr, *d_r2 = nullptr, *d_dry = nullptr, *d_out = nullptr;
+	const uint32_t n1 = std::min(length, len), n2 = fade ? std::min(length2, len) : 0;
+	CUDA_TRY(cudaMalloc(&d_r1, std::max<size_t>(n1, 1) * 4)); CUDA_TRY(cudaMalloc(&d_dry, (size_t)n_dry * 4));
+	CUDA_TRY(cudaMalloc(&d_out, (size_t)(last + 1) * 4));
+	CUDA_TRY(cudaMemcpy(d_r1, response, (size_t)n1 * 4, cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(d_dry, dry, (size_t)n_dry * 4, cudaMemcpyHostToDevice));
+	if (fade) { CUDA_TRY(cudaMalloc(&d_r2, std::max<size_t>(n2, 1) * 4)); CUDA_TRY(cudaMemcpy(d_r2, response2, (size_t)n2 * 4, cudaMemcpyHostToDevice)); }
+	const unsigned grid = (unsigned)((last + 1 + kConvTile - 1) / kConvTile);
+	if (fade) convolve_kernel<true><<<grid, kConvTile>>>(d_r1, n1, d_r2, n2, first, len, d_dry, n_dry, offset, d_out, (uint32_t)(last + 1));
+	else convolve_kernel<false><<<grid, kConvTile>>>(d_r1, n1, nullptr, 0, first, len, d_dry, n_dry, offset, d_out, (uint32_t)(last + 1));
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaMemcpy(out, d_out, (size_t)(last + 1) * 4, cudaMemcpyDeviceToHost));
+	cudaFree(d_r1); cudaFree(d_r2); cudaFree(d_dry); cudaFree(d_out);
 	return 0;
 }
 

@@ -255,8 +255,9 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 	// ---- convolution with the dry signal (src/EAR.cpp:296-355, src/Recorder.cpp:343-363) ----
 	{
 		std::vector<std::thread> pool;
-		const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+		const unsigned hw = (unsigned)std::max(1, 2 * n_gpus);   // two host threads per GPU keep its copy engines busy
 		std::atomic<int> next(0);
+		std::string conv_error;
 		for (Context& c : ctxs) c.processed.resize((size_t)n_rec * 2);
 		auto work = [&]() {
 			for (;;) {
@@ -277,26 +278,34 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 					const Track* tr = c.tracks[r * 2 + k].get();
 					if (!tr) continue;
 					const float* ptr; unsigned n, off;
+					const Track* next = nullptr;
 					if (sf.has_keys) {
 						const float offset_s = sf.keys[(size_t)c.keyframe];
 						const int lastkey = (int)sf.keys.size() - 1;
-						if (c.keyframe == lastkey) {
-							section(offset_s, -1.0f, ptr, n, off);
-							c.processed[r * 2 + k].reset(tr->convolve(ptr, n, off));
-						} else {
-							const Context& nx = ctxs[(size_t)ci + 3];   // same sound/band, next keyframe
+						if (c.keyframe == lastkey) section(offset_s, -1.0f, ptr, n, off);
+						else {
+							next = ctxs[(size_t)ci + 3].tracks[r * 2 + k].get();   // same sound/band, next keyframe
 							section(offset_s, sf.keys[(size_t)c.keyframe + 1] - offset_s, ptr, n, off);
-							c.processed[r * 2 + k].reset(tr->convolve_fade(*nx.tracks[r * 2 + k], ptr, n, off));
 						}
-					} else {
-						section(0.0f, -1.0f, ptr, n, off);
-						c.processed[r * 2 + k].reset(tr->convolve(ptr, n, off));
+					} else section(0.0f, -1.0f, ptr, n, off);
+					// RecorderTrack::Process on the GPU (include/ear_b200.h: ear_b200_convolve)
+					const unsigned len = next ? std::max(tr->real_length, next->real_length) : tr->real_length;
+					std::vector<float> out((size_t)std::max<unsigned>(3 * kSampleRate, n + off + len), 0.0f);
+					uint32_t of = 0, orl = 0;
+					if (ear_b200_convolve(job % n_gpus, tr->data(), tr->allocated(), tr->first_sample, tr->real_length,
+					                      next ? next->data() : nullptr, next ? next->allocated() : 0, next ? next->first_sample : 0,
+					                      next ? next->real_length : 0, n ? ptr : nullptr, n, off, out.data(), (uint32_t)out.size(), &of, &orl)) {
+						conv_error = ear_b200_last_error();
+						return;
 					}
+					c.processed[r * 2 + k].reset(new Track());
+					c.processed[r * 2 + k]->assign(out.data(), (uint32_t)out.size(), of, orl);
 				}
 			}
 		};
 		for (unsigned t = 0; t < std::min<unsigned>(hw, (unsigned)(n_ctx * n_rec)); ++t) pool.emplace_back(work);
 		for (auto& t : pool) t.join();
+		if (!conv_error.empty()) throw std::runtime_error(conv_error);
 	}
 
 	std::cout << "Merging result..." << std::endl;

@@ -82,30 +82,6 @@ void Track::add(const Track& other) {
 	for (unsigned i = 0; i < len; ++i) at(i) += other.get(i);
 }
 
-Track* Track::convolve(const float* dry, unsigned n, unsigned offset) const {
-	Track* out = new Track();
-	const unsigned len = real_length;
-	for (unsigned i = 0; i < n; ++i) {
-		const float s = dry[i];
-		unsigned index = i + offset + first_sample;
-		for (unsigned j = first_sample; j < len; ++j) out->at(index++) += s * get(j);
-	}
-	return out;
-}
-
-Track* Track::convolve_fade(const Track& next, const float* dry, unsigned n, unsigned offset) const {
-	Track* out = new Track();
-	const float inv = 1.0f / (float)n;
-	const unsigned len = std::max(real_length, next.real_length);
-	const unsigned first = std::min(first_sample, next.first_sample);
-	for (unsigned i = 0; i < n; ++i) {
-		const float i1 = i * inv, i2 = 1.0f - i1, s = dry[i];
-		unsigned index = i + offset + first;
-		for (unsigned j = first; j < len; ++j) out->at(index++) += s * (i2 * get(j) + i1 * next.get(j));
-	}
-	return out;
-}
-
 void Track::write_raw(const std::string& path) const {
 	std::ofstream f(path.c_str(), std::ios::binary);
 	f.write((const char*)data_.data(), sizeof(float) * ((size_t)real_length + 1));

@@ -33,10 +33,7 @@ public:
 	unsigned length(float threshold = -1.0f) const;          // getLength
 	float t60() const;
 	void add(const Track& other);
-	// direct convolution of a dry signal with this response (RecorderTrack::Process)
-	Track* convolve(const float* dry, unsigned n, unsigned offset) const;
-	// keyframe variant: response cross-faded linearly into `next` over the dry section
-	Track* convolve_fade(const Track& next, const float* dry, unsigned n, unsigned offset) const;
+	// convolution with the dry signal (RecorderTrack::Process) runs on the GPU: ear_b200_convolve (include/ear_b200.h)
 	void write_raw(const std::string& path) const;
 private:
 	std::vector<float> data_;

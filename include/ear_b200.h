@@ -155,6 +155,21 @@ int32_t ear_b200_finalise_device(ear_b200_scene* scene, const ear_b200_context* 
                                  float* d_hist, uint32_t* d_range, void* stream);
 /* Bins per track the library would choose for these options (same rule as ear_b200_render). */
 int32_t ear_b200_default_bins(ear_b200_scene* scene, const ear_b200_options* opt);
+/* SURVEY.md 8(f) rank 1 -- impulse-response convolution, RecorderTrack::Process (src/Recorder.cpp:247-292,
+ * direct form, the reference's default build).  out[k] for k in [0, out_len) receives, bit for bit, what the
+ * reference's loops leave in the result track: for i in [0, n_dry) (outer) and j in [first, len) (inner)
+ *     out[i + offset + j] += dry[i] * p(j)
+ * with p(j) = response[j]                                  when response2 == NULL  (static scene, :247-263), or
+ *      p(j) = (1 - i/n_dry) * response[j] + (i/n_dry) * response2[j]   keyframe cross-fade (:267-292),
+ *      first = min(first_sample, first_sample2), len = max(real_length, real_length2), tracks read as 0 beyond
+ *      their allocated length.  Every output sample is accumulated in increasing i, one float multiply and one
+ *      float add per term (no FMA), exactly the order the CPU loop produces.
+ * Host buffers in and out; out_first / out_real receive the result track's first_sample / real_length. */
+int32_t ear_b200_convolve(int32_t device, const float* response, uint32_t length, uint32_t first_sample,
+                          uint32_t real_length, const float* response2, uint32_t length2, uint32_t first_sample2,
+                          uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
+                          uint32_t out_len, uint32_t* out_first, uint32_t* out_real);
+
 /* Launch counts and device time per kernel class since the last reset (synchronises the scene's last stream). */
 int32_t ear_b200_scene_stats(ear_b200_scene* scene, ear_b200_stats* out);
 void ear_b200_scene_stats_reset(ear_b200_scene* scene);

@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         l.oracle_t60.argtypes = [vp, u32, u32]
         l.oracle_t60.restype = f32
         l.oracle_sabine_eyring.argtypes = [vp, vp, i32, f32, f32, C.POINTER(f32), C.POINTER(f32)]
+        l.oracle_convolve.argtypes = [vp, u32, u32, u32, vp, u32, u32, u32, vp, u32, u32, vp]
         _lib = l
     return _lib
 
@@ -165,6 +166,24 @@ def post_t60(tracks_per_context, which=(0, 0, 0)):
                 out.append((d, tr.first_sample, max(1, ln)))
     d, first, real = out[0]
     return float(l.oracle_t60(d.ctypes.data, first, real))
+
+
+def convolve(response: Track, dry, offset=0, response2: Track = None) -> np.ndarray:
+    """RecorderTrack::Process restated (src/Recorder.cpp:247-292); returns the raw result samples."""
+    dry = np.ascontiguousarray(dry, np.float32)
+    r1 = np.ascontiguousarray(response.data, np.float32)
+    first, length = response.first_sample, response.real_length
+    r2 = None
+    if response2 is not None:
+        r2 = np.ascontiguousarray(response2.data, np.float32)
+        first, length = min(first, response2.first_sample), max(length, response2.real_length)
+    out = np.zeros(max(3 * 44100, dry.shape[0] + offset + length), np.float32)
+    lib().oracle_convolve(r1.ctypes.data, r1.shape[0], response.first_sample, response.real_length,
+                          r2.ctypes.data if r2 is not None else None, r2.shape[0] if r2 is not None else 0,
+                          response2.first_sample if response2 is not None else 0,
+                          response2.real_length if response2 is not None else 0,
+                          dry.ctypes.data, dry.shape[0], offset, out.ctypes.data)
+    return out
 
 
 # ---------------- the reference itself (oracle/_ref) ----------------
