@@ -52,6 +52,8 @@ struct Builder {
 	static constexpr int32_t kParallelThreshold = 1 << 15;
 	std::atomic<int> live_tasks{0};
 	int max_tasks = 1;
+	int max_leaf = kMaxLeaf;   // triangles per leaf (<= 8: three bits in the leaf reference)
+	float sah_ct = 1.0f;       // cost of one node step in triangle tests
 
 	int32_t alloc() { return next_node.fetch_add(1); }
 
@@ -118,13 +120,13 @@ struct Builder {
 		}
 		// leaf cost (1 per triangle) vs split cost (traversal step ~ 1 triangle test)
 		const float parent_area = bounds.half_area();
-		if (count <= kMaxLeaf) {
+		if (count <= max_leaf) {
 			const float leaf_cost = (float)count;
-			const float split_cost = best_axis < 0 ? INFINITY : 1.0f + best_cost / std::max(parent_area, 1e-30f);
+			const float split_cost = best_axis < 0 ? INFINITY : sah_ct + best_cost / std::max(parent_area, 1e-30f);
 			if (!(split_cost < leaf_cost)) { make_leaf(id, first, count); return; }
 		}
 		int32_t mid;
-		if (depth >= kSahDepth && count > kMaxLeaf) {
+		if (depth >= kSahDepth && count > max_leaf) {
 			int ax = 0;
 			for (int k = 1; k < 3; ++k) if (cbounds.hi[k] - cbounds.lo[k] > cbounds.hi[ax] - cbounds.lo[ax]) ax = k;
 			mid = first + count / 2;
@@ -211,6 +213,8 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 	}
 	b.nodes.resize(std::max<size_t>(2 * (size_t)n, 4));
 	b.max_tasks = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+	if (const char* e = std::getenv("EAR_B200_MAX_LEAF")) b.max_leaf = std::max(1, std::min(8, std::atoi(e)));
+	if (const char* e = std::getenv("EAR_B200_SAH_CT")) b.sah_ct = (float)std::atof(e);
 	const int32_t root = b.alloc();
 	if (n > 0) b.build(root, 0, n);
 	else { b.nodes[root].left = b.nodes[root].right = -1; b.nodes[root].first = 0; b.nodes[root].count = 0; b.nodes[root].slack = 0; b.nodes[root].box.reset(); }

@@ -198,6 +198,30 @@ __device__ __forceinline__ void leaf_step(const SceneDev& sc, TravState& ts) {
 	else pop_next<EXACT>(sc, ts);
 }
 
+// Speculative variant used by the persistent kernels: the leaf is PARKED in `pend` (one triangle is tested per
+// call) while the lane keeps walking inner nodes from its stack; best_t only shrinks later, which is conservative.
+template <bool ANY_HIT>
+__device__ __forceinline__ void pend_step(const SceneDev& sc, TravState& ts, int32_t& pend) {
+	const int32_t code = ~pend;
+	const int32_t first = code >> 3, rest = code & 7;
+	const float4* rec = sc.tris + 4 * (size_t)first;
+	const F8 r01 = ldg256(rec);
+	const float4 r2 = __ldg(rec + 2);
+	float t;
+	if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
+		if (ANY_HIT) {
+			if (t > 1e-5f && t < 1.0f) ts.best_idx = 1;
+		} else {
+			const int32_t idx = __float_as_int(r01.lo.w);
+			if (t > 0.001f && (t < ts.best_t || (t == ts.best_t && idx < ts.best_idx))) {   // src/Mesh.cpp:40
+				ts.best_t = t; ts.best_idx = idx; ts.best_slot = first;
+			}
+		}
+	}
+	if (ANY_HIT && ts.best_idx) { pend = 0; ts.node = kEmptyChildDev; ts.st.sp = 0; }   // occluded: the query is over
+	else pend = rest > 0 ? ~(((first + 1) << 3) | (rest - 1)) : 0;
+}
+
 // Warp-synchronous traversal of one ray per lane; must be called by all 32 lanes of the warp
 // (inactive lanes pass active = false).
 // ANY_HIT = false: argmin over (t, original index) of triangles with MT hit and t > 0.001 (t < 1e6):

@@ -45,6 +45,7 @@ struct WfPool {
 };
 
 constexpr int kSortBins = 32768;   // 15-bit keys: 3 octant bits (closest) or 3 recorder bits (queries) + 12 Morton cell bits
+constexpr int32_t kWaitLeaf = 0x7ffffffe;   // closest-hit lane waiting for its parked leaf (kEmptyChildDev - 1)
 constexpr int kSlotBits = 24;
 constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
 
@@ -65,16 +66,24 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 	ts.o = mk(0, 0, 0); ts.d = mk(0, 0, 0); ts.rs = make_setup(ts.o, ts.d);
 	bool has_job = false, exhausted = total <= 0;
 	uint2 job = make_uint2(0u, 0u);   // closest: x = slot; any-hit: the query
+	int32_t pend = 0;                 // parked leaf (0 = none): tested one triangle per leaf round
 	for (;;) {
-		const bool inner = ts.node >= 0 && ts.node != kEmptyChildDev;
-		const bool leaf = ts.node < 0;
+		// Any-hit: a lane that reaches a leaf parks it and keeps walking inner nodes (it only blocks on a second
+		// leaf): order does not matter for a yes/no answer and the leaf rounds fill up (-2 % time).  Closest hit:
+		// the lane waits for its leaf, because the hit it may find prunes the rest of its walk (parking measured +10 %).
+		if (ts.node < 0 && pend == 0) {
+			pend = ts.node;
+			if (ANY_HIT) pop_next<EXACT>(sc, ts); else ts.node = kWaitLeaf;
+		}
+		const bool inner = ts.node >= 0 && ts.node < kWaitLeaf;
+		const bool parked = pend != 0;
 		const unsigned m_inner = __ballot_sync(0xffffffffu, inner);
-		const unsigned m_leaf = __ballot_sync(0xffffffffu, leaf);
-		const unsigned m_idle = ~(m_inner | m_leaf);
-		const bool busy = (m_inner | m_leaf) != 0u;
+		const unsigned m_pend = __ballot_sync(0xffffffffu, parked);
+		const unsigned m_idle = ~(m_inner | m_pend);
+		const bool busy = (m_inner | m_pend) != 0u;
 		if (!exhausted && (__popc(m_idle) >= sc.fetch_vote || !busy)) {
 			// ---------------- retire finished lanes, fetch new work ----------------
-			const bool idle = !inner && !leaf;
+			const bool idle = !inner && !parked;
 			if (ANY_HIT) {
 				const bool visible = idle && has_job && ts.best_idx == 0;
 				const unsigned m_vis = __ballot_sync(0xffffffffu, visible);
@@ -130,10 +139,13 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 			}
 			break;
 		}
-		if (m_inner != 0u && __popc(m_leaf) < sc.leaf_vote) {
+		if (m_inner != 0u && __popc(m_pend) < sc.leaf_vote) {
 			if (inner) node_step<EXACT>(sc, ts);
 		} else {
-			if (leaf) leaf_step<ANY_HIT, EXACT>(sc, ts);
+			if (parked) {
+				pend_step<ANY_HIT>(sc, ts, pend);
+				if (!ANY_HIT && pend == 0) pop_next<EXACT>(sc, ts);
+			}
 		}
 	}
 }
