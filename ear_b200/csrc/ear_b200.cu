@@ -290,6 +290,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 }
 
 #include "wavefront.cuh"
+#include "vismap.cuh"
 
 // Fused single-kernel engine (EAR_B200_ENGINE=mega): grid = SMs x resident blocks; warps pull ray ids from a
 // global queue until it is dry.
@@ -423,6 +424,14 @@ struct ear_b200_scene {
 	int* h_counts = nullptr;        // pinned
 	unsigned long long* d_scratch_counters = nullptr;
 	ear_b200_stats stats{};
+	// recorder visibility maps (vismap.cuh), cached per recorder position
+	struct VisMapHost { float x[3]; int res; int* d_offsets; int* d_items; size_t n_items; };
+	std::vector<VisMapHost> vismaps;
+	int vismap_res = -1;            // -1: choose from the triangle count; 0: disabled (EAR_B200_VISMAP_RES)
+	VisMapDev* d_maps = nullptr; int* d_map_of = nullptr; size_t map_of_cap = 0;
+	uint2* d_q_bvh = nullptr; size_t q_bvh_cap = 0;
+	std::vector<ear_b200_recorder> h_rec;   // host copy of the recorders of the current call
+	float maxabs = 0.0f;
 	// event pairs recorded around every engine launch, harvested at the engine's sync points
 	struct Timed { cudaEvent_t a, b; int cls; };
 	std::vector<Timed> ev_pool;
@@ -499,6 +508,8 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
 	const char* sl = std::getenv("EAR_B200_SLOTS");
 	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
+	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
+	for (int k = 0; k < 3; ++k) s->maxabs = std::max(s->maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
 	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
@@ -519,11 +530,14 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaFree(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+	for (auto& m : s->vismaps) { cudaFree(m.d_offsets); cudaFree(m.d_items); }
+	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
 
 static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries);
+static int32_t prepare_vismaps(ear_b200_scene* s, int n_ctx, int n_rec, cudaStream_t stream, int* n_mapped);
 
 extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, const float* dirs, int64_t n,
                                       int32_t* tri_index, float* t) {
@@ -571,6 +585,26 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 	CUDA_TRY(cudaMalloc(&d_qx, chunk * sizeof(float4)));
 	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, (size_t)chunk)) return rc; }
 	RenderParams p{};
+	// all segments end at one point (the render loop's case): answer through that point's visibility map,
+	// exactly as the render does, with the BVH any-hit kernel for the texels whose lists are too long
+	bool same_x = s->engine == 0;
+	for (int64_t i = 1; i < n && same_x; ++i) same_x = std::memcmp(x, x + 3 * i, 12) == 0;
+	int n_mapped = 0;
+	if (same_x) {
+		ear_b200_recorder one{};
+		one.kind = EAR_B200_MONO;
+		std::memcpy(one.position, x, 12);
+		s->h_rec.assign(1, one);
+		if (s->rec_cap < 1) { cudaFree(s->d_rec); CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder))); s->rec_cap = 1; }
+		CUDA_TRY(cudaMemcpyAsync(s->d_rec, &one, sizeof(one), cudaMemcpyHostToDevice, s->stream));
+		if (int32_t rc = prepare_vismaps(s, 1, 1, s->stream, &n_mapped)) return rc;
+		if (n_mapped && (size_t)chunk > s->q_bvh_cap) {
+			cudaFree(s->d_q_bvh);
+			CUDA_TRY(cudaMalloc(&s->d_q_bvh, (size_t)chunk * sizeof(uint2)));
+			s->q_bvh_cap = (size_t)chunk;
+		}
+		p.rec = s->d_rec; p.n_rec = 1; p.n_ctx = 1;
+	}
 	for (int64_t at = 0; at < n; at += chunk) {
 		const int m = (int)std::min<int64_t>(chunk, n - at);
 		const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
@@ -583,7 +617,12 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 			int bps = 0;
 			void (*anyhit)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<true, true> : wf_traverse_kernel<true, false>;
 			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, anyhit, kBlock, kStackBytes));
-			anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
+			if (n_mapped) {
+				WfPool pl_fb = pl;
+				pl_fb.qx = nullptr; pl_fb.q_list = s->d_q_bvh; pl_fb.q_count_idx = 5; pl_fb.q_cursor_idx = 6;
+				wf_vismap_kernel<<<s->sm_count * 8, 256, 0, s->stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh);
+				anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl_fb, p);
+			} else anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
 			wf_mark_visible_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(pl, d_out);
 		} else if (s->dev.exact) occluded_kernel<true><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
 		else occluded_kernel<false><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
@@ -645,6 +684,7 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 		prefix[c + 1] = prefix[c] + cnt;
 	}
 	if (prefix_override) for (int32_t c = 0; c <= n_ctx; ++c) prefix[c] = prefix_override[c];
+	s->h_rec.assign(rec, rec + (size_t)n_ctx * n_rec);
 	CUDA_TRY(cudaMemcpyAsync(s->d_ctx, ctx, sizeof(ear_b200_context) * n_ctx, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_prefix, prefix.data(), sizeof(long long) * (n_ctx + 1), cudaMemcpyHostToDevice, stream));
@@ -716,12 +756,78 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 		s->pool_queries = queries;
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
+	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, 2 * kSortBins * sizeof(int)));
 	for (int k = 0; k < 3; ++k) {
 		pl.cell_origin[k] = s->lo[k];
 		const float ext = s->hi[k] - s->lo[k];
 		pl.cell_scale[k] = ext > 0.0f ? 16.0f / ext : 0.0f;
 	}
+	return 0;
+}
+
+// Builds (or finds) the visibility map of one recorder position; returns its index or -1 when maps are disabled.
+static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stream, int* index) {
+	*index = -1;
+	int res = s->vismap_res;
+	if (res == 0 || s->n_tris == 0) return 0;
+	if (res < 0) {
+		res = 64;
+		while (res < 1024 && (double)res * res * 6.0 < 1.5 * (double)s->n_tris) res *= 2;
+	}
+	for (size_t i = 0; i < s->vismaps.size(); ++i)
+		if (s->vismaps[i].res == res && std::memcmp(s->vismaps[i].x, x, 12) == 0) { *index = (int)i; return 0; }
+	if (s->vismaps.size() >= 64) return 0;   // plenty of distinct recorder positions: the rest use the BVH
+	ear_b200_scene::VisMapHost m{};
+	std::memcpy(m.x, x, 12); m.res = res;
+	const int n_tex = 6 * res * res;
+	int* d_counts = nullptr;
+	CUDA_TRY(cudaMalloc(&d_counts, (size_t)n_tex * sizeof(int)));
+	CUDA_TRY(cudaMalloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
+	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
+	const double reach = 2.0 * (double)s->diagonal + 1.0;
+	const unsigned grid = (unsigned)((6LL * s->n_tris + 127) / 128);
+	vis_build_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, nullptr, nullptr);
+	vis_scan_kernel<<<1, 1024, 0, stream>>>(d_counts, m.d_offsets, n_tex);
+	int total = 0;
+	CUDA_TRY(cudaMemcpyAsync(&total, m.d_offsets + n_tex, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	if (total < 0) { cudaFree(d_counts); cudaFree(m.d_offsets); return fail("visibility map overflow"); }
+	m.n_items = (size_t)total;
+	CUDA_TRY(cudaMalloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
+	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
+	vis_build_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, m.d_offsets, m.d_items);
+	CUDA_TRY(cudaGetLastError());
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	cudaFree(d_counts);
+	s->vismaps.push_back(m);
+	*index = (int)s->vismaps.size() - 1;
+	return 0;
+}
+
+// uploads the map table for the recorders of the current call; returns the number of recorders that have a map
+static int32_t prepare_vismaps(ear_b200_scene* s, int n_ctx, int n_rec, cudaStream_t stream, int* n_mapped) {
+	*n_mapped = 0;
+	const size_t n = (size_t)n_ctx * n_rec;
+	if (n == 0 || s->h_rec.size() < n) return 0;
+	std::vector<int> map_of(n, -1);
+	for (size_t i = 0; i < n; ++i) {
+		int idx = -1;
+		if (int32_t rc = get_vismap(s, s->h_rec[i].position, stream, &idx)) return rc;
+		map_of[i] = idx;
+		if (idx >= 0) ++*n_mapped;
+	}
+	if (*n_mapped == 0) return 0;
+	if (n > s->map_of_cap) { cudaFree(s->d_map_of); CUDA_TRY(cudaMalloc(&s->d_map_of, n * sizeof(int))); s->map_of_cap = n; }
+	if (!s->d_maps) CUDA_TRY(cudaMalloc(&s->d_maps, 64 * sizeof(VisMapDev)));
+	std::vector<VisMapDev> maps(s->vismaps.size());
+	for (size_t i = 0; i < maps.size(); ++i) {
+		maps[i].offsets = s->vismaps[i].d_offsets; maps[i].items = s->vismaps[i].d_items; maps[i].res = s->vismaps[i].res;
+		std::memcpy(maps[i].x, s->vismaps[i].x, 12);
+	}
+	CUDA_TRY(cudaMemcpyAsync(s->d_map_of, map_of.data(), n * sizeof(int), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(s->d_maps, maps.data(), maps.size() * sizeof(VisMapDev), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
 	return 0;
 }
 
@@ -736,8 +842,19 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / 4));
 	slots = (slots + 255) / 256 * 256;
 	if (int32_t rc = ensure_pool(s, (size_t)slots, (size_t)slots * std::max(1, p.n_rec))) return rc;
+	int n_mapped = 0;
+	if (p.n_rec > 0) { if (int32_t rc = prepare_vismaps(s, p.n_ctx, p.n_rec, stream, &n_mapped)) return rc; }
+	const size_t n_queries = (size_t)slots * std::max(1, p.n_rec);
+	if (n_mapped && n_queries > s->q_bvh_cap) {
+		cudaFree(s->d_q_bvh);
+		CUDA_TRY(cudaMalloc(&s->d_q_bvh, n_queries * sizeof(uint2)));
+		s->q_bvh_cap = n_queries;
+	}
 	WfPool pl = s->pool;
 	pl.n_slots = (int)slots;
+	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
+	WfPool pl_fb = pl;   // the map fallback list, traced by the BVH any-hit kernel
+	pl_fb.q_list = s->d_q_bvh; pl_fb.q_count_idx = 5; pl_fb.q_cursor_idx = 6;
 	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
 	if ((size_t)p.n_ctx > s->log2af_cap) {
 		cudaFree(s->pool.ctx_log2af);
@@ -768,14 +885,21 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 			}
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 			if (p.n_rec > 0) {
-				{ LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
+				if (n_mapped) {
+					LaunchTimer t(s, stream, 2);
+					++s->stats.launches[2];
+					wf_vismap_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh);
+					anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl_fb, p);
+				} else { LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 				{ LaunchTimer t(s, stream, 3); wf_splat_kernel<<<splat_grid, 256, 0, stream>>>(pl, p); }
 			}
 			++s->stats.iterations;
 		}
 		CUDA_TRY(cudaGetLastError());
-		CUDA_TRY(cudaMemcpyAsync(s->h_counts, pl.counts, 4 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaMemcpyAsync(s->h_counts, pl.counts, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
+		if (std::getenv("EAR_B200_DEBUG"))
+			std::fprintf(stderr, "[ear_b200] it %lld: trav %d queries %d visible %d map-fallback %d\n", it, s->h_counts[0], s->h_counts[1], s->h_counts[2], s->h_counts[5]);
 		harvest_events(s);
 		if (s->h_counts[0] == 0) break;   // nothing left to trace after the last shade
 	}

@@ -1,0 +1,187 @@
+// Recorder visibility maps: K4 (Scene::Connect / Mesh::LineIntersection, src/Scene.cpp:84-96, src/Mesh.cpp:58-71)
+// for the render loop, where every occlusion query ends at one of a handful of fixed points (the recorders).
+//
+// For a recorder position X the directions around X are cut into a cube map (6 faces x res x res texels); each
+// texel holds the list of triangles whose projection from X, dilated by the lateral slop of the float32
+// Moeller-Trumbore test, touches the texel.  A query P -> X then looks up the texel of (P - X) and runs the
+// reference's exact float test on that short list -- no tree walk, no stack, no divergence beyond the list
+// length.  The list is a SUPERSET of the triangles the float test can accept for any segment through X in that
+// texel (the line must pass within h of the triangle; h as in bvh_build.cpp), so the yes/no answer is the same as
+// the O(T) loop's.  Texels with long lists (grazing views along a wall) fall back to the BVH any-hit kernel.
+#pragma once
+#include "wavefront.cuh"
+
+namespace earb {
+
+struct VisMapDev {
+	const int* offsets;    // [6 * res * res + 1]
+	const int* items;      // triangle record slots
+	float x[3];            // recorder position
+	int res;
+};
+
+constexpr int kVisMaxList = 64;   // longer texel lists are traced through the BVH instead
+
+// face f: major axis m = f >> 1, sign = +1 (even) / -1 (odd); the other two axes in cyclic order
+__device__ __forceinline__ int vis_texel(const VisMapDev& mp, float dx, float dy, float dz) {
+	const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+	int m = 0; float w = ax;
+	if (ay > w) { m = 1; w = ay; }
+	if (az > w) { m = 2; w = az; }
+	const float major = m == 0 ? dx : m == 1 ? dy : dz;
+	const float b = m == 0 ? dy : m == 1 ? dz : dx;
+	const float c = m == 0 ? dz : m == 1 ? dx : dy;
+	const int face = 2 * m + (major < 0.0f ? 1 : 0);
+	if (!(w > 0.0f)) return 0;
+	const float u = b / w, v = c / w;   // [-1, 1]
+	const int i = min(mp.res - 1, max(0, (int)((u + 1.0f) * 0.5f * (float)mp.res)));
+	const int j = min(mp.res - 1, max(0, (int)((v + 1.0f) * 0.5f * (float)mp.res)));
+	return (face * mp.res + j) * mp.res + i;
+}
+
+// Conservative footprint of triangle `t` on face `face` of the cube map around X: texel rectangle [i0,i1]x[j0,j1].
+__device__ __forceinline__ bool vis_footprint(const SceneDev& sc, int t, const double X[3], int res, int face, double reach,
+                                              double maxabs, int& i0, int& i1, int& j0, int& j1) {
+	const float4 r0 = sc.tris[4 * (size_t)t], r1 = sc.tris[4 * (size_t)t + 1], r2 = sc.tris[4 * (size_t)t + 2];
+	double a[3][3] = {{(double)r0.x - X[0], (double)r0.y - X[1], (double)r0.z - X[2]}, {0, 0, 0}, {0, 0, 0}};
+	const double e1[3] = {r1.x, r1.y, r1.z}, e2[3] = {r2.x, r2.y, r2.z};
+	for (int k = 0; k < 3; ++k) { a[1][k] = a[0][k] + e1[k]; a[2][k] = a[0][k] + e2[k]; }
+	// lateral slop of the float test (same bound as the BVH leaf padding), doubled
+	const double l1 = sqrt(e1[0] * e1[0] + e1[1] * e1[1] + e1[2] * e1[2]), l2 = sqrt(e2[0] * e2[0] + e2[1] * e2[1] + e2[2] * e2[2]);
+	const double cx = e1[1] * e2[2] - e1[2] * e2[1], cy = e1[2] * e2[0] - e1[0] * e2[2], cz = e1[0] * e2[1] - e1[1] * e2[0];
+	double sinphi = (l1 > 0 && l2 > 0) ? sqrt(cx * cx + cy * cy + cz * cz) / (l1 * l2) : 1.0;
+	if (sinphi < 1e-3) sinphi = 1e-3;
+	const double eps = 5.9604645e-8;
+	const double h = 2.0 * (16.0 * eps * reach / sinphi + 8.0 * eps * (maxabs + reach)) + 4.0 * eps * (l1 + l2);
+	// lower bound of the distance from X to the triangle: centroid distance minus the largest centroid-vertex distance
+	double g[3] = {(a[0][0] + a[1][0] + a[2][0]) / 3.0, (a[0][1] + a[1][1] + a[2][1]) / 3.0, (a[0][2] + a[1][2] + a[2][2]) / 3.0};
+	double rmax = 0.0;
+	for (int v = 0; v < 3; ++v) {
+		const double dx = a[v][0] - g[0], dy = a[v][1] - g[1], dz = a[v][2] - g[2];
+		rmax = fmax(rmax, sqrt(dx * dx + dy * dy + dz * dz));
+	}
+	const double lb = sqrt(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]) - rmax;
+	if (lb < 16.0 * h) { i0 = 0; j0 = 0; i1 = res - 1; j1 = res - 1; return true; }   // X (almost) touches the triangle
+	const double margin = 3.1 * (h / lb) + 1e-5;     // angular slop h/lb in projected (tangent) coordinates, |u|,|v| <= 1
+	const int m = face >> 1, b = (m + 1) % 3, c = (m + 2) % 3;
+	const double sgn = (face & 1) ? -1.0 : 1.0;
+	const double wmin = 1e-9 * reach;
+	// clip the triangle against w = sgn * a[m] >= wmin (Sutherland-Hodgman), project, bound
+	double u0 = 1e30, u1 = -1e30, v0 = 1e30, v1 = -1e30;
+	bool any = false;
+	for (int k = 0; k < 3; ++k) {
+		const double* p = a[k];
+		const double* q = a[(k + 1) % 3];
+		const double wp = sgn * p[m], wq = sgn * q[m];
+		if (wp >= wmin) {
+			const double u = p[b] / wp, v = p[c] / wp;
+			u0 = fmin(u0, u); u1 = fmax(u1, u); v0 = fmin(v0, v); v1 = fmax(v1, v); any = true;
+		}
+		if ((wp >= wmin) != (wq >= wmin)) {
+			const double s = (wmin - wp) / (wq - wp);
+			const double ub = (p[b] + s * (q[b] - p[b])) / wmin, vc = (p[c] + s * (q[c] - p[c])) / wmin;
+			u0 = fmin(u0, ub); u1 = fmax(u1, ub); v0 = fmin(v0, vc); v1 = fmax(v1, vc); any = true;
+		}
+	}
+	if (!any) return false;
+	u0 -= margin; u1 += margin; v0 -= margin; v1 += margin;
+	if (u1 < -1.0 || u0 > 1.0 || v1 < -1.0 || v0 > 1.0) return false;
+	i0 = max(0, min(res - 1, (int)floor((fmax(u0, -1.0) + 1.0) * 0.5 * res)));
+	i1 = max(0, min(res - 1, (int)floor((fmin(u1, 1.0) + 1.0) * 0.5 * res)));
+	j0 = max(0, min(res - 1, (int)floor((fmax(v0, -1.0) + 1.0) * 0.5 * res)));
+	j1 = max(0, min(res - 1, (int)floor((fmin(v1, 1.0) + 1.0) * 0.5 * res)));
+	return true;
+}
+
+// pass 0: count list lengths; pass 1: fill the lists (cursor = running fill position per texel)
+template <int PASS>
+__global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, double x1, double x2, int res, double reach, double maxabs,
+                                                        int* counts_or_cursor, const int* offsets, int* items) {
+	const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one (triangle, face) per thread
+	if (id >= 6LL * sc.n_tris) return;
+	const int t = (int)(id / 6), face = (int)(id % 6);
+	const double X[3] = {x0, x1, x2};
+	int i0, i1, j0, j1;
+	if (!vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1)) return;
+	for (int j = j0; j <= j1; ++j)
+		for (int i = i0; i <= i1; ++i) {
+			const int texel = (face * res + j) * res + i;
+			if (PASS == 0) atomicAdd(counts_or_cursor + texel, 1);
+			else items[offsets[texel] + atomicAdd(counts_or_cursor + texel, 1)] = t;
+		}
+}
+
+// exclusive scan of n ints by one block (n up to a few million), out[n] = total
+__global__ void __launch_bounds__(1024) vis_scan_kernel(const int* in, int* out, int n) {
+	__shared__ long long part[1024];
+	const int per = (n + 1023) / 1024;
+	const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+	long long s = 0;
+	for (int i = beg; i < end; ++i) s += in[i];
+	part[threadIdx.x] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		long long run = 0;
+		for (int i = 0; i < 1024; ++i) { const long long v = part[i]; part[i] = run; run += v; }
+		out[n] = (int)run;
+	}
+	__syncthreads();
+	long long run = part[threadIdx.x];
+	for (int i = beg; i < end; ++i) { out[i] = (int)run; run += in[i]; }
+}
+
+// K4 through the maps: one query per thread.  Visible queries go to vis_list; queries whose texel list is too
+// long (or whose recorder has no map) go to `q_bvh` for the BVH any-hit kernel.
+__global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool, RenderParams p, const VisMapDev* maps,
+                                                        const int* map_of, uint2* q_bvh) {
+	const int total = pool.counts[1];
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const int stride = gridDim.x * blockDim.x;
+	for (int base_i = blockIdx.x * blockDim.x; base_i < total; base_i += stride) {   // warp-uniform trip count
+		const int i = base_i + threadIdx.x;
+		bool visible = false, fallback = false;
+		uint2 q = make_uint2(0u, 0u);
+		if (i < total) {
+			q = pool.q_list[i];
+			const uint32_t slot = q.x & kSlotMask, r = q.x >> kSlotBits, c = q.y & 0xffffu;
+			const int mi = map_of[c * p.n_rec + r];
+			if (mi < 0) fallback = true;
+			else {
+				const VisMapDev mp = maps[mi];
+				const float4 s0 = pool.sh0[slot];
+				const V3 pnt = mk(s0.x, s0.y, s0.z), x = mk(mp.x[0], mp.x[1], mp.x[2]);
+				const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
+				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1];
+				if (end - beg > kVisMaxList) fallback = true;
+				else {
+					const V3 d = vsub(x, pnt);   // LineSeg(p, x) = Ray(p, x - p)
+					visible = true;
+					for (int k = beg; k < end; ++k) {
+						const float4* rec = sc.tris + 4 * (size_t)mp.items[k];
+						const F8 r01 = ldg256(rec);
+						const float4 r2 = __ldg(rec + 2);
+						float t;
+						if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), pnt, d, t) &&
+						    t > 1e-5f && t < 1.0f) { visible = false; break; }
+					}
+				}
+			}
+		}
+		const unsigned m_vis = __ballot_sync(0xffffffffu, visible), m_fb = __ballot_sync(0xffffffffu, fallback);
+		if (m_vis) {
+			int b = 0;
+			if (lane == 0) b = atomicAdd(pool.counts + 2, __popc(m_vis));
+			b = __shfl_sync(0xffffffffu, b, 0);
+			if (visible) pool.vis_list[b + __popc(m_vis & lt_mask)] = q;
+		}
+		if (m_fb) {
+			int b = 0;
+			if (lane == 0) b = atomicAdd(pool.counts + 5, __popc(m_fb));
+			b = __shfl_sync(0xffffffffu, b, 0);
+			if (fallback) q_bvh[b + __popc(m_fb & lt_mask)] = q;
+		}
+	}
+}
+
+}  // namespace earb

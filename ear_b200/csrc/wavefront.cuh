@@ -41,6 +41,7 @@ struct WfPool {
 	uint2* vis_list;    // [N*R] the unoccluded ones
 	int* counts;        // 0 trav_count, 1 q_count, 2 vis_count, 3 trav_cursor, 4 q_cursor
 	const float4* qx;   // harness only: explicit segment end point per query (else the recorder position)
+	int q_count_idx, q_cursor_idx;   // which counters the any-hit kernel uses (1, 4 normally; 5, 6 for the map fallback list)
 	int n_slots;
 };
 
@@ -57,8 +58,8 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 	extern __shared__ int2 stack_smem[];
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	const int total = ANY_HIT ? pool.counts[1] : pool.counts[0];
-	int* cursor = pool.counts + (ANY_HIT ? 4 : 3);
+	const int total = ANY_HIT ? pool.counts[pool.q_count_idx] : pool.counts[0];
+	int* cursor = pool.counts + (ANY_HIT ? pool.q_cursor_idx : 3);
 	TravState ts;
 	ts.st.smem = stack_smem + threadIdx.x; ts.st.stride = blockDim.x; ts.st.sp = 0;
 	ts.node = kEmptyChildDev;
@@ -470,7 +471,7 @@ __global__ void wf_load_segments_kernel(WfPool pool, float4* qx, const float* pp
 	qx[i] = make_float4(xx[3 * i], xx[3 * i + 1], xx[3 * i + 2], 0.0f);
 	pool.q_list[i] = make_uint2((uint32_t)i, 0u);
 	out[i] = 1;   // occluded unless the traversal reports the query visible
-	if (i == 0) { pool.counts[1] = n; pool.counts[2] = 0; pool.counts[4] = 0; }
+	if (i == 0) { pool.counts[1] = n; pool.counts[2] = 0; pool.counts[4] = 0; pool.counts[5] = 0; pool.counts[6] = 0; }
 }
 __global__ void wf_mark_visible_kernel(WfPool pool, uint8_t* out) {
 	const int total = pool.counts[2];

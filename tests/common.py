@@ -104,3 +104,31 @@ def make_segments(sc: SceneDef, n: int, seed: int = 2):
     p2 = rng.uniform(lo, hi, (n - h, 3))
     x2 = rng.uniform(lo, hi, (n - h, 3))
     return np.concatenate([p1, p2]).astype(np.float32), np.concatenate([x1, x2]).astype(np.float32)
+
+
+def make_segments_to_point(sc: SceneDef, n: int, x, seed: int = 3):
+    """Occlusion queries that all end at one point (what the render loop asks): surface points, points exactly
+    on triangle vertices / edges, free-space points, and points whose segment grazes a triangle's plane."""
+    rng = np.random.default_rng(seed)
+    tris = sc.triangles()
+    lo, hi = tris.reshape(-1, 3).min(0), tris.reshape(-1, 3).max(0)
+    T = tris.shape[0]
+    x = np.asarray(x, np.float64)
+    q = n // 4
+    k = rng.integers(0, T, q)
+    u = rng.uniform(0, 1, (q, 2))
+    flip = u.sum(1) > 1
+    u[flip] = 1 - u[flip]
+    p1 = tris[k, 0] + u[:, :1] * (tris[k, 1] - tris[k, 0]) + u[:, 1:] * (tris[k, 2] - tris[k, 0])
+    k = rng.integers(0, T, q)
+    w = rng.integers(0, 3, q)
+    s = rng.choice([0.0, 0.5, 1.0], q)[:, None]
+    p2 = tris[k, w] + s * (tris[k, (w + 1) % 3] - tris[k, w])
+    p3 = rng.uniform(lo, hi, (q, 3))
+    # grazing: start in the plane of triangle k, on the far side of it as seen from x, so the segment skims the triangle
+    k = rng.integers(0, T, n - 3 * q)
+    cen = tris[k].mean(1)
+    d = cen - x
+    p4 = cen + d * rng.uniform(0.01, 0.5, (n - 3 * q, 1)) + rng.normal(scale=1e-4, size=(n - 3 * q, 3))
+    p = np.concatenate([p1, p2, p3, p4]).astype(np.float32)
+    return p, np.tile(x.astype(np.float32)[None, :], (n, 1))

@@ -27,6 +27,8 @@ def test_first_hit_matches_bruteforce_oracle_on_a_sample(hall):
     assert np.array_equal(gt[ci >= 0].view(np.uint32), ct[ci >= 0].view(np.uint32))
     p, x = common.make_segments(sc, 400, seed=42)
     assert np.array_equal(gpu.occluded(p, x), cpu.occluded(p, x))
+    p, x = common.make_segments_to_point(sc, 400, sc.recorders[0].position, seed=43)   # through the visibility map
+    assert np.array_equal(gpu.occluded(p, x), cpu.occluded(p, x))
 
 
 def test_closest_hit_and_occlusion_agree_with_each_other(hall):

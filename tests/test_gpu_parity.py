@@ -49,6 +49,20 @@ def test_occlusion_identical(ob, name, n):
     assert np.array_equal(g, c), f"{(g != c).sum()} of {n} occlusion answers differ"
 
 
+@pytest.mark.parametrize("name,n", [("rt60", 40000), ("example1", 40000), ("soup", 40000), ("hall20k", 24000)])
+def test_occlusion_to_recorder_identical(ob, name, n):
+    """All segments end at the recorder: answered through the recorder's visibility map (+ BVH fallback), the
+    way the render loop does it."""
+    sc = common.named_scene(name)
+    gpu, cpu = _pair(ob, sc)
+    for x in (sc.recorders[0].position, sc.sources[0].position):
+        p, xx = common.make_segments_to_point(sc, n, x)
+        g = gpu.occluded(p, xx)
+        c = cpu.occluded(p, xx)
+        assert np.array_equal(g, c), f"{(g != c).sum()} of {n} occlusion answers differ"
+        assert 0.01 < c.mean() < 0.99 or name == "rt60"
+
+
 def test_empty_and_tiny_scenes(ob):
     # one triangle, and a ray batch of size 1 / 0
     sc = common.soup_scene(n_tris=2, seed=9)
