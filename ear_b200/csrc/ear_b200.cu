@@ -508,6 +508,8 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
 	const char* sl = std::getenv("EAR_B200_SLOTS");
 	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
+	s->dev.vis_cap = kVisMaxList;
+	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::atoi(vc));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	for (int k = 0; k < 3; ++k) s->maxabs = std::max(s->maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
@@ -773,7 +775,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	if (res == 0 || s->n_tris == 0) return 0;
 	if (res < 0) {
 		res = 64;
-		while (res < 1024 && (double)res * res * 6.0 < 1.5 * (double)s->n_tris) res *= 2;
+		while (res < 1024 && (double)res * res < (double)s->n_tris) res *= 2;   // ~6 texels per triangle
 	}
 	for (size_t i = 0; i < s->vismaps.size(); ++i)
 		if (s->vismaps[i].res == res && std::memcmp(s->vismaps[i].x, x, 12) == 0) { *index = (int)i; return 0; }

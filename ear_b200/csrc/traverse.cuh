@@ -30,6 +30,7 @@ struct SceneDev {
 	int32_t exact;            // 1: rigorous per-child slack
 	int32_t leaf_vote;        // lanes that must wait on a leaf before the warp runs a leaf step
 	int32_t fetch_vote;       // idle lanes that trigger a fetch of new work in the persistent kernels
+	int32_t vis_cap;          // visibility-map texel lists longer than this are traced through the BVH instead
 };
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;

@@ -20,7 +20,9 @@ struct VisMapDev {
 	int res;
 };
 
-constexpr int kVisMaxList = 64;   // longer texel lists are traced through the BVH instead
+constexpr int kVisMaxList = 96;   // longer texel lists are traced through the BVH instead (measured: 16 -> 523 ms,
+                                  // 48 -> 338, 96 -> 326, 192 -> 407 per 1.9e9 queries; binning queries by direction
+                                  // instead of origin cell made both the sort and the lookups slower)
 
 // face f: major axis m = f >> 1, sign = +1 (even) / -1 (odd); the other two axes in cyclic order
 __device__ __forceinline__ int vis_texel(const VisMapDev& mp, float dx, float dy, float dz) {
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 				const V3 pnt = mk(s0.x, s0.y, s0.z), x = mk(mp.x[0], mp.x[1], mp.x[2]);
 				const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
 				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1];
-				if (end - beg > kVisMaxList) fallback = true;
+				if (end - beg > sc.vis_cap) fallback = true;
 				else {
 					const V3 d = vsub(x, pnt);   // LineSeg(p, x) = Ray(p, x - p)
 					visible = true;

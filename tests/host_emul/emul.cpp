@@ -16,7 +16,7 @@ void* emul_create(const float* verts, const int32_t* mats, int32_t n) {
 	e->dev.nodes = (const float4*)e->bvh.nodes.data();
 	e->dev.tris = (const float4*)e->bvh.tris.data();
 	e->dev.materials = nullptr; e->dev.n_tris = n; e->dev.n_materials = 0; e->dev.n_bands = 0;
-	e->dev.s0 = e->bvh.s0; e->dev.exact = 0; e->dev.leaf_vote = kLeafVote; e->dev.fetch_vote = 8;
+	e->dev.s0 = e->bvh.s0; e->dev.exact = 0; e->dev.leaf_vote = kLeafVote; e->dev.fetch_vote = 8; e->dev.vis_cap = 64;
 	return e;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }
