@@ -192,31 +192,34 @@ def run_ours(args):
 
     # ---- e2e: host buffers through the public C ABI, every step ----
     e2e_ms = []
+    e2e_create_ms = []
     h2d = verts.nbytes + tri_mat.nbytes + table.nbytes + C.sizeof(ctx_c) + C.sizeof(rec_c)
     d2h = 0
     e2e_segments = 0
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
+    from ear_b200.sharding import create_replicated_scene, render_sharded
     for _ in range(e2e_steps):
         barrier()
         w0 = time.perf_counter()
-        s2 = api.Scene(verts, tri_mat, table, device=local)
-        res = s2.render(ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo,
-                        finalise=(world == 1))
-        if world > 1:
-            part = torch.from_numpy(np.stack([t.data for c in res.tracks for r in c for t in r])).to(dev)
-            dist.reduce(part, dst=0, op=dist.ReduceOp.SUM)
-            part = part.cpu()
+        # the public multi-GPU path: one BVH build (rank 0), image broadcast over NVLink, sharded trace, one reduce
+        s2 = create_replicated_scene(verts, tri_mat, table, device=local)
+        torch.cuda.synchronize()
+        wc = time.perf_counter()
+        e2e_create_ms.append((wc - w0) * 1e3)
+        res = render_sharded(s2, ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234)
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         s2.close()
-        d2h = sum((t.real_length + 1) * 4 for c in res.tracks for r in c for t in r)
+        if res is not None:
+            d2h = sum((t.real_length + 1) * 4 for c in res.tracks for r in c for t in r)
+            e2e_segments += res.segments
         e2e_ms.append((w1 - w0) * 1e3)
-        e2e_segments += res.segments
+        if os.environ.get("EAR_BENCH_VERBOSE"):
+            print(f"[bench] rank {rank} e2e step: create {e2e_create_ms[-1]:.1f} ms, render {(w1 - wc) * 1e3:.1f} ms", file=sys.stderr)
     e2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     es = torch.tensor([e2e_segments], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(e2, op=dist.ReduceOp.MAX)
-        dist.all_reduce(es, op=dist.ReduceOp.SUM)
     e2e_value = float(es.item()) / (float(e2.item()) * 1e-3) if e2e_steps else None
 
     cpu_base = None
@@ -246,7 +249,8 @@ def run_ours(args):
             "segments_per_step": segments // args.steps, "occlusion_queries_per_step": occl // args.steps,
             "bin_updates_per_step": bins // args.steps, "dropped_updates": dropped,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "includes": "scene upload + BVH build + trace + finalise + track download"},
+                    "includes": "scene upload + BVH build (rank 0) + image broadcast + trace + reduce + finalise + track download",
+                    "ms_per_step": sum(e2e_ms) / max(1, len(e2e_ms)), "scene_create_ms": sum(e2e_create_ms) / max(1, len(e2e_create_ms))},
             "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
             "launches_per_step": {k: v / args.steps for k, v in st["launches"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -67,6 +67,7 @@ EXPORTS = [
     "ear_b200_scene_destroy", "ear_b200_first_hit", "ear_b200_occluded", "ear_b200_trace_paths",
     "ear_b200_render", "ear_b200_result_free", "ear_b200_trace_device", "ear_b200_finalise_device",
     "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset", "ear_b200_convolve",
+    "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
 ]
 
 _lib = None
@@ -89,6 +90,10 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.ear_b200_scene_create.argtypes = [vp, vp, i32, vp, i32, i32, i32, C.POINTER(vp)]
     lib.ear_b200_scene_destroy.argtypes = [vp]
     lib.ear_b200_scene_destroy.restype = None
+    lib.ear_b200_scene_image_size.argtypes = [vp, C.POINTER(C.c_uint64)]
+    lib.ear_b200_scene_image_write.argtypes = [vp, vp, C.c_uint64]
+    lib.ear_b200_scene_create_from_image.argtypes = [vp, C.c_uint64, i32, C.POINTER(vp)]
+    lib.ear_b200_scene_clone.argtypes = [vp, i32, C.POINTER(vp)]
     lib.ear_b200_first_hit.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.ear_b200_occluded.argtypes = [vp, vp, vp, i64, vp]
     lib.ear_b200_trace_paths.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(OptionsC), i64, vp, vp]
@@ -263,6 +268,28 @@ class Scene:
     def from_def(cls, scene_def, materials: Optional[np.ndarray] = None, device: int = 0) -> "Scene":
         tab = scene_def.material_table() if materials is None else materials
         return cls(scene_def.triangles(), scene_def.triangle_materials(), tab, device)
+
+    @classmethod
+    def from_image(cls, image_ptr: int, image_bytes: int, n_bands: int, device: int = 0) -> "Scene":
+        """Adopts a scene image resident in device memory (ear_b200_scene_create_from_image)."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.verts = self.tri_material = self.materials = None
+        self.n_bands = n_bands
+        self.device = device
+        h = C.c_void_p()
+        _check(self.lib, self.lib.ear_b200_scene_create_from_image(C.c_void_p(image_ptr), image_bytes, device, C.byref(h)))
+        self.handle = h
+        return self
+
+    def image_size(self) -> int:
+        n = C.c_uint64()
+        _check(self.lib, self.lib.ear_b200_scene_image_size(self.handle, C.byref(n)))
+        return int(n.value)
+
+    def image_write(self, dst_ptr: int, dst_bytes: int) -> None:
+        """Copies the scene image into device memory at dst_ptr (e.g. a torch uint8 tensor's data_ptr())."""
+        _check(self.lib, self.lib.ear_b200_scene_image_write(self.handle, C.c_void_p(dst_ptr), dst_bytes))
 
     def close(self):
         if getattr(self, "handle", None):

@@ -3,6 +3,8 @@
 // src/Mesh.cpp:39); this replaces that O(T) loop while returning the SAME winner.
 #pragma once
 #include <cstdint>
+#include <memory>
+#include <utility>
 #include <vector>
 
 namespace earb {
@@ -41,9 +43,25 @@ static_assert(sizeof(TriRecord) == 64, "triangle record must be 64 bytes");
 constexpr int32_t kEmptyChild = 0x7fffffff;
 constexpr int kMaxLeaf = 4;
 
+// Allocator whose resize() leaves trivially-constructible elements uninitialised: the builder overwrites every
+// element, and zero-filling 100+ MB first costs more than some of its passes.
+template <class T>
+struct RawAllocator {
+	using value_type = T;
+	RawAllocator() = default;
+	template <class U> RawAllocator(const RawAllocator<U>&) {}
+	T* allocate(std::size_t n) { return std::allocator<T>().allocate(n); }
+	void deallocate(T* p, std::size_t n) { std::allocator<T>().deallocate(p, n); }
+	template <class U> void construct(U* p) { ::new (static_cast<void*>(p)) U; }
+	template <class U, class A0, class... A> void construct(U* p, A0&& a0, A&&... a) { ::new (static_cast<void*>(p)) U(std::forward<A0>(a0), std::forward<A>(a)...); }
+	template <class U> bool operator==(const RawAllocator<U>&) const { return true; }
+	template <class U> bool operator!=(const RawAllocator<U>&) const { return false; }
+};
+template <class T> using RawVector = std::vector<T, RawAllocator<T>>;
+
 struct Bvh {
-	std::vector<Node> nodes;         // nodes[0] is the root and is always internal
-	std::vector<TriRecord> tris;     // leaf order
+	RawVector<Node> nodes;           // nodes[0] is the root and is always internal
+	RawVector<TriRecord> tris;       // leaf order
 	float lo[3], hi[3];              // scene bounds (unpadded)
 	float diagonal;
 	float s0;                        // absolute ray-interval margin used with the relative slack

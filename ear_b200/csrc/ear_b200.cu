@@ -404,7 +404,9 @@ constexpr size_t kStackBytes = (size_t)kStackEntries * kBlock * sizeof(int2);
 struct ear_b200_scene {
 	int device = 0;
 	SceneDev dev{};
-	float4* d_nodes = nullptr;
+	unsigned char* d_image = nullptr;   // [header | nodes | tris | materials], one allocation
+	size_t image_bytes = 0;
+	float4* d_nodes = nullptr;          // views into d_image
 	float4* d_tris = nullptr;
 	float4* d_materials = nullptr;
 	std::vector<float> materials;
@@ -430,6 +432,7 @@ struct ear_b200_scene {
 	int vismap_res = -1;            // -1: choose from the triangle count; 0: disabled (EAR_B200_VISMAP_RES)
 	VisMapDev* d_maps = nullptr; int* d_map_of = nullptr; size_t map_of_cap = 0;
 	uint2* d_q_bvh = nullptr; size_t q_bvh_cap = 0;
+	int* d_vis_counts = nullptr; long long* d_vis_sums = nullptr; size_t vis_scratch_cap = 0;
 	std::vector<ear_b200_recorder> h_rec;   // host copy of the recorders of the current call
 	float maxabs = 0.0f;
 	// event pairs recorded around every engine launch, harvested at the engine's sync points
@@ -451,49 +454,47 @@ extern "C" int32_t ear_b200_device_count(void) {
 	return n;
 }
 
-extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_material, int32_t n_tris,
-                                         const float* materials, int32_t n_materials, int32_t n_bands, int32_t device,
-                                         ear_b200_scene** out) {
-	if (!out) return fail("scene_create: out is null");
-	*out = nullptr;
-	if (n_tris < 0 || n_materials <= 0 || n_bands <= 0 || n_bands > EAR_B200_MAX_BANDS)
-		return fail("scene_create: bad sizes (need n_materials >= 1, 1 <= n_bands <= 8)");
-	if ((n_tris > 0 && !verts) || !materials) return fail("scene_create: null input");
-	if (n_tris >= (1 << 28)) return fail("scene_create: too many triangles (limit 2^28)");
-	for (int32_t i = 0; i < n_tris && tri_material; ++i)
-		if (tri_material[i] < 0 || tri_material[i] >= n_materials) return fail("scene_create: material index out of range");
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-		cudaGetLastError();
-		return fail("no CUDA device: ear_b200 has no CPU fallback");
-	}
-	if (device < 0 || device >= ndev) return fail("scene_create: device index out of range");
-	CUDA_TRY(cudaSetDevice(device));
-	ear_b200_scene* s = new ear_b200_scene();
-	s->device = device;
-	const auto t0 = std::chrono::steady_clock::now();
-	Bvh bvh;
-	build_bvh(verts, tri_material, n_tris, bvh);
-	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-	s->n_tris = n_tris; s->n_materials = n_materials; s->n_bands = n_bands;
-	s->n_nodes = (int32_t)bvh.nodes.size(); s->depth = bvh.depth; s->diagonal = bvh.diagonal;
-	for (int k = 0; k < 3; ++k) { s->lo[k] = bvh.lo[k]; s->hi[k] = bvh.hi[k]; }
-	s->materials.assign(materials, materials + (size_t)n_materials * n_bands * 4);
+extern "C" void ear_b200_scene_destroy(ear_b200_scene* s);
+
+// Device image of a scene: [header | nodes | triangle records | materials] in ONE allocation, so a scene built
+// on one GPU can be replicated to the others with a single NVLink broadcast instead of N host BVH builds.
+struct ImageHeader {
+	uint32_t magic, version;
+	int32_t n_tris, n_materials, n_bands, n_nodes, depth, reserved;
+	float diagonal, s0, maxabs, reserved_f;
+	float lo[3], hi[3];
+	uint64_t off_nodes, off_tris, off_materials, bytes;
+};
+constexpr uint32_t kImageMagic = 0x42524145u;   // "EARB"
+constexpr size_t kImageAlign = 256;
+static_assert(sizeof(ImageHeader) <= kImageAlign, "header must fit its slot");
+
+static size_t image_round(size_t x) { return (x + kImageAlign - 1) / kImageAlign * kImageAlign; }
+
+static void image_layout(ImageHeader& h) {
+	h.off_nodes = kImageAlign;
+	h.off_tris = h.off_nodes + image_round(std::max<size_t>((size_t)h.n_nodes, 1) * sizeof(Node));
+	h.off_materials = h.off_tris + image_round(std::max<size_t>((size_t)h.n_tris, 1) * sizeof(TriRecord));
+	h.bytes = h.off_materials + image_round((size_t)h.n_materials * h.n_bands * 4 * sizeof(float));
+}
+
+// everything of scene creation that does not depend on where the image came from
+static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
+	s->n_tris = h.n_tris; s->n_materials = h.n_materials; s->n_bands = h.n_bands;
+	s->n_nodes = h.n_nodes; s->depth = h.depth; s->diagonal = h.diagonal; s->maxabs = h.maxabs;
+	for (int k = 0; k < 3; ++k) { s->lo[k] = h.lo[k]; s->hi[k] = h.hi[k]; }
+	s->image_bytes = (size_t)h.bytes;
+	s->d_nodes = (float4*)(s->d_image + h.off_nodes);
+	s->d_tris = (float4*)(s->d_image + h.off_tris);
+	s->d_materials = (float4*)(s->d_image + h.off_materials);
 	cudaDeviceProp prop;
-	CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+	CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
 	s->sm_count = prop.multiProcessorCount;
 	CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaMalloc(&s->d_nodes, std::max<size_t>(bvh.nodes.size(), 1) * sizeof(Node)));
-	CUDA_TRY(cudaMalloc(&s->d_tris, std::max<size_t>(bvh.tris.size(), 1) * sizeof(TriRecord)));
-	CUDA_TRY(cudaMalloc(&s->d_materials, s->materials.size() * sizeof(float)));
-	CUDA_TRY(cudaMemcpy(s->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
-	if (!bvh.tris.empty())
-		CUDA_TRY(cudaMemcpy(s->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMemcpy(s->d_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMalloc(&s->d_queue, sizeof(unsigned long long)));
 	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
-	s->dev.n_tris = n_tris; s->dev.n_materials = n_materials; s->dev.n_bands = n_bands;
-	s->dev.s0 = bvh.s0;
+	s->dev.n_tris = h.n_tris; s->dev.n_materials = h.n_materials; s->dev.n_bands = h.n_bands;
+	s->dev.s0 = h.s0;
 	// EAR_B200_EXACT_SLACK=1 selects the rigorous per-child interval bound (about 2x the node visits)
 	const char* ex = std::getenv("EAR_B200_EXACT_SLACK");
 	s->dev.exact = (ex && std::atoi(ex) != 0) ? 1 : 0;
@@ -509,21 +510,115 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	const char* sl = std::getenv("EAR_B200_SLOTS");
 	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
 	s->dev.vis_cap = kVisMaxList;
-	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::atoi(vc));
+	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(255, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
-	for (int k = 0; k < 3; ++k) s->maxabs = std::max(s->maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
 	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
 	CUDA_TRY(cudaMalloc(&s->d_scratch_counters, 8 * sizeof(unsigned long long)));
-	*out = s;
 	return 0;
+}
+
+static int32_t pick_device(int32_t device, const char* who) {
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+		cudaGetLastError();
+		return fail("no CUDA device: ear_b200 has no CPU fallback");
+	}
+	if (device < 0 || device >= ndev) return fail(std::string(who) + ": device index out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	return 0;
+}
+
+extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_material, int32_t n_tris,
+                                         const float* materials, int32_t n_materials, int32_t n_bands, int32_t device,
+                                         ear_b200_scene** out) {
+	if (!out) return fail("scene_create: out is null");
+	*out = nullptr;
+	if (n_tris < 0 || n_materials <= 0 || n_bands <= 0 || n_bands > EAR_B200_MAX_BANDS)
+		return fail("scene_create: bad sizes (need n_materials >= 1, 1 <= n_bands <= 8)");
+	if ((n_tris > 0 && !verts) || !materials) return fail("scene_create: null input");
+	if (n_tris >= (1 << 28)) return fail("scene_create: too many triangles (limit 2^28)");
+	for (int32_t i = 0; i < n_tris && tri_material; ++i)
+		if (tri_material[i] < 0 || tri_material[i] >= n_materials) return fail("scene_create: material index out of range");
+	if (int32_t rc = pick_device(device, "scene_create")) return rc;
+	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
+	s->device = device;
+	const auto t0 = std::chrono::steady_clock::now();
+	Bvh bvh;
+	build_bvh(verts, tri_material, n_tris, bvh);
+	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	ImageHeader h{};
+	h.magic = kImageMagic; h.version = EAR_B200_ABI_VERSION;
+	h.n_tris = n_tris; h.n_materials = n_materials; h.n_bands = n_bands;
+	h.n_nodes = (int32_t)bvh.nodes.size(); h.depth = bvh.depth; h.diagonal = bvh.diagonal; h.s0 = bvh.s0;
+	for (int k = 0; k < 3; ++k) {
+		h.lo[k] = bvh.lo[k]; h.hi[k] = bvh.hi[k];
+		h.maxabs = std::max(h.maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
+	}
+	image_layout(h);
+	s->materials.assign(materials, materials + (size_t)n_materials * n_bands * 4);
+	CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+	CUDA_TRY(cudaMemcpy(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(s->d_image + h.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+	if (!bvh.tris.empty())
+		CUDA_TRY(cudaMemcpy(s->d_image + h.off_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+	CUDA_TRY(cudaMemcpy(s->d_image + h.off_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice));
+	if (int32_t rc = scene_finish(s.get(), h)) return rc;
+	*out = s.release();
+	return 0;
+}
+
+extern "C" int32_t ear_b200_scene_image_size(ear_b200_scene* s, uint64_t* bytes) {
+	if (!s || !bytes) return fail("scene_image_size: null argument");
+	*bytes = (uint64_t)s->image_bytes;
+	return 0;
+}
+
+extern "C" int32_t ear_b200_scene_image_write(ear_b200_scene* s, void* dst_device, uint64_t bytes) {
+	if (!s || !dst_device) return fail("scene_image_write: null argument");
+	if (bytes < (uint64_t)s->image_bytes) return fail("scene_image_write: destination smaller than the image");
+	CUDA_TRY(cudaSetDevice(s->device));
+	CUDA_TRY(cudaMemcpy(dst_device, s->d_image, s->image_bytes, cudaMemcpyDefault));
+	return 0;
+}
+
+extern "C" int32_t ear_b200_scene_create_from_image(const void* src_device, uint64_t bytes, int32_t device, ear_b200_scene** out) {
+	if (!out) return fail("scene_create_from_image: out is null");
+	*out = nullptr;
+	if (!src_device || bytes < kImageAlign) return fail("scene_create_from_image: no image");
+	if (int32_t rc = pick_device(device, "scene_create_from_image")) return rc;
+	ImageHeader h{};
+	CUDA_TRY(cudaMemcpy(&h, src_device, sizeof(h), cudaMemcpyDefault));
+	ImageHeader want = h;
+	if (h.magic != kImageMagic || h.version != (uint32_t)EAR_B200_ABI_VERSION)
+		return fail("scene_create_from_image: not a scene image of this library version");
+	if (h.n_tris < 0 || h.n_nodes < 1 || h.n_materials <= 0 || h.n_bands <= 0 || h.n_bands > EAR_B200_MAX_BANDS)
+		return fail("scene_create_from_image: corrupt header");
+	image_layout(want);
+	if (want.off_nodes != h.off_nodes || want.off_tris != h.off_tris || want.off_materials != h.off_materials || want.bytes != h.bytes ||
+	    h.bytes > bytes)
+		return fail("scene_create_from_image: image size does not match its header");
+	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
+	s->device = device;
+	CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+	CUDA_TRY(cudaMemcpy(s->d_image, src_device, (size_t)h.bytes, cudaMemcpyDefault));
+	s->materials.resize((size_t)h.n_materials * h.n_bands * 4);
+	CUDA_TRY(cudaMemcpy(s->materials.data(), s->d_image + h.off_materials, s->materials.size() * sizeof(float), cudaMemcpyDeviceToHost));
+	if (int32_t rc = scene_finish(s.get(), h)) return rc;
+	*out = s.release();
+	return 0;
+}
+
+extern "C" int32_t ear_b200_scene_clone(ear_b200_scene* s, int32_t device, ear_b200_scene** out) {
+	if (!s) return fail("scene_clone: null scene");
+	return ear_b200_scene_create_from_image(s->d_image, (uint64_t)s->image_bytes, device, out);
 }
 
 extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_materials);
+	cudaFree(s->d_image);
 	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue);
 	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
@@ -533,7 +628,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	for (auto& m : s->vismaps) { cudaFree(m.d_offsets); cudaFree(m.d_items); }
-	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh);
+	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh); cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -783,25 +878,58 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	ear_b200_scene::VisMapHost m{};
 	std::memcpy(m.x, x, 12); m.res = res;
 	const int n_tex = 6 * res * res;
-	int* d_counts = nullptr;
-	CUDA_TRY(cudaMalloc(&d_counts, (size_t)n_tex * sizeof(int)));
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!dbg) return;
+		cudaDeviceSynchronize();
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[ear_b200] vismap: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
+	// scratch (texel counters + block sums) is kept with the scene: every map of a scene has the same size
+	if ((size_t)n_tex > s->vis_scratch_cap) {
+		cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums);
+		s->d_vis_counts = nullptr; s->d_vis_sums = nullptr; s->vis_scratch_cap = 0;
+		CUDA_TRY(cudaMalloc(&s->d_vis_counts, (size_t)n_tex * sizeof(int)));
+		CUDA_TRY(cudaMalloc(&s->d_vis_sums, kVisScanBlocks * sizeof(long long)));
+		s->vis_scratch_cap = (size_t)n_tex;
+	}
+	int* d_counts = s->d_vis_counts;
 	CUDA_TRY(cudaMalloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
+	lap("alloc + clear");
 	const double reach = 2.0 * (double)s->diagonal + 1.0;
-	const unsigned grid = (unsigned)((6LL * s->n_tris + 127) / 128);
-	vis_build_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, nullptr, nullptr);
-	vis_scan_kernel<<<1, 1024, 0, stream>>>(d_counts, m.d_offsets, n_tex);
+	int id_bits = 7;   // thread ids cover [0, 2^id_bits) >= 6 * n_tris, visited in bit-reversed order
+	while ((1LL << id_bits) < 6LL * s->n_tris) ++id_bits;
+	const unsigned grid = (unsigned)((1LL << id_bits) / 128);
+	const int cap = s->dev.vis_cap;
+	const int per = (n_tex + kVisScanBlocks - 1) / kVisScanBlocks;
+	vis_build_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, nullptr, nullptr, id_bits);
+	lap("count pass");
+	vis_scan_sums_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, n_tex, per, cap);
+	vis_scan_top_kernel<<<1, kVisScanBlocks, 0, stream>>>(s->d_vis_sums, m.d_offsets, n_tex);
+	vis_scan_offsets_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, m.d_offsets, n_tex, per, cap);
 	int total = 0;
 	CUDA_TRY(cudaMemcpyAsync(&total, m.d_offsets + n_tex, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	CUDA_TRY(cudaStreamSynchronize(stream));
-	if (total < 0) { cudaFree(d_counts); cudaFree(m.d_offsets); return fail("visibility map overflow"); }
+	lap("scan");
+	if (dbg) {
+		std::vector<int> hc((size_t)n_tex);
+		cudaMemcpy(hc.data(), d_counts, (size_t)n_tex * sizeof(int), cudaMemcpyDeviceToHost);
+		long long sum = 0, over = 0, over_sum = 0; int mx = 0;
+		for (int v : hc) { sum += v; mx = std::max(mx, v); if (v > cap) { ++over; over_sum += v; } }
+		std::fprintf(stderr, "[ear_b200] vismap: %lld entries, longest list %d, %lld texels over the cap hold %lld entries, stored %d\n", sum, mx, over, over_sum, total);
+		t_prev = std::chrono::steady_clock::now();
+	}
+	if (total < 0) { cudaFree(m.d_offsets); return fail("visibility map overflow"); }
 	m.n_items = (size_t)total;
 	CUDA_TRY(cudaMalloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
-	vis_build_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, m.d_offsets, m.d_items);
+	vis_build_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, m.d_offsets, m.d_items, id_bits);
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaStreamSynchronize(stream));
-	cudaFree(d_counts);
+	lap("fill pass");
 	s->vismaps.push_back(m);
 	*index = (int)s->vismaps.size() - 1;
 	return 0;
@@ -844,8 +972,12 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / 4));
 	slots = (slots + 255) / 256 * 256;
 	if (int32_t rc = ensure_pool(s, (size_t)slots, (size_t)slots * std::max(1, p.n_rec))) return rc;
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	auto t_a = std::chrono::steady_clock::now();
+	if (dbg) cudaDeviceSynchronize();
 	int n_mapped = 0;
 	if (p.n_rec > 0) { if (int32_t rc = prepare_vismaps(s, p.n_ctx, p.n_rec, stream, &n_mapped)) return rc; }
+	if (dbg) { cudaDeviceSynchronize(); std::fprintf(stderr, "[ear_b200] pool + visibility maps: %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count()); }
 	const size_t n_queries = (size_t)slots * std::max(1, p.n_rec);
 	if (n_mapped && n_queries > s->q_bvh_cap) {
 		cudaFree(s->d_q_bvh);
@@ -957,6 +1089,15 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	if (!s || !out) return fail("render: null scene/out");
 	*out = nullptr;
 	CUDA_TRY(cudaSetDevice(s->device));
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	auto tick = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!dbg) return;
+		cudaDeviceSynchronize();
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[ear_b200] render: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
+		tick = now;
+	};
 	RenderParams p{};
 	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, s->stream, p)) return rc;
 	const int32_t n_bins = ear_b200_default_bins(s, opt);
@@ -969,11 +1110,13 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
 	init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(d_range, (int)n_tracks);
 	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = d_counters;
+	lap("upload + histogram alloc");
 	cudaEvent_t e0, e1;
 	CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
 	CUDA_TRY(cudaEventRecord(e0, s->stream));
 	if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
 	CUDA_TRY(cudaEventRecord(e1, s->stream));
+	lap("trace (incl. pool + maps)");
 	if (!opt || opt->finalise) { if (int32_t rc = launch_finalise(s, p, s->stream)) return rc; }
 	std::vector<uint32_t> range(n_tracks * 2);
 	unsigned long long counters[8];
@@ -998,6 +1141,7 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 		CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + k * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
 	}
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
+	lap("finalise + track download");
 	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
 	res->contributions = counters[3]; res->bin_updates = counters[4]; res->dropped_updates = counters[5];
 	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;

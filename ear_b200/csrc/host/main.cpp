@@ -176,21 +176,25 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 	uint64_t segments = 0; double device_ms = 0.0;
 	std::vector<uint64_t> seg_per_gpu((size_t)n_gpus, 0);
 	std::vector<double> ms_per_gpu((size_t)n_gpus, 0.0);
+	// one BVH build: the scene is built on GPU 0 and its device image copied to the other GPUs
+	std::vector<ear_b200_scene*> scenes((size_t)n_gpus, nullptr);
+	if (ear_b200_scene_create(sf.vertices.data(), sf.tri_material.data(), sf.triangle_count(), table.data(),
+	                          (int32_t)std::max<size_t>(sf.materials.size(), 1), 3, 0, &scenes[0]))
+		throw std::runtime_error(ear_b200_last_error());
 	for (int g = 0; g < n_gpus; ++g) {
 		workers.emplace_back([&, g]() {
 			std::vector<int> mine;
 			for (int c = g; c < n_ctx; c += n_gpus) mine.push_back(c);
 			std::vector<ear_b200_context> lc; std::vector<ear_b200_recorder> lr;
 			for (int c : mine) { lc.push_back(cc[c]); for (int r = 0; r < n_rec; ++r) lr.push_back(rr[(size_t)c * n_rec + r]); }
-			ear_b200_scene* scene = nullptr;
-			if (ear_b200_scene_create(sf.vertices.data(), sf.tri_material.data(), sf.triangle_count(), table.data(),
-			                          (int32_t)std::max<size_t>(sf.materials.size(), 1), 3, g, &scene)) { errors[g] = ear_b200_last_error(); return; }
+			if (g > 0 && ear_b200_scene_clone(scenes[0], g, &scenes[g])) { errors[g] = ear_b200_last_error(); return; }
+			ear_b200_scene* scene = scenes[g];
 			ear_b200_result* res = nullptr;
 			// the Philox stream is keyed by the context's position in the call: keep the global index
 			// stable by rendering each context as its own call slot would be -- contexts of one GPU
 			// are passed together, keyed 0..k-1; different GPUs use different seeds
 			ear_b200_options o = opt; o.seed = opt.seed + 0x9E3779B97F4A7C15ull * (uint64_t)g;
-			if (ear_b200_render(scene, lc.data(), (int32_t)lc.size(), lr.data(), n_rec, &o, &res)) { errors[g] = ear_b200_last_error(); ear_b200_scene_destroy(scene); return; }
+			if (ear_b200_render(scene, lc.data(), (int32_t)lc.size(), lr.data(), n_rec, &o, &res)) { errors[g] = ear_b200_last_error(); return; }
 			for (size_t i = 0; i < mine.size(); ++i) {
 				Context& c = ctxs[mine[i]];
 				for (int r = 0; r < n_rec; ++r)
@@ -204,10 +208,10 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 			seg_per_gpu[g] = res->segments; ms_per_gpu[g] = res->device_ms;
 			if (res->dropped_updates) errors[g] = "histogram too short: bin updates were dropped";
 			ear_b200_result_free(res);
-			ear_b200_scene_destroy(scene);
 		});
 	}
 	for (auto& w : workers) w.join();
+	for (ear_b200_scene* sc : scenes) ear_b200_scene_destroy(sc);
 	for (int g = 0; g < n_gpus; ++g) {
 		if (!errors[g].empty()) throw std::runtime_error(errors[g]);
 		segments += seg_per_gpu[g]; device_ms = std::max(device_ms, ms_per_gpu[g]);

@@ -95,41 +95,112 @@ __device__ __forceinline__ bool vis_footprint(const SceneDev& sc, int t, const d
 	return true;
 }
 
-// pass 0: count list lengths; pass 1: fill the lists (cursor = running fill position per texel)
+// pass 0: count list lengths; pass 1: fill the lists (cursor = running fill position per texel).
+// One (triangle, face) footprint per thread; footprints of more than a few texels are spread over the warp
+// (a near triangle covers thousands of texels: left to one thread its atomics serialise into hundreds of ms).
+// Texels whose list is longer than the cap are never looked up (the query goes to the BVH), so pass 1 skips them:
+// their offset carries kVisOverlong and they own no items.
+constexpr int kVisOverlong = (int)0x80000000u;
+
 template <int PASS>
-__global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, double x1, double x2, int res, double reach, double maxabs,
-                                                        int* counts_or_cursor, const int* offsets, int* items) {
-	const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one (triangle, face) per thread
-	if (id >= 6LL * sc.n_tris) return;
-	const int t = (int)(id / 6), face = (int)(id % 6);
-	const double X[3] = {x0, x1, x2};
-	int i0, i1, j0, j1;
-	if (!vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1)) return;
-	for (int j = j0; j <= j1; ++j)
-		for (int i = i0; i <= i1; ++i) {
-			const int texel = (face * res + j) * res + i;
-			if (PASS == 0) atomicAdd(counts_or_cursor + texel, 1);
-			else items[offsets[texel] + atomicAdd(counts_or_cursor + texel, 1)] = t;
-		}
+__device__ __forceinline__ void vis_emit(int texel, int t, int* counts_or_cursor, const int* offsets, int* items) {
+	if (PASS == 0) atomicAdd(counts_or_cursor + texel, 1);
+	else {
+		const int o = offsets[texel];
+		if (o >= 0) items[o + atomicAdd(counts_or_cursor + texel, 1)] = t;
+	}
 }
 
-// exclusive scan of n ints by one block (n up to a few million), out[n] = total
-__global__ void __launch_bounds__(1024) vis_scan_kernel(const int* in, int* out, int n) {
-	__shared__ long long part[1024];
-	const int per = (n + 1023) / 1024;
-	const int beg = min(n, (int)threadIdx.x * per), end = min(n, beg + per);
+template <int PASS>
+__global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, double x1, double x2, int res, double reach, double maxabs,
+                                                        int* counts_or_cursor, const int* offsets, int* items, int id_bits) {
+	// neighbouring triangles cover the same texels: taking them in bit-reversed order keeps the atomics of the
+	// threads in flight on different addresses
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long id = (long long)(__brevll(tid) >> (64 - id_bits));
+	const int lane = threadIdx.x & 31;
+	const double X[3] = {x0, x1, x2};
+	int i0 = 0, i1 = -1, j0 = 0, j1 = -1, t = 0, face = 0;
+	bool valid = id < 6LL * sc.n_tris;
+	if (valid) {
+		t = (int)(id / 6); face = (int)(id % 6);
+		valid = vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1);
+	}
+	const int w = valid ? i1 - i0 + 1 : 0;
+	const int area = valid ? w * (j1 - j0 + 1) : 0;
+	constexpr int kOwn = 4;
+	if (area > 0 && area <= kOwn)
+		for (int k = 0; k < area; ++k) vis_emit<PASS>((face * res + j0 + k / w) * res + i0 + k % w, t, counts_or_cursor, offsets, items);
+	unsigned big = __ballot_sync(0xffffffffu, area > kOwn);
+	while (big) {
+		const int src = __ffs(big) - 1;
+		big &= big - 1;
+		const int b_i0 = __shfl_sync(0xffffffffu, i0, src), b_j0 = __shfl_sync(0xffffffffu, j0, src), b_w = __shfl_sync(0xffffffffu, w, src);
+		const int b_area = __shfl_sync(0xffffffffu, area, src), b_t = __shfl_sync(0xffffffffu, t, src), b_face = __shfl_sync(0xffffffffu, face, src);
+		for (int k = lane; k < b_area; k += 32)
+			vis_emit<PASS>((b_face * res + b_j0 + k / b_w) * res + b_i0 + k % b_w, b_t, counts_or_cursor, offsets, items);
+	}
+}
+
+// Exclusive scan of the list lengths in three launches (block sums, scan of the sums, offsets).  Lengths above
+// `cap` count as zero and mark their offset with kVisOverlong.  out[n] = total (negative on overflow).
+constexpr int kVisScanBlocks = 1024;
+
+__device__ __forceinline__ int vis_len(int v, int cap) { return v > cap ? 0 : v; }
+
+__global__ void __launch_bounds__(1024) vis_scan_sums_kernel(const int* in, long long* sums, int n, int per, int cap) {
+	__shared__ long long part[32];
+	const int beg = min(n, (int)blockIdx.x * per), end = min(n, beg + per);
 	long long s = 0;
-	for (int i = beg; i < end; ++i) s += in[i];
-	part[threadIdx.x] = s;
+	for (int i = beg + threadIdx.x; i < end; i += 1024) s += vis_len(in[i], cap);
+	for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		s = part[threadIdx.x];
+		for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+		if (threadIdx.x == 0) sums[blockIdx.x] = s;
+	}
+}
+
+__global__ void __launch_bounds__(1024) vis_scan_top_kernel(long long* sums, int* out, int n) {
+	__shared__ long long part[kVisScanBlocks];
+	part[threadIdx.x] = sums[threadIdx.x];
 	__syncthreads();
 	if (threadIdx.x == 0) {
 		long long run = 0;
-		for (int i = 0; i < 1024; ++i) { const long long v = part[i]; part[i] = run; run += v; }
-		out[n] = (int)run;
+		for (int i = 0; i < kVisScanBlocks; ++i) { const long long v = part[i]; part[i] = run; run += v; }
+		out[n] = run < 0x7fffffffLL ? (int)run : -1;
 	}
 	__syncthreads();
-	long long run = part[threadIdx.x];
-	for (int i = beg; i < end; ++i) { out[i] = (int)run; run += in[i]; }
+	sums[threadIdx.x] = part[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(1024) vis_scan_offsets_kernel(const int* in, const long long* sums, int* out, int n, int per, int cap) {
+	__shared__ int warp_tot[32];
+	__shared__ int tile_tot;
+	const int beg = min(n, (int)blockIdx.x * per), end = min(n, beg + per);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	long long run = sums[blockIdx.x];
+	for (int base = beg; base < end; base += 1024) {   // block-uniform trip count
+		const int i = base + threadIdx.x;
+		const int raw = i < end ? in[i] : 0;
+		const int v = vis_len(raw, cap);
+		int inc = v;
+		for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+		if (lane == 31) warp_tot[wid] = inc;
+		__syncthreads();
+		if (wid == 0) {
+			int wv = warp_tot[lane], winc = wv;
+			for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, winc, o); if (lane >= o) winc += u; }
+			warp_tot[lane] = winc - wv;
+			if (lane == 31) tile_tot = winc;
+		}
+		__syncthreads();
+		if (i < end) out[i] = (int)(run + warp_tot[wid] + inc - v) | (raw > cap ? kVisOverlong : 0);
+		run += tile_tot;
+		__syncthreads();
+	}
 }
 
 // K4 through the maps: one query per thread.  Visible queries go to vis_list; queries whose texel list is too
@@ -154,8 +225,8 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 				const float4 s0 = pool.sh0[slot];
 				const V3 pnt = mk(s0.x, s0.y, s0.z), x = mk(mp.x[0], mp.x[1], mp.x[2]);
 				const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
-				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1];
-				if (end - beg > sc.vis_cap) fallback = true;
+				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1] & ~kVisOverlong;
+				if (beg < 0) fallback = true;   // list longer than the cap: not stored
 				else {
 					const V3 d = vsub(x, pnt);   // LineSeg(p, x) = Ray(p, x - p)
 					visible = true;

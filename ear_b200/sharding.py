@@ -28,3 +28,97 @@ def reduce_partials(hist, first_sample, real_length, dst: int = 0) -> None:
     dist.reduce(hist, dst=dst, op=dist.ReduceOp.SUM)
     dist.reduce(first_sample, dst=dst, op=dist.ReduceOp.MIN)
     dist.reduce(real_length, dst=dst, op=dist.ReduceOp.MAX)
+
+
+def create_replicated_scene(verts, tri_material, materials, device: int, src: int = 0):
+    """One host BVH build per job: rank `src` builds the scene on its GPU, broadcasts the device image
+    (header + nodes + triangle records + materials, one contiguous buffer) over NCCL / NVLink, and the other
+    ranks adopt the received bytes (ear_b200_scene_create_from_image).  With a single process this is just
+    Scene(...).  Needs the NCCL backend for world > 1 (the image lives in device memory)."""
+    import torch
+    import torch.distributed as dist
+    from . import api
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return api.Scene(verts, tri_material, materials, device=device)
+    rank = dist.get_rank()
+    dev = torch.device("cuda", device)
+    size = torch.zeros((2,), dtype=torch.int64, device=dev)
+    scene = None
+    if rank == src:
+        scene = api.Scene(verts, tri_material, materials, device=device)
+        size[0] = scene.image_size()
+        size[1] = scene.n_bands
+    dist.broadcast(size, src=src)
+    n_bytes, n_bands = int(size[0].item()), int(size[1].item())
+    image = torch.empty((n_bytes,), dtype=torch.uint8, device=dev)
+    if rank == src:
+        scene.image_write(image.data_ptr(), n_bytes)
+    dist.broadcast(image, src=src)
+    if rank != src:
+        scene = api.Scene.from_image(image.data_ptr(), n_bytes, n_bands, device=device)
+    return scene
+
+
+def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0, dst: int = 0):
+    """Scene::Render (src/Scene.cpp:111-318) over all ranks of the default process group: every rank traces its
+    ray-id range of every context into a device-resident partial histogram, the partials meet in ONE reduce on
+    rank `dst`, which finalises and downloads the tracks.  Host contexts in, host tracks out (RenderResult on
+    `dst`, None elsewhere).  Identical to Scene.render() when there is one rank."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import api
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if world == 1:
+        return scene.render(contexts, recorders, max_bounces=max_bounces, seed=seed, n_bins=n_bins)
+    lib = scene.lib
+    dev = torch.device("cuda", scene.device)
+    n_ctx = len(contexts)
+    ctx_c = api.pack_contexts(contexts)
+    rec_c, n_rec = api.pack_recorders(recorders, n_ctx)
+    rays = max(int(c.num_samples) for c in contexts) if n_ctx else 0
+    lo, hi = shard_bounds(rays, rank, world)
+    opt = api.make_options(max_bounces, n_bins, seed, lo, hi - lo, False)
+    if n_bins <= 0:
+        n_bins = scene.default_bins(opt)
+    n_tracks = n_ctx * n_rec * 2
+    hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
+    rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
+    rng[:, 0] = api.FIRST_SAMPLE_INIT
+    rng[:, 1] = 0
+    counters = torch.zeros((8,), dtype=torch.int64, device=dev)
+    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
+                                              hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
+    first = rng[:, 0].contiguous()
+    real = rng[:, 1].contiguous()
+    reduce_partials(hist, first, real, dst=dst)
+    dist.reduce(counters, dst=dst, op=dist.ReduceOp.SUM)
+    if rank != dst:
+        return None
+    rng[:, 0] = first
+    rng[:, 1] = real
+    api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
+                                                 hist.data_ptr(), rng.data_ptr(), sp))
+    h_rng = rng.cpu().numpy()
+    c = counters.cpu().numpy()
+    # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
+    longest = int(h_rng[:, 1].max()) + 1 if n_tracks else 0
+    h_hist = hist[:, :longest].cpu().numpy()
+    tracks = []
+    for ci in range(n_ctx):
+        per_rec = []
+        for k in range(n_rec):
+            pair = []
+            for tr in range(2 if rec_c[ci * n_rec + k].kind == api.STEREO else 1):
+                t = (ci * n_rec + k) * 2 + tr
+                real_len = int(h_rng[t, 1])
+                data = np.zeros((n_bins,), np.float32)       # Track.data spans the whole buffer, like Scene.render()
+                data[:real_len + 1] = h_hist[t, :real_len + 1]
+                pair.append(api.Track(data, int(h_rng[t, 0]), real_len))
+            per_rec.append(pair)
+        tracks.append(per_rec)
+    return api.RenderResult(tracks, int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), 0.0)

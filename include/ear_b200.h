@@ -119,6 +119,21 @@ int32_t ear_b200_scene_create(const float* verts /*[n_tris][3][3]*/, const int32
                               int32_t device, ear_b200_scene** out);
 void ear_b200_scene_destroy(ear_b200_scene* scene);
 
+/* Multi-GPU replication: the acceleration data of a scene is one contiguous device
+ * image.  One rank builds the scene, writes its image into a device buffer it can broadcast (NCCL over
+ * NVLink), and every other rank adopts the received bytes -- one host BVH build per job instead of one per
+ * GPU.  The reference has nothing to replace here (all its threads share one Scene, src/Scene.cpp:283-312);
+ * this is the cross-process form of that sharing.
+ *   image_size   bytes the image occupies
+ *   image_write  copies the image to `dst_device` (device memory on any GPU of this process, >= image_size)
+ *   create_from_image  new scene on `device` from image bytes resident in device memory; the bytes are copied,
+ *                      the source buffer may be freed afterwards.  Fails on a foreign or truncated image. */
+int32_t ear_b200_scene_image_size(ear_b200_scene* scene, uint64_t* bytes);
+int32_t ear_b200_scene_image_write(ear_b200_scene* scene, void* dst_device, uint64_t bytes);
+int32_t ear_b200_scene_create_from_image(const void* src_device, uint64_t bytes, int32_t device, ear_b200_scene** out);
+/* Same process, several GPUs: a copy of `scene` on `device` (peer copy of the image, no second BVH build). */
+int32_t ear_b200_scene_clone(ear_b200_scene* scene, int32_t device, ear_b200_scene** out);
+
 /* Harness: Mesh::RayIntersection (src/Mesh.cpp:33-56) for explicit rays.
  * tri_index[i] = winning triangle or -1; t[i] = its distance (undefined on miss). */
 int32_t ear_b200_first_hit(ear_b200_scene* scene, const float* origins /*[n][3]*/, const float* dirs /*[n][3]*/,
@@ -145,7 +160,9 @@ void ear_b200_result_free(ear_b200_result* result);
  *   d_hist   float  [n_contexts][n_recorders][2][n_bins]   (zeroed by the caller)
  *   d_range  uint32 [n_contexts][n_recorders][2][2]        {first_sample (init 132299), real_length (init 0)}
  *   d_counters uint64 [8]: rays, segments, occlusion_queries, contributions, bin_updates, dropped, -, -
- * `stream` is a cudaStream_t (0 = legacy default stream).  Asynchronous. */
+ * `stream` is a cudaStream_t (0 = legacy default stream).  All work is ordered on `stream`; the call returns once
+ * the last ray has ended (the wavefront loop reads a 32-byte counter block every few iterations to know when to
+ * stop), so the results are complete -- but not yet visible to other streams -- on return. */
 int32_t ear_b200_trace_device(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
                               const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
                               int32_t n_bins, float* d_hist, uint32_t* d_range, uint64_t* d_counters, void* stream);

@@ -153,3 +153,40 @@ def test_errors_are_reported_not_swallowed():
         gpu.render([api.Context(7, 10, 1.0, (0, 0, 1))], [api.Recorder((1, 0, 1))])   # band outside the table
     with pytest.raises(api.EarError):
         api.Scene(sc.triangles(), np.full(12, 3, np.int32), sc.material_table())       # bad material index
+
+
+def test_scene_image_round_trip(ob):
+    """Multi-GPU replication path on one GPU: a scene adopted from another scene's device image answers every
+    query and renders exactly like the scene that was built from the triangles; a damaged image is refused."""
+    import torch
+    sc = common.named_scene("example1")
+    sc.samples = 6000
+    built = api.Scene.from_def(sc)
+    n = built.image_size()
+    assert n > 0 and n % 256 == 0
+    buf = torch.zeros((n,), dtype=torch.uint8, device="cuda:0")
+    built.image_write(buf.data_ptr(), n)
+    torch.cuda.synchronize()
+    adopted = api.Scene.from_image(buf.data_ptr(), n, built.n_bands, device=0)
+    del buf
+    o, d = common.make_rays(sc, 20000)
+    bi, bt = built.first_hit(o, d)
+    ai, at = adopted.first_hit(o, d)
+    assert np.array_equal(ai, bi) and np.array_equal(at.view(np.uint32)[bi >= 0], bt.view(np.uint32)[bi >= 0])
+    ctxs, recs = api.contexts_from_def(sc)
+    ra = adopted.render(ctxs, recs, max_bounces=40, seed=5)
+    rb = built.render(ctxs, recs, max_bounces=40, seed=5)
+    assert ra.segments == rb.segments and ra.contributions == rb.contributions
+    for c in range(len(ctxs)):
+        f, g = ra.tracks[c][0][0], rb.tracks[c][0][0]
+        assert (f.first_sample, f.real_length) == (g.first_sample, g.real_length)
+        assert np.abs(f.data - g.data).max() <= 1e-4 * np.abs(g.data).max()
+    bad = torch.zeros((n,), dtype=torch.uint8, device="cuda:0")
+    built.image_write(bad.data_ptr(), n)
+    bad[0] = 0   # magic
+    with pytest.raises(api.EarError):
+        api.Scene.from_image(bad.data_ptr(), n, built.n_bands, device=0)
+    with pytest.raises(api.EarError):
+        api.Scene.from_image(bad.data_ptr(), 128, built.n_bands, device=0)
+    with pytest.raises(api.EarError):
+        built.image_write(bad.data_ptr(), n - 256)
