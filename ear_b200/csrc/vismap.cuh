@@ -42,8 +42,13 @@ __device__ __forceinline__ int vis_texel(const VisMapDev& mp, float dx, float dy
 }
 
 // Conservative footprint of triangle `t` on face `face` of the cube map around X: texel rectangle [i0,i1]x[j0,j1].
+// When all three vertices lie in front of the face, `edge` also receives the three edge functions of the projected
+// triangle, pushed outward by the margin plus half a texel diagonal-wise: texel centre (u, v) can only matter if
+// edge[3k] * u + edge[3k+1] * v + edge[3k+2] >= 0 for k = 0..2 (conservative rasterisation; about half of the
+// bounding rectangle of a triangle is empty).  has_edges = false means "take the whole rectangle".
 __device__ __forceinline__ bool vis_footprint(const SceneDev& sc, int t, const double X[3], int res, int face, double reach,
-                                              double maxabs, int& i0, int& i1, int& j0, int& j1) {
+                                              double maxabs, int& i0, int& i1, int& j0, int& j1, float edge[9], bool& has_edges) {
+	has_edges = false;
 	const float4 r0 = sc.tris[4 * (size_t)t], r1 = sc.tris[4 * (size_t)t + 1], r2 = sc.tris[4 * (size_t)t + 2];
 	double a[3][3] = {{(double)r0.x - X[0], (double)r0.y - X[1], (double)r0.z - X[2]}, {0, 0, 0}, {0, 0, 0}};
 	const double e1[3] = {r1.x, r1.y, r1.z}, e2[3] = {r2.x, r2.y, r2.z};
@@ -86,6 +91,28 @@ __device__ __forceinline__ bool vis_footprint(const SceneDev& sc, int t, const d
 		}
 	}
 	if (!any) return false;
+	{
+		const double w0 = sgn * a[0][m], w1 = sgn * a[1][m], w2 = sgn * a[2][m];
+		if (w0 >= wmin && w1 >= wmin && w2 >= wmin) {
+			const double pu[3] = {a[0][b] / w0, a[1][b] / w1, a[2][b] / w2}, pv[3] = {a[0][c] / w0, a[1][c] / w1, a[2][c] / w2};
+			const double orient = (pu[1] - pu[0]) * (pv[2] - pv[0]) - (pv[1] - pv[0]) * (pu[2] - pu[0]);
+			const double span = fmax(fmax(fabs(pu[1] - pu[0]), fabs(pu[2] - pu[0])), fmax(fabs(pv[1] - pv[0]), fabs(pv[2] - pv[0])));
+			if (fabs(orient) > 1e-12 * span * span) {   // not edge-on
+				const double flip = orient > 0.0 ? 1.0 : -1.0, grow = margin + 1.0 / (double)res;
+				has_edges = true;
+				for (int k = 0; k < 3; ++k) {
+					const int k1 = (k + 1) % 3;
+					double A = -(pv[k1] - pv[k]) * flip, B = (pu[k1] - pu[k]) * flip;
+					const double mx = fmax(fabs(A), fabs(B));
+					if (!(mx > 0.0)) { has_edges = false; break; }
+					A /= mx; B /= mx;
+					double C = -(A * pu[k] + B * pv[k]) + (fabs(A) + fabs(B)) * grow;
+					C += 1e-5 + 1e-6 * fabs(C);   // float evaluation of the test below
+					edge[3 * k] = (float)A; edge[3 * k + 1] = (float)B; edge[3 * k + 2] = __double2float_ru(C);
+				}
+			}
+		}
+	}
 	u0 -= margin; u1 += margin; v0 -= margin; v1 += margin;
 	if (u1 < -1.0 || u0 > 1.0 || v1 < -1.0 || v0 > 1.0) return false;
 	i0 = max(0, min(res - 1, (int)floor((fmax(u0, -1.0) + 1.0) * 0.5 * res)));
@@ -121,24 +148,40 @@ __global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, 
 	const int lane = threadIdx.x & 31;
 	const double X[3] = {x0, x1, x2};
 	int i0 = 0, i1 = -1, j0 = 0, j1 = -1, t = 0, face = 0;
+	float edge[9] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f};   // accepts every texel
 	bool valid = id < 6LL * sc.n_tris;
 	if (valid) {
+		bool has_edges;
 		t = (int)(id / 6); face = (int)(id % 6);
-		valid = vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1);
+		valid = vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1, edge, has_edges);
+		if (!has_edges) { for (int k = 0; k < 3; ++k) { edge[3 * k] = 0.0f; edge[3 * k + 1] = 0.0f; edge[3 * k + 2] = 1.0f; } }
 	}
 	const int w = valid ? i1 - i0 + 1 : 0;
 	const int area = valid ? w * (j1 - j0 + 1) : 0;
+	const float texel = 2.0f / (float)res;
 	constexpr int kOwn = 4;
 	if (area > 0 && area <= kOwn)
-		for (int k = 0; k < area; ++k) vis_emit<PASS>((face * res + j0 + k / w) * res + i0 + k % w, t, counts_or_cursor, offsets, items);
+		for (int k = 0; k < area; ++k) {
+			const int i = i0 + k % w, j = j0 + k / w;
+			const float u = ((float)i + 0.5f) * texel - 1.0f, v = ((float)j + 0.5f) * texel - 1.0f;
+			if (edge[0] * u + edge[1] * v + edge[2] >= 0.0f && edge[3] * u + edge[4] * v + edge[5] >= 0.0f && edge[6] * u + edge[7] * v + edge[8] >= 0.0f)
+				vis_emit<PASS>((face * res + j) * res + i, t, counts_or_cursor, offsets, items);
+		}
 	unsigned big = __ballot_sync(0xffffffffu, area > kOwn);
 	while (big) {
 		const int src = __ffs(big) - 1;
 		big &= big - 1;
 		const int b_i0 = __shfl_sync(0xffffffffu, i0, src), b_j0 = __shfl_sync(0xffffffffu, j0, src), b_w = __shfl_sync(0xffffffffu, w, src);
 		const int b_area = __shfl_sync(0xffffffffu, area, src), b_t = __shfl_sync(0xffffffffu, t, src), b_face = __shfl_sync(0xffffffffu, face, src);
-		for (int k = lane; k < b_area; k += 32)
-			vis_emit<PASS>((b_face * res + b_j0 + k / b_w) * res + b_i0 + k % b_w, b_t, counts_or_cursor, offsets, items);
+		float e[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) e[k] = __shfl_sync(0xffffffffu, edge[k], src);
+		for (int k = lane; k < b_area; k += 32) {
+			const int i = b_i0 + k % b_w, j = b_j0 + k / b_w;
+			const float u = ((float)i + 0.5f) * texel - 1.0f, v = ((float)j + 0.5f) * texel - 1.0f;
+			if (e[0] * u + e[1] * v + e[2] >= 0.0f && e[3] * u + e[4] * v + e[5] >= 0.0f && e[6] * u + e[7] * v + e[8] >= 0.0f)
+				vis_emit<PASS>((b_face * res + j) * res + i, b_t, counts_or_cursor, offsets, items);
+		}
 	}
 }
 
