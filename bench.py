@@ -184,8 +184,9 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     st = scene.stats()
     n_launch = sum(st["launches"].values())
-    trav_ms = st["ms"]["closest"] + st["ms"]["anyhit"] + st["ms"]["fused"]        # dominant kernel class, this rank
-    trav_launches = st["launches"]["closest"] + st["launches"]["anyhit"] + st["launches"]["fused"]
+    # dominant kernel of the step: the closest-hit traversal (wf_traverse_kernel<false>), this rank's launches
+    trav_ms = st["ms"]["closest"] + st["ms"]["fused"]
+    trav_launches = st["launches"]["closest"] + st["launches"]["fused"]
     total_ms = float(ms.item())
     segments, occl, bins, dropped = (int(x) for x in tot.tolist())
     value = segments / (total_ms * 1e-3)
@@ -235,8 +236,15 @@ def run_ours(args):
         # recorded by the library around every launch on the launch stream, summed over the timed region.
         depth = math.ceil(math.log2(max(2, math.ceil(N_TRIS / 4))))
         q_bytes = 32 * depth + 192 + 40
-        trav_bytes = q_bytes * (segments + occl) / world
+        trav_bytes = q_bytes * segments / world                      # all closest-hit launches of one rank
         achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
+        traffic = None
+        try:   # DRAM bytes of one steady-state launch from the committed ncu --set full capture (never measured here)
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            traffic = int(tj["dram_bytes_read_per_launch"]) + int(tj["dram_bytes_write_per_launch"])
+        except Exception:
+            traffic = None
         whole = algorithmic_bytes(N_TRIS, segments / world, occl / world, bins / world) / (total_ms * 1e-3) / 1e9
         line = {
             "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s", "n_gpus": world,
@@ -254,11 +262,13 @@ def run_ours(args):
             "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
             "launches_per_step": {k: v / args.steps for k, v in st["launches"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "wf_traverse_kernel (closest + any-hit)",
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)",
+                         "algorithmic_bytes_per_launch": trav_bytes / max(1, trav_launches),
+                         "kernel": "wf_traverse_kernel<false> (closest hit)",
                          "kernel_ms": trav_ms / max(1, trav_launches), "kernel_launches": trav_launches,
                          "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                          "peak_source": which,
-                         "bytes_model": "traversal launches: (32*ceil(log2(ceil(T/4)))+192 + 40)*(S+O); whole step: "
+                         "bytes_model": "closest-hit launches: (32*ceil(log2(ceil(T/4)))+192 + 40)*S; whole step: "
                                         "64*S + (32*ceil(log2(ceil(T/4)))+192)*(S+O) + 8*U (SURVEY 8d)"},
             "cpu_baseline": cpu_base, "clocks": clocks,
         }

@@ -421,6 +421,7 @@ struct ear_b200_scene {
 	int max_slots = 1 << 23;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS)
 	bool slots_forced = false;
 	int check_every = 8;            // iterations between host checks for completion
+	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
 	int* h_counts = nullptr;        // pinned
@@ -512,6 +513,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(255, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
+	if (const char* rk = std::getenv("EAR_B200_RAY_KEY")) s->ray_key = std::max(0, std::min(4, std::atoi(rk)));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
 	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
@@ -854,7 +856,8 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
-	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, 2 * kSortBins * sizeof(int)));
+	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, kBinsTotal * sizeof(int)));
+	pl.ray_key = s->ray_key;
 	for (int k = 0; k < 3; ++k) {
 		pl.cell_origin[k] = s->lo[k];
 		const float ext = s->hi[k] - s->lo[k];
@@ -1009,12 +1012,13 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	for (long long it = 0; it < max_iter;) {
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
 			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
-			CUDA_TRY(cudaMemsetAsync(pl.bins, 0, 2 * kSortBins * sizeof(int), stream));
+			CUDA_TRY(cudaMemsetAsync(pl.bins, 0, kBinsTotal * sizeof(int), stream));
 			{
 				LaunchTimer t(s, stream, 0);
-				s->stats.launches[0] += 2;
+				s->stats.launches[0] += 3;
 				wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p);
-				wf_scan_kernel<<<2, 1024, 0, stream>>>(pl);
+				wf_scan_kernel<<<kRayScanBlocks + 1, 1024, 0, stream>>>(pl);
+				wf_scan_top_kernel<<<1, kRayScanBlocks, 0, stream>>>(pl);
 				wf_scatter_kernel<<<s->sm_count * 8, 256, 0, stream>>>(pl);
 			}
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }

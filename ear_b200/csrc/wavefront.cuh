@@ -34,8 +34,9 @@ struct WfPool {
 	int* trav_list;     // [N] slots that need a closest-hit query, binned by (direction octant, origin cell)
 	uint2* trav_tmp;    // [N] (slot, bin) as appended by the shade kernel, before binning
 	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
-	int* bins;          // [2][kSortBins] histogram -> offsets of the two counting sorts (closest rays, queries)
+	int* bins;          // [kRayBins + kSortBins (+ block sums)] histogram -> offsets of the two counting sorts (closest rays, queries)
 	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
+	int ray_key;        // how closest-hit rays are binned (EAR_B200_RAY_KEY): 0 octant+cell12, 1 octant+axis order+cell12, 2 octant+cell15
 	double* ctx_log2af; // [n_ctx] log2(absorption_factor), hoisted out of pow(af, length)
 	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
 	uint2* vis_list;    // [N*R] the unoccluded ones
@@ -45,7 +46,11 @@ struct WfPool {
 	int n_slots;
 };
 
-constexpr int kSortBins = 32768;   // 15-bit keys: 3 octant bits (closest) or 3 recorder bits (queries) + 12 Morton cell bits
+constexpr int kSortBins = 32768;   // queries: 15-bit keys = 3 recorder bits + 12 Morton cell bits
+constexpr int kRayBins = 262144;   // closest-hit rays: up to 18-bit keys (3 octant bits + 15 more, see ray_bin)
+constexpr int kRayScanBlocks = kRayBins / 1024;
+// bins layout: [0, kRayBins) rays | [kRayBins, +kSortBins) queries | [.., +kRayScanBlocks) ray block prefixes
+constexpr int kBinsTotal = kRayBins + kSortBins + kRayScanBlocks;
 constexpr int32_t kWaitLeaf = 0x7ffffffe;   // closest-hit lane waiting for its parked leaf (kEmptyChildDev - 1)
 constexpr int kSlotBits = 24;
 constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
@@ -166,14 +171,30 @@ __device__ __forceinline__ uint32_t cell_key(const WfPool& pool, float x, float 
 	const int cz = min(15, max(0, (int)((z - pool.cell_origin[2]) * pool.cell_scale[2])));
 	return spread4((uint32_t)cx) | (spread4((uint32_t)cy) << 1) | (spread4((uint32_t)cz) << 2);   // 12-bit Morton code
 }
-// exclusive scan of the two histograms (block 0: closest rays, block 1: queries), in place
-__global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
-	__shared__ int warp_tot[32];
-	int* h = pool.bins + blockIdx.x * kSortBins;
-	constexpr int kPer = kSortBins / 1024;
-	int v[kPer];
-	int sum = 0;
-	for (int i = 0; i < kPer; ++i) { v[i] = h[threadIdx.x * kPer + i]; sum += v[i]; }
+__device__ __forceinline__ uint32_t spread5(uint32_t v) { return spread4(v & 15u) | ((v & 16u) << 8); }
+// bin of a closest-hit ray: warps fetch consecutive list entries, so a finer key means more alike rays per warp
+__device__ __forceinline__ uint32_t ray_bin(const WfPool& pool, float ox, float oy, float oz, float dx, float dy, float dz) {
+	const uint32_t oct = (dx < 0.0f ? 1u : 0u) | (dy < 0.0f ? 2u : 0u) | (dz < 0.0f ? 4u : 0u);
+	if (pool.ray_key == 2 || pool.ray_key == 3) {
+		const int cx = min(31, max(0, (int)((ox - pool.cell_origin[0]) * pool.cell_scale[0] * 2.0f)));
+		const int cy = min(31, max(0, (int)((oy - pool.cell_origin[1]) * pool.cell_scale[1] * 2.0f)));
+		const int cz = min(31, max(0, (int)((oz - pool.cell_origin[2]) * pool.cell_scale[2] * 2.0f)));
+		const uint32_t cell = spread5((uint32_t)cx) | (spread5((uint32_t)cy) << 1) | (spread5((uint32_t)cz) << 2);
+		return pool.ray_key == 2 ? (oct << 15) | cell : (cell << 3) | oct;
+	}
+	const uint32_t cell = cell_key(pool, ox, oy, oz);
+	if (pool.ray_key == 1) {
+		const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+		const uint32_t order = (ax > ay ? 1u : 0u) | (ay > az ? 2u : 0u) | (ax > az ? 4u : 0u);
+		return (((oct << 3) | order) << 12) | cell;
+	}
+	if (pool.ray_key == 4) return (cell << 3) | oct;
+	return (oct << 12) | cell;
+}
+// exclusive scan of the two histograms, in place.  Blocks [0, kRayScanBlocks) each scan 1024 ray bins and leave their
+// total in the block-prefix area; block kRayScanBlocks scans all the query bins.  wf_scan_top_kernel then turns the ray
+// block totals into prefixes (the scatter adds them).
+__device__ __forceinline__ int block_exclusive_scan(int sum, int* warp_tot, int& total) {
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	int inc = sum;
 	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
@@ -185,8 +206,39 @@ __global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
 		warp_tot[lane] = w;
 	}
 	__syncthreads();
-	int run = inc - sum + (wid ? warp_tot[wid - 1] : 0);
+	total = warp_tot[31];
+	return inc - sum + (wid ? warp_tot[wid - 1] : 0);
+}
+__global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
+	__shared__ int warp_tot[32];
+	int total;
+	if (blockIdx.x < kRayScanBlocks) {
+		int* h = pool.bins + blockIdx.x * 1024;
+		const int v = h[threadIdx.x];
+		h[threadIdx.x] = block_exclusive_scan(v, warp_tot, total);
+		if (threadIdx.x == 0) pool.bins[kRayBins + kSortBins + blockIdx.x] = total;
+		return;
+	}
+	int* h = pool.bins + kRayBins;
+	constexpr int kPer = kSortBins / 1024;
+	int v[kPer];
+	int sum = 0;
+	for (int i = 0; i < kPer; ++i) { v[i] = h[threadIdx.x * kPer + i]; sum += v[i]; }
+	int run = block_exclusive_scan(sum, warp_tot, total);
 	for (int i = 0; i < kPer; ++i) { h[threadIdx.x * kPer + i] = run; run += v[i]; }
+}
+__global__ void __launch_bounds__(kRayScanBlocks) wf_scan_top_kernel(WfPool pool) {
+	__shared__ int warp_tot[32];
+	int* h = pool.bins + kRayBins + kSortBins;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int v = h[threadIdx.x];
+	int inc = v;
+	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) warp_tot[wid] = inc;
+	__syncthreads();
+	int before = 0;
+	for (int w = 0; w < wid; ++w) before += warp_tot[w];
+	h[threadIdx.x] = before + inc - v;
 }
 // scatter the appended entries to their bins (order inside a bin is arbitrary)
 __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
@@ -199,7 +251,7 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) e[k] = pool.trav_tmp[i + k * stride];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pos[k] = atomicAdd(pool.bins + e[k].y, 1);
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pos[k] = atomicAdd(pool.bins + e[k].y, 1) + pool.bins[kRayBins + kSortBins + (e[k].y >> 10)];
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pool.trav_list[pos[k]] = (int)e[k].x;
 	}
@@ -208,7 +260,7 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = pool.q_tmp[i + k * stride];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kSortBins + ((e[k].y >> 16) & 0x7fffu), 1);
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kRayBins + ((e[k].y >> 16) & 0x7fffu), 1);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pool.q_list[pos[k]] = e[k];
 	}
@@ -366,7 +418,7 @@ __global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool po
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if (facing) {
 				const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
-				atomicAdd(pool.bins + kSortBins + bin, 1);
+				atomicAdd(pool.bins + kRayBins + bin, 1);
 				pool.q_tmp[base + __popc(mq & lt_mask)] =
 				    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
 			}
@@ -383,8 +435,7 @@ __global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool po
 		if (lane == 0) base = atomicAdd(pool.counts + 0, __popc(live));
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (alive) {
-			const uint32_t oct = (rd.x < 0.0f ? 1u : 0u) | (rd.y < 0.0f ? 2u : 0u) | (rd.z < 0.0f ? 4u : 0u);
-			const uint32_t bin = (oct << 12) | cell_key(pool, ro.x, ro.y, ro.z);
+			const uint32_t bin = ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
 			atomicAdd(pool.bins + bin, 1);
 			pool.trav_tmp[base + __popc(live & lt_mask)] = make_uint2((uint32_t)slot, bin);
 		}
