@@ -314,7 +314,13 @@ def reference_sample(sc, procs=None, budget=20):
     for f in os.listdir(tmp):
         os.unlink(os.path.join(tmp, f))
     os.rmdir(tmp)
-    return {"value": seg / secs, "unit": "segments/s", "cores": procs, "kind": "reference",
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            model = next((ln.split(":", 1)[1].strip() for ln in f if ln.startswith("model name")), "unknown")
+    except OSError:
+        pass
+    return {"value": seg / secs, "unit": "segments/s", "cores": procs, "cpu_model": model, "nproc": cores, "kind": "reference",
             "sample": f"{procs} processes x 1 context, {budget} s budget each (reference's 1000-bounce loop), {int(seg)} segments, "
                       f"{secs:.1f} s render, {wall:.1f} s wall incl. parse"}
 

@@ -421,6 +421,7 @@ struct ear_b200_scene {
 	int max_slots = 1 << 23;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS)
 	bool slots_forced = false;
 	int check_every = 8;            // iterations between host checks for completion
+	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
 	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
@@ -513,6 +514,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(255, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
+	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
 	if (const char* rk = std::getenv("EAR_B200_RAY_KEY")) s->ray_key = std::max(0, std::min(4, std::atoi(rk)));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
@@ -858,6 +860,7 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, kBinsTotal * sizeof(int)));
 	pl.ray_key = s->ray_key;
+	pl.sort_queries = s->sort_queries;
 	for (int k = 0; k < 3; ++k) {
 		pl.cell_origin[k] = s->lo[k];
 		const float ext = s->hi[k] - s->lo[k];

@@ -36,6 +36,7 @@ struct WfPool {
 	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
 	int* bins;          // [kRayBins + kSortBins (+ block sums)] histogram -> offsets of the two counting sorts (closest rays, queries)
 	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
+	int sort_queries;   // 0: occlusion queries keep their slot order (EAR_B200_SORT_QUERIES)
 	int ray_key;        // how closest-hit rays are binned (EAR_B200_RAY_KEY): 0 octant+cell12, 1 octant+axis order+cell12, 2 octant+cell15
 	double* ctx_log2af; // [n_ctx] log2(absorption_factor), hoisted out of pow(af, length)
 	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kRayScanBlocks) wf_scan_top_kernel(WfPool pool
 }
 // scatter the appended entries to their bins (order inside a bin is arbitrary)
 __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
-	const int n_trav = pool.counts[0], n_q = pool.counts[1];
+	const int n_trav = pool.counts[0], n_q = pool.sort_queries ? pool.counts[1] : 0;
 	const int stride = gridDim.x * blockDim.x;
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
 	// four independent atomics in flight per thread: the returning atomic's round trip is the whole cost here
@@ -417,10 +418,15 @@ __global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool po
 			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
 			base = __shfl_sync(0xffffffffu, base, 0);
 			if (facing) {
-				const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
-				atomicAdd(pool.bins + kRayBins + bin, 1);
-				pool.q_tmp[base + __popc(mq & lt_mask)] =
-				    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
+				if (pool.sort_queries) {
+					const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
+					atomicAdd(pool.bins + kRayBins + bin, 1);
+					pool.q_tmp[base + __popc(mq & lt_mask)] =
+					    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
+				} else {
+					pool.q_list[base + __popc(mq & lt_mask)] =
+					    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
+				}
 			}
 		}
 	}

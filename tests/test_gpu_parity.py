@@ -39,6 +39,22 @@ def test_first_hit_bit_exact(ob, name, n):
     assert np.array_equal(gt[hit].view(np.uint32), ct[hit].view(np.uint32))
 
 
+@pytest.mark.parametrize("name,n", [("rt60", 1000000), ("example1", 1000000), ("soup", 100000)])
+def test_first_hit_and_occlusion_at_survey_ray_counts(ob, name, n):
+    """SURVEY.md section 8(d) parity procedure (i): 10^6 seeded rays per scene (uniform, edge/vertex-aimed, grazing,
+    surface-leaving) -- indices identical, distances bit-identical, occlusion answers identical."""
+    sc = common.named_scene(name)
+    gpu, cpu = _pair(ob, sc)
+    o, d = common.make_rays(sc, n, seed=77)
+    gi, gt = gpu.first_hit(o, d)
+    ci, ct = cpu.first_hit(o, d)
+    assert np.array_equal(gi, ci), f"{(gi != ci).sum()} of {n} first-hit indices differ"
+    hit = ci >= 0
+    assert np.array_equal(gt[hit].view(np.uint32), ct[hit].view(np.uint32))
+    p, x = common.make_segments(sc, n, seed=78)
+    assert np.array_equal(gpu.occluded(p, x), cpu.occluded(p, x))
+
+
 @pytest.mark.parametrize("name,n", [("rt60", 40000), ("example1", 40000), ("soup", 40000), ("hall20k", 24000)])
 def test_occlusion_identical(ob, name, n):
     sc = common.named_scene(name)
@@ -190,3 +206,27 @@ def test_scene_image_round_trip(ob):
         api.Scene.from_image(bad.data_ptr(), 128, built.n_bands, device=0)
     with pytest.raises(api.EarError):
         built.image_write(bad.data_ptr(), n - 256)
+
+
+def test_many_recorders_match_oracle(ob):
+    """C5's recorder count and beyond: 66 recorders (mono and stereo mixed) in one call.  The library caches 64
+    visibility maps per scene, so the last recorders take the BVH any-hit path -- the answers must not depend
+    on which path a recorder got."""
+    sc = common.named_scene("example1")
+    sc.samples = 3000
+    rng = np.random.default_rng(5)
+    first = sc.recorders[0]
+    sc.recorders = []
+    for i in range(66):
+        pos = (float(rng.uniform(-9, 9)), float(rng.uniform(-5, 5)), float(rng.uniform(0.5, 3.5)))
+        ear = rng.normal(size=3)
+        ear /= np.linalg.norm(ear)
+        sc.recorders.append(type(first)(f"/tmp/r{i}.wav", position=pos, stereo=(i % 3 == 0),
+                                        right_ear=tuple(float(x) for x in ear)))
+    gpu, cpu = _pair(ob, sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    res = gpu.render(ctxs, recs, max_bounces=30, seed=21)
+    tracks, cnt = cpu.render(ctxs, recs, max_bounces=30, seed=21)
+    assert res.segments == cnt["segments"] and res.occlusion_queries == cnt["occlusion_queries"]
+    assert res.contributions == cnt["contributions"]
+    assert _compare_tracks(res, tracks) < REL_TOL
