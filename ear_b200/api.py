@@ -68,6 +68,7 @@ EXPORTS = [
     "ear_b200_render", "ear_b200_result_free", "ear_b200_trace_device", "ear_b200_finalise_device",
     "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset", "ear_b200_convolve",
     "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
+    "ear_b200_post_power_device", "ear_b200_post_truncate_device",
 ]
 
 _lib = None
@@ -94,6 +95,8 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.ear_b200_scene_image_write.argtypes = [vp, vp, C.c_uint64]
     lib.ear_b200_scene_create_from_image.argtypes = [vp, C.c_uint64, i32, C.POINTER(vp)]
     lib.ear_b200_scene_clone.argtypes = [vp, i32, C.POINTER(vp)]
+    lib.ear_b200_post_power_device.argtypes = [vp, C.POINTER(RecorderC), i32, i32, i32, vp, vp, C.c_float, C.POINTER(C.c_float), vp, vp]
+    lib.ear_b200_post_truncate_device.argtypes = [vp, C.POINTER(RecorderC), i32, i32, i32, vp, vp, C.c_float, vp, vp]
     lib.ear_b200_first_hit.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.ear_b200_occluded.argtypes = [vp, vp, vp, i64, vp]
     lib.ear_b200_trace_paths.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(OptionsC), i64, vp, vp]
@@ -223,6 +226,8 @@ class RenderResult:
     bin_updates: int
     dropped_updates: int
     device_ms: float
+    maximum: float = 0.0               # set by the device post chain (sharding.render_sharded(post=...))
+    t60: Optional[list] = None         # [context][recorder][track]
 
 
 def convolve(response: "Track", dry: np.ndarray, offset: int = 0, response2: Optional["Track"] = None, device: int = 0) -> "Track":

@@ -291,6 +291,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 
 #include "wavefront.cuh"
 #include "vismap.cuh"
+#include "post.cuh"
 
 // Fused single-kernel engine (EAR_B200_ENGINE=mega): grid = SMs x resident blocks; warps pull ray ids from a
 // global queue until it is dry.
@@ -434,6 +435,7 @@ struct ear_b200_scene {
 	int vismap_res = -1;            // -1: choose from the triangle count; 0: disabled (EAR_B200_VISMAP_RES)
 	VisMapDev* d_maps = nullptr; int* d_map_of = nullptr; size_t map_of_cap = 0;
 	uint2* d_q_bvh = nullptr; size_t q_bvh_cap = 0;
+	float* d_post = nullptr; size_t post_cap = 0;   // post-chain scratch: [n_tracks] float + [n_tracks] uint32
 	int* d_vis_counts = nullptr; long long* d_vis_sums = nullptr; size_t vis_scratch_cap = 0;
 	std::vector<ear_b200_recorder> h_rec;   // host copy of the recorders of the current call
 	float maxabs = 0.0f;
@@ -632,7 +634,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
 	for (auto& m : s->vismaps) { cudaFree(m.d_offsets); cudaFree(m.d_items); }
-	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh); cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums);
+	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh); cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums); cudaFree(s->d_post);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -1020,8 +1022,8 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 				LaunchTimer t(s, stream, 0);
 				s->stats.launches[0] += 3;
 				wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p);
-				wf_scan_kernel<<<kRayScanBlocks + 1, 1024, 0, stream>>>(pl);
-				wf_scan_top_kernel<<<1, kRayScanBlocks, 0, stream>>>(pl);
+				wf_scan_kernel<<<kScanBlocks, 1024, 0, stream>>>(pl);
+				wf_scan_top_kernel<<<1, kScanBlocks, 0, stream>>>(pl);
 				wf_scatter_kernel<<<s->sm_count * 8, 256, 0, stream>>>(pl);
 			}
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
@@ -1088,6 +1090,72 @@ extern "C" int32_t ear_b200_finalise_device(ear_b200_scene* s, const ear_b200_co
 	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, nullptr, (cudaStream_t)stream, p)) return rc;
 	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range;
 	return launch_finalise(s, p, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// post chain on device tracks (post.cuh)
+// ------------------------------------------------------------------------------------------
+static int32_t upload_recorders(ear_b200_scene* s, const ear_b200_recorder* rec, size_t n, cudaStream_t stream) {
+	for (size_t i = 0; i < n; ++i)
+		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("post: unknown recorder kind");
+	if (n > s->rec_cap) {
+		cudaFree(s->d_rec); s->d_rec = nullptr; s->rec_cap = 0;
+		CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder) * n));
+		s->rec_cap = n;
+	}
+	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * n, cudaMemcpyHostToDevice, stream));
+	return 0;
+}
+
+static int32_t ensure_post_scratch(ear_b200_scene* s, size_t n_tracks) {
+	if (n_tracks > s->post_cap) {
+		cudaFree(s->d_post); s->d_post = nullptr; s->post_cap = 0;
+		CUDA_TRY(cudaMalloc(&s->d_post, n_tracks * 2 * sizeof(float)));   // [track_max or t60 | track_len]
+		s->post_cap = n_tracks;
+	}
+	return 0;
+}
+
+extern "C" int32_t ear_b200_post_power_device(ear_b200_scene* s, const ear_b200_recorder* rec, int32_t n_ctx, int32_t n_rec,
+                                              int32_t n_bins, float* d_hist, const uint32_t* d_range, float exponent,
+                                              float* maximum, float* track_maximum, void* stream) {
+	if (!s) return fail("post_power_device: null scene");
+	if (!rec || n_ctx <= 0 || n_rec <= 0 || n_bins <= 0 || !d_hist || !d_range) return fail("post_power_device: bad arguments");
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	if (int32_t rc = upload_recorders(s, rec, (size_t)n_ctx * n_rec, st)) return rc;
+	if (int32_t rc = ensure_post_scratch(s, n_tracks)) return rc;
+	post_power_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, exponent, s->d_post);
+	CUDA_TRY(cudaGetLastError());
+	std::vector<float> mx(n_tracks);
+	CUDA_TRY(cudaMemcpyAsync(mx.data(), s->d_post, n_tracks * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	float m = 0.0f;
+	for (size_t t = 0; t < n_tracks; ++t) { if (mx[t] > m) m = mx[t]; if (track_maximum) track_maximum[t] = mx[t]; }
+	if (maximum) *maximum = m;
+	return 0;
+}
+
+extern "C" int32_t ear_b200_post_truncate_device(ear_b200_scene* s, const ear_b200_recorder* rec, int32_t n_ctx, int32_t n_rec,
+                                                 int32_t n_bins, const float* d_hist, uint32_t* d_range, float threshold,
+                                                 float* t60, void* stream) {
+	if (!s) return fail("post_truncate_device: null scene");
+	if (!rec || n_ctx <= 0 || n_rec <= 0 || n_bins <= 0 || !d_hist || !d_range) return fail("post_truncate_device: bad arguments");
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	if (int32_t rc = upload_recorders(s, rec, (size_t)n_ctx * n_rec, st)) return rc;
+	if (int32_t rc = ensure_post_scratch(s, n_tracks)) return rc;
+	uint32_t* d_len = (uint32_t*)(s->d_post + n_tracks);
+	post_length_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, threshold, d_len);
+	post_truncate_t60_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, d_len, s->d_post);
+	CUDA_TRY(cudaGetLastError());
+	std::vector<float> h(n_tracks);
+	CUDA_TRY(cudaMemcpyAsync(h.data(), s->d_post, n_tracks * sizeof(float), cudaMemcpyDeviceToHost, st));
+	CUDA_TRY(cudaStreamSynchronize(st));
+	if (t60) std::memcpy(t60, h.data(), n_tracks * sizeof(float));
+	return 0;
 }
 
 extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,

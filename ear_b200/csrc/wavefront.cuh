@@ -50,8 +50,10 @@ struct WfPool {
 constexpr int kSortBins = 32768;   // queries: 15-bit keys = 3 recorder bits + 12 Morton cell bits
 constexpr int kRayBins = 262144;   // closest-hit rays: up to 18-bit keys (3 octant bits + 15 more, see ray_bin)
 constexpr int kRayScanBlocks = kRayBins / 1024;
-// bins layout: [0, kRayBins) rays | [kRayBins, +kSortBins) queries | [.., +kRayScanBlocks) ray block prefixes
-constexpr int kBinsTotal = kRayBins + kSortBins + kRayScanBlocks;
+constexpr int kQueryScanBlocks = kSortBins / 1024;
+constexpr int kScanBlocks = kRayScanBlocks + kQueryScanBlocks;
+// bins layout: [0, kRayBins) rays | [kRayBins, +kSortBins) queries | [.., +kScanBlocks) prefixes of the 1024-bin blocks
+constexpr int kBinsTotal = kRayBins + kSortBins + kScanBlocks;
 constexpr int32_t kWaitLeaf = 0x7ffffffe;   // closest-hit lane waiting for its parked leaf (kEmptyChildDev - 1)
 constexpr int kSlotBits = 24;
 constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
@@ -192,9 +194,8 @@ __device__ __forceinline__ uint32_t ray_bin(const WfPool& pool, float ox, float 
 	if (pool.ray_key == 4) return (cell << 3) | oct;
 	return (oct << 12) | cell;
 }
-// exclusive scan of the two histograms, in place.  Blocks [0, kRayScanBlocks) each scan 1024 ray bins and leave their
-// total in the block-prefix area; block kRayScanBlocks scans all the query bins.  wf_scan_top_kernel then turns the ray
-// block totals into prefixes (the scatter adds them).
+// exclusive scan of the two histograms, in place, two levels: every block scans 1024 bins and leaves its total in the
+// block-prefix area; wf_scan_top_kernel turns the totals into prefixes (the scatter adds them).
 __device__ __forceinline__ int block_exclusive_scan(int sum, int* warp_tot, int& total) {
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	int inc = sum;
@@ -213,22 +214,13 @@ __device__ __forceinline__ int block_exclusive_scan(int sum, int* warp_tot, int&
 __global__ void __launch_bounds__(1024) wf_scan_kernel(WfPool pool) {
 	__shared__ int warp_tot[32];
 	int total;
-	if (blockIdx.x < kRayScanBlocks) {
-		int* h = pool.bins + blockIdx.x * 1024;
-		const int v = h[threadIdx.x];
-		h[threadIdx.x] = block_exclusive_scan(v, warp_tot, total);
-		if (threadIdx.x == 0) pool.bins[kRayBins + kSortBins + blockIdx.x] = total;
-		return;
-	}
-	int* h = pool.bins + kRayBins;
-	constexpr int kPer = kSortBins / 1024;
-	int v[kPer];
-	int sum = 0;
-	for (int i = 0; i < kPer; ++i) { v[i] = h[threadIdx.x * kPer + i]; sum += v[i]; }
-	int run = block_exclusive_scan(sum, warp_tot, total);
-	for (int i = 0; i < kPer; ++i) { h[threadIdx.x * kPer + i] = run; run += v[i]; }
+	int* h = pool.bins + blockIdx.x * 1024;     // ray bins and query bins are contiguous: block b owns bins [1024 b, 1024 b + 1024)
+	const int v = h[threadIdx.x];
+	h[threadIdx.x] = block_exclusive_scan(v, warp_tot, total);
+	if (threadIdx.x == 0) pool.bins[kRayBins + kSortBins + blockIdx.x] = total;
 }
-__global__ void __launch_bounds__(kRayScanBlocks) wf_scan_top_kernel(WfPool pool) {
+// block totals -> exclusive prefixes, separately for the ray blocks and the query blocks
+__global__ void __launch_bounds__(kScanBlocks) wf_scan_top_kernel(WfPool pool) {
 	__shared__ int warp_tot[32];
 	int* h = pool.bins + kRayBins + kSortBins;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -237,8 +229,9 @@ __global__ void __launch_bounds__(kRayScanBlocks) wf_scan_top_kernel(WfPool pool
 	for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
 	if (lane == 31) warp_tot[wid] = inc;
 	__syncthreads();
+	const int first_warp = threadIdx.x < kRayScanBlocks ? 0 : kRayScanBlocks / 32;   // both segments are whole warps
 	int before = 0;
-	for (int w = 0; w < wid; ++w) before += warp_tot[w];
+	for (int w = first_warp; w < wid; ++w) before += warp_tot[w];
 	h[threadIdx.x] = before + inc - v;
 }
 // scatter the appended entries to their bins (order inside a bin is arbitrary)
@@ -261,7 +254,7 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = pool.q_tmp[i + k * stride];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kRayBins + ((e[k].y >> 16) & 0x7fffu), 1);
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kRayBins + ((e[k].y >> 16) & 0x7fffu), 1) + pool.bins[kRayBins + kSortBins + kRayScanBlocks + ((e[k].y >> 26) & 0x1fu)];
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pool.q_list[pos[k]] = e[k];
 	}

@@ -60,11 +60,16 @@ def create_replicated_scene(verts, tri_material, materials, device: int, src: in
     return scene
 
 
-def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0, dst: int = 0):
+def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0, dst: int = 0,
+                   post=None):
     """Scene::Render (src/Scene.cpp:111-318) over all ranks of the default process group: every rank traces its
     ray-id range of every context into a device-resident partial histogram, the partials meet in ONE reduce on
     rank `dst`, which finalises and downloads the tracks.  Host contexts in, host tracks out (RenderResult on
-    `dst`, None elsewhere).  Identical to Scene.render() when there is one rank."""
+    `dst`, None elsewhere).  Identical to Scene.render() when there is one rank.
+
+    post=(exponent, divisor), e.g. (0.335, 256.0): also run Render()'s post chain (src/EAR.cpp:209-228) on the device
+    before the download -- Power, global maximum, Truncate(getLength(maximum / divisor)), T60 per track; the result
+    then carries `maximum` and `t60` ([context][recorder][track]) and the tracks come back compressed and truncated."""
     import ctypes as C
     import numpy as np
     import torch
@@ -72,7 +77,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
     from . import api
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
-    if world == 1:
+    if world == 1 and post is None:
         return scene.render(contexts, recorders, max_bounces=max_bounces, seed=seed, n_bins=n_bins)
     lib = scene.lib
     dev = torch.device("cuda", scene.device)
@@ -85,29 +90,43 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
     if n_bins <= 0:
         n_bins = scene.default_bins(opt)
     n_tracks = n_ctx * n_rec * 2
-    hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
-    rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
-    rng[:, 0] = api.FIRST_SAMPLE_INIT
-    rng[:, 1] = 0
-    counters = torch.zeros((8,), dtype=torch.int64, device=dev)
-    sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-    api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
-                                              hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
-    first = rng[:, 0].contiguous()
-    real = rng[:, 1].contiguous()
-    reduce_partials(hist, first, real, dst=dst)
-    dist.reduce(counters, dst=dst, op=dist.ReduceOp.SUM)
-    if rank != dst:
-        return None
-    rng[:, 0] = first
-    rng[:, 1] = real
-    api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
-                                                 hist.data_ptr(), rng.data_ptr(), sp))
-    h_rng = rng.cpu().numpy()
-    c = counters.cpu().numpy()
-    # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
-    longest = int(h_rng[:, 1].max()) + 1 if n_tracks else 0
-    h_hist = hist[:, :longest].cpu().numpy()
+    with torch.cuda.device(dev):
+        hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
+        rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
+        rng[:, 0] = api.FIRST_SAMPLE_INIT
+        rng[:, 1] = 0
+        counters = torch.zeros((8,), dtype=torch.int64, device=dev)
+        sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
+                                                  hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
+        if world > 1:
+            first = rng[:, 0].contiguous()
+            real = rng[:, 1].contiguous()
+            reduce_partials(hist, first, real, dst=dst)
+            dist.reduce(counters, dst=dst, op=dist.ReduceOp.SUM)
+            if rank != dst:
+                return None
+            rng[:, 0] = first
+            rng[:, 1] = real
+        api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
+                                                     hist.data_ptr(), rng.data_ptr(), sp))
+        maximum, t60 = 0.0, None
+        if post is not None:
+            exponent, divisor = post
+            mx = C.c_float(0.0)
+            api._check(lib, lib.ear_b200_post_power_device(scene.handle, rec_c, n_ctx, n_rec, n_bins, hist.data_ptr(),
+                                                           rng.data_ptr(), exponent, C.byref(mx), None, sp))
+            maximum = float(mx.value)
+            threshold = float(np.float32(maximum) / np.float32(divisor))
+            h_t60 = np.zeros((n_tracks,), np.float32)
+            api._check(lib, lib.ear_b200_post_truncate_device(scene.handle, rec_c, n_ctx, n_rec, n_bins, hist.data_ptr(),
+                                                              rng.data_ptr(), threshold, h_t60.ctypes.data, sp))
+            t60 = h_t60.reshape(n_ctx, n_rec, 2).tolist()
+        h_rng = rng.cpu().numpy()
+        c = counters.cpu().numpy()
+        # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
+        longest = min(n_bins, int(h_rng[:, 1].max()) + 1) if n_tracks else 0
+        h_hist = hist[:, :longest].cpu().numpy()
     tracks = []
     for ci in range(n_ctx):
         per_rec = []
@@ -121,4 +140,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
                 pair.append(api.Track(data, int(h_rng[t, 0]), real_len))
             per_rec.append(pair)
         tracks.append(per_rec)
-    return api.RenderResult(tracks, int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), 0.0)
+    res = api.RenderResult(tracks, int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), 0.0)
+    res.maximum = maximum
+    res.t60 = t60
+    return res

@@ -187,6 +187,24 @@ int32_t ear_b200_convolve(int32_t device, const float* response, uint32_t length
                           uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
                           uint32_t out_len, uint32_t* out_first, uint32_t* out_real);
 
+/* SURVEY.md section 8(f) rank 2 -- the post chain of Render() (src/EAR.cpp:209-228) on device-resident tracks, in
+ * the two phases the reference runs it in (every track is compressed before the global maximum is known):
+ *   post_power     Recorder::Power(exponent) in place on every track (FloatBuffer::Power, src/Recorder.cpp:101-106:
+ *                  sign(x) * |x|^exponent over [first_sample, real_length)), then FloatBuffer::Maximum of each track
+ *                  (:76-83).  maximum = the largest of them (host, may be NULL); track_maximum [n_contexts][n_recorders][2]
+ *                  (host, may be NULL).  Multi-GPU callers reduce `maximum` by MAX before phase 2.
+ *   post_truncate  Recorder::Truncate(Recorder::getLength(threshold)) for every recorder (src/Recorder.cpp:399-430,
+ *                  108-118; the reference passes threshold = maximum / 256) -- updates real_length in d_range -- and
+ *                  RecorderTrack::T60 (src/Recorder.cpp:303-340) of every truncated track into t60 [n_contexts][n_recorders][2]
+ *                  (host; `EAR calc T60` prints t60[0]).
+ * d_hist / d_range as in ear_b200_trace_device, after ear_b200_finalise_device.  Both calls synchronise `stream`. */
+int32_t ear_b200_post_power_device(ear_b200_scene* scene, const ear_b200_recorder* rec, int32_t n_contexts, int32_t n_recorders,
+                                   int32_t n_bins, float* d_hist, const uint32_t* d_range, float exponent, float* maximum,
+                                   float* track_maximum, void* stream);
+int32_t ear_b200_post_truncate_device(ear_b200_scene* scene, const ear_b200_recorder* rec, int32_t n_contexts, int32_t n_recorders,
+                                      int32_t n_bins, const float* d_hist, uint32_t* d_range, float threshold, float* t60,
+                                      void* stream);
+
 /* Launch counts and device time per kernel class since the last reset (synchronises the scene's last stream). */
 int32_t ear_b200_scene_stats(ear_b200_scene* scene, ear_b200_stats* out);
 void ear_b200_scene_stats_reset(ear_b200_scene* scene);

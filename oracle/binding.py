@@ -261,3 +261,35 @@ def ref_calc_t60(ear_path, seed, timeout=None):
     if len(vals) != 3:
         raise RuntimeError("EAR_ref failed: " + r.stdout[-400:])
     return tuple(vals)
+
+
+def post_all(tracks_per_context, exponent=0.335, divisor=256.0):
+    """The whole post chain of Render() (src/EAR.cpp:209-228) on every track: returns (maximum, [[[(data, first_sample,
+    real_length, t60)]]]) in [ctx][rec][track] order.  Same steps as post_t60, but nothing is thrown away."""
+    l = lib()
+    mx = 0.0
+    powered = []
+    for ctx in tracks_per_context:
+        pc = []
+        for rec in ctx:
+            pr = []
+            for tr in rec:
+                d = np.ascontiguousarray(tr.data, np.float32).copy()
+                l.oracle_power(d.ctypes.data, tr.first_sample, tr.real_length, exponent)
+                mx = max(mx, l.oracle_maximum(d.ctypes.data, tr.first_sample, tr.real_length))
+                pr.append(d)
+            pc.append(pr)
+        powered.append(pc)
+    thr = np.float32(mx) / np.float32(divisor)
+    out = []
+    for ctx, pc in zip(tracks_per_context, powered):
+        oc = []
+        for rec, pr in zip(ctx, pc):
+            ln = 0
+            if any(tr.real_length > 0 for tr in rec):
+                for tr, d in zip(rec, pr):
+                    ln = max(ln, l.oracle_get_length(d.ctypes.data, tr.first_sample, tr.real_length, d.shape[0], thr))
+            ln = max(1, ln)
+            oc.append([(d, tr.first_sample, ln, float(l.oracle_t60(d.ctypes.data, tr.first_sample, ln))) for tr, d in zip(rec, pr)])
+        out.append(oc)
+    return float(mx), out
