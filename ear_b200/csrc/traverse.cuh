@@ -67,20 +67,45 @@ __device__ __forceinline__ RaySetup make_setup(V3 o, V3 d) {
 
 // per-lane stack: shared memory first, local memory beyond kStackEntries (never reached by SAH trees
 // of realistic scenes; the builder bounds the depth so even adversarial input cannot overflow both)
+// Per-lane traversal stack: kStackEntries entries in shared memory (column `threadIdx.x` of an [entry][thread]
+// array: conflict-free), deeper pushes spill to a local array.  On the device the shared part is addressed through
+// explicit shared-space instructions: stores through a generic pointer made the compiler assume they might alias the
+// struct itself (which lives in local memory because of the spill array), so it kept `sp` in local memory and
+// re-loaded it around every push and pop.
 struct LaneStack {
+#ifdef EARB_HOST_EMULATION
 	int2* smem;       // this lane's column: entry k at smem[k * stride]
 	int stride;
+	__device__ __forceinline__ void bind(int2* column, int stride_entries) { smem = column; stride = stride_entries; }
+	__device__ __forceinline__ void put(int k, int2 e) { smem[k * stride] = e; }
+	__device__ __forceinline__ int2 get(int k) const { return smem[k * stride]; }
+#else
+	uint32_t base;    // shared-space byte address of this lane's column
+	uint32_t pitch;   // bytes between consecutive entries of a column
+	__device__ __forceinline__ void bind(int2* column, int stride_entries) {
+		base = (uint32_t)__cvta_generic_to_shared(column);
+		pitch = (uint32_t)stride_entries * (uint32_t)sizeof(int2);
+	}
+	__device__ __forceinline__ void put(int k, int2 e) {
+		asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(base + (uint32_t)k * pitch), "r"(e.x), "r"(e.y));
+	}
+	__device__ __forceinline__ int2 get(int k) const {
+		int2 e;
+		asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(base + (uint32_t)k * pitch));
+		return e;
+	}
+#endif
 	int2 spill[kStackSpill];
 	int sp;
 	__device__ __forceinline__ void push(int32_t node, float key) {
 		const int2 e = make_int2(node, __float_as_int(key));
-		if (sp < kStackEntries) smem[sp * stride] = e;
+		if (sp < kStackEntries) put(sp, e);
 		else if (sp < kStackEntries + kStackSpill) spill[sp - kStackEntries] = e;
 		++sp;
 	}
 	__device__ __forceinline__ int2 pop() {
 		--sp;
-		return sp < kStackEntries ? smem[sp * stride] : spill[min(sp - kStackEntries, kStackSpill - 1)];
+		return sp < kStackEntries ? get(sp) : spill[min(sp - kStackEntries, kStackSpill - 1)];
 	}
 };
 
@@ -166,9 +191,27 @@ __device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
 	cswap(key[0], key[1]); cswap(key[2], key[3]); cswap(key[0], key[2]); cswap(key[1], key[3]); cswap(key[1], key[2]);
 	const int32_t c0 = __float_as_int(n0.hi.x), c1 = __float_as_int(n0.hi.y), c2 = __float_as_int(n0.hi.z), c3 = __float_as_int(n0.hi.w);
 	if (key[0] == 0xffffffffu) { pop_next<EXACT>(sc, ts); return; }
-	if (key[3] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[3] & 3u), __uint_as_float(key[3] & ~3u));
-	if (key[2] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[2] & 3u), __uint_as_float(key[2] & ~3u));
-	if (key[1] != 0xffffffffu) ts.st.push(pick4(c0, c1, c2, c3, key[1] & 3u), __uint_as_float(key[1] & ~3u));
+	// farther children go on the stack, farthest first.  The keys are sorted, so the valid ones are a prefix; with
+	// room for all three in the shared-memory part (nearly always) the pushes are three predicated stores -- the
+	// per-push branches of the general path ran with 2-5 lanes active and made up ~20 % of the kernel's instructions
+	const bool h1 = key[1] != 0xffffffffu, h2 = key[2] != 0xffffffffu, h3 = key[3] != 0xffffffffu;
+	const int2 e1 = make_int2(pick4(c0, c1, c2, c3, key[1] & 3u), (int)(key[1] & ~3u));
+	const int2 e2 = make_int2(pick4(c0, c1, c2, c3, key[2] & 3u), (int)(key[2] & ~3u));
+	const int2 e3 = make_int2(pick4(c0, c1, c2, c3, key[3] & 3u), (int)(key[3] & ~3u));
+	if (ts.st.sp + 3 <= kStackEntries) {
+		int sp = ts.st.sp;
+		if (h3) ts.st.put(sp, e3);
+		sp += h3 ? 1 : 0;
+		if (h2) ts.st.put(sp, e2);
+		sp += h2 ? 1 : 0;
+		if (h1) ts.st.put(sp, e1);
+		sp += h1 ? 1 : 0;
+		ts.st.sp = sp;
+	} else {
+		if (h3) ts.st.push(e3.x, __int_as_float(e3.y));
+		if (h2) ts.st.push(e2.x, __int_as_float(e2.y));
+		if (h1) ts.st.push(e1.x, __int_as_float(e1.y));
+	}
 	ts.node = pick4(c0, c1, c2, c3, key[0] & 3u);
 }
 
@@ -232,7 +275,7 @@ template <bool ANY_HIT, bool EXACT>
 __device__ __forceinline__ void traverse_warp(const SceneDev& sc, int2* stack_smem, int stack_stride, bool active, V3 o,
                                               V3 d, float& best_t, int32_t& best_idx, int32_t& best_slot) {
 	TravState ts;
-	ts.st.smem = stack_smem; ts.st.stride = stack_stride;
+	ts.st.bind(stack_smem, stack_stride);
 	ts.begin<ANY_HIT>(o, d);
 	if (!active) ts.node = kEmptyChildDev;
 	for (;;) {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 	const int total = ANY_HIT ? pool.counts[pool.q_count_idx] : pool.counts[0];
 	int* cursor = pool.counts + (ANY_HIT ? pool.q_cursor_idx : 3);
 	TravState ts;
-	ts.st.smem = stack_smem + threadIdx.x; ts.st.stride = blockDim.x; ts.st.sp = 0;
+	ts.st.bind(stack_smem + threadIdx.x, blockDim.x); ts.st.sp = 0;
 	ts.node = kEmptyChildDev;
 	ts.best_t = 0.0f; ts.best_idx = 0; ts.best_slot = -1;
 	ts.o = mk(0, 0, 0); ts.d = mk(0, 0, 0); ts.rs = make_setup(ts.o, ts.d);
