@@ -132,3 +132,35 @@ def make_segments_to_point(sc: SceneDef, n: int, x, seed: int = 3):
     p4 = cen + d * rng.uniform(0.01, 0.5, (n - 3 * q, 1)) + rng.normal(scale=1e-4, size=(n - 3 * q, 3))
     p = np.concatenate([p1, p2, p3, p4]).astype(np.float32)
     return p, np.tile(x.astype(np.float32)[None, :], (n, 1))
+
+
+def edge_case_scene():
+    """example1 plus: every triangle stored twice more (equal t: the LOWER original index must win, src/Mesh.cpp:40
+    strict '<'), zero-area triangles (two or three equal vertices, collinear), one huge far-away triangle."""
+    sc = named_scene("example1")
+    tris = sc.triangles()
+    rng = np.random.default_rng(3)
+    deg = tris[rng.integers(0, tris.shape[0], 12)].copy()
+    deg[:4, 1] = deg[:4, 0]                                   # two equal vertices
+    deg[4:8, 1] = deg[4:8, 0]
+    deg[4:8, 2] = deg[4:8, 0]                                 # a point
+    deg[8:, 2] = 0.5 * (deg[8:, 0] + deg[8:, 1])              # collinear
+    far = np.array([[[9000.0, 9000.0, -5.0], [9500.0, 9000.0, 300.0], [9000.0, 9500.0, 300.0]]], np.float32)
+    extra = np.concatenate([tris, deg, far, tris[::-1]]).astype(np.float32)
+    sc.meshes.append(MeshDef(sc.meshes[0].material, extra))
+    return sc, tris.shape[0]
+
+
+def edge_case_queries(sc: SceneDef, n: int = 20000):
+    """Rays with exactly zero direction components (infinite inverse directions in the slab test), rays starting
+    exactly on vertices, zero-length occlusion segments -- on top of the usual mix."""
+    rng = np.random.default_rng(4)
+    o, d = make_rays(sc, n, seed=9)
+    q = n // 4
+    d[:q] = np.eye(3, dtype=np.float32)[rng.integers(0, 3, q)] * rng.choice([-1.0, 1.0], (q, 1)).astype(np.float32)
+    d[q: 2 * q, rng.integers(0, 3)] = 0.0
+    verts = sc.triangles().reshape(-1, 3)
+    o[2 * q: 2 * q + n // 10] = verts[rng.integers(0, verts.shape[0], n // 10)]
+    p, x = make_segments(sc, n, seed=10)
+    x[: n // 40] = p[: n // 40]
+    return o, d, p, x

@@ -230,3 +230,19 @@ def test_many_recorders_match_oracle(ob):
     assert res.segments == cnt["segments"] and res.occlusion_queries == cnt["occlusion_queries"]
     assert res.contributions == cnt["contributions"]
     assert _compare_tracks(res, tracks) < REL_TOL
+
+
+def test_ties_degenerate_triangles_and_axis_aligned_rays(ob):
+    """Collisions and nulls as this domain has them (tests/common.py::edge_case_scene / edge_case_queries): duplicated
+    triangles (lowest index wins the tie), zero-area triangles, a huge far triangle, axis-aligned rays, origins exactly
+    on vertices, zero-length segments."""
+    sc, n_orig = common.edge_case_scene()
+    gpu, cpu = _pair(ob, sc)
+    o, d, p, x = common.edge_case_queries(sc)
+    gi, gt = gpu.first_hit(o, d)
+    ci, ct = cpu.first_hit(o, d)
+    assert np.array_equal(gi, ci), f"{(gi != ci).sum()} of {o.shape[0]} first-hit indices differ"
+    hit = ci >= 0
+    assert np.array_equal(gt[hit].view(np.uint32), ct[hit].view(np.uint32))
+    assert (ci[hit] < n_orig).mean() > 0.9                         # the duplicates (higher indices) lose the ties
+    assert np.array_equal(gpu.occluded(p, x), cpu.occluded(p, x))

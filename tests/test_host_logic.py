@@ -96,6 +96,22 @@ def test_bvh_traversal_logic_is_exact_on_host(oracle_lib, name):
     assert np.array_equal(em.occluded(p, x), cpu.occluded(p, x))
 
 
+def test_bvh_ties_and_degenerate_triangles_on_host(oracle_lib):
+    """Duplicated triangles (equal t: lowest original index wins), zero-area triangles, a far outlier, axis-aligned
+    rays, origins on vertices, zero-length segments: builder + traversal logic against the O(T) loop."""
+    sc, n_orig = common.edge_case_scene()
+    em = eb.EmulScene(sc.triangles())
+    cpu = ob.OracleScene.from_def(sc)
+    o, d, p, x = common.edge_case_queries(sc, 12000)
+    ei, et = em.first_hit(o, d)
+    ci, ct = cpu.first_hit(o, d)
+    assert np.array_equal(ei, ci)
+    hit = ci >= 0
+    assert np.array_equal(et[hit].view(np.uint32), ct[hit].view(np.uint32))
+    assert (ci[hit] < n_orig).mean() > 0.9
+    assert np.array_equal(em.occluded(p, x), cpu.occluded(p, x))
+
+
 def test_bvh_margins_are_load_bearing(oracle_lib):
     """With pad and slack switched off the edge-aimed rays DO lose their reference winner: the
     adversarial set exercises exactly what the margins are there for."""
