@@ -24,7 +24,7 @@ MONO, STEREO = 1, 2
 FIRST_SAMPLE_INIT = 3 * SAMPLE_RATE - 1   # FloatBuffer ctor, src/Recorder.cpp:43-48
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libear_b200.so")
+LIB_PATH = os.environ.get("EAR_B200_LIB") or os.path.join(_HERE, "csrc", "libear_b200.so")   # env: A/B builds only
 
 
 class RecorderC(C.Structure):

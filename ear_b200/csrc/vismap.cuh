@@ -20,6 +20,10 @@ struct VisMapDev {
 	int res;
 };
 
+#ifndef EARB_VIS_BATCH
+#define EARB_VIS_BATCH 2
+#endif
+constexpr int kVisBatch = EARB_VIS_BATCH;   // candidates whose loads are issued together in the lookup loop      // candidates whose loads are issued together in the lookup loop
 constexpr int kVisMaxList = 96;   // longer texel lists are traced through the BVH instead (measured: 16 -> 523 ms,
                                   // 48 -> 338, 96 -> 326, 192 -> 407 per 1.9e9 queries; binning queries by direction
                                   // instead of origin cell made both the sort and the lookups slower)
@@ -273,13 +277,29 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 				else {
 					const V3 d = vsub(x, pnt);   // LineSeg(p, x) = Ray(p, x - p)
 					visible = true;
-					for (int k = beg; k < end; ++k) {
-						const float4* rec = sc.tris + 4 * (size_t)mp.items[k];
-						const F8 r01 = ldg256(rec);
-						const float4 r2 = __ldg(rec + 2);
-						float t;
-						if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), pnt, d, t) &&
-						    t > 1e-5f && t < 1.0f) { visible = false; break; }
+					// The loop is a chain of dependent loads (item -> triangle record -> test; ncu: long-scoreboard stalls
+					// 15 per issue).  Two candidates per round, their loads in flight before the first test (measured: 1 -> 123.4,
+					// 2 -> 112.5, 4 -> 127.1 ms per 2e7 rays).  The
+					// tail of a list repeats its last entry (testing a triangle twice cannot change a yes/no answer).
+					for (int k = beg; k < end && visible; k += kVisBatch) {
+						int item[kVisBatch];
+#pragma unroll
+						for (int j = 0; j < kVisBatch; ++j) item[j] = __ldg(mp.items + min(k + j, end - 1));
+						F8 r01[kVisBatch];
+						float4 r2[kVisBatch];
+#pragma unroll
+						for (int j = 0; j < kVisBatch; ++j) {
+							const float4* rec = sc.tris + 4 * (size_t)item[j];
+							r01[j] = ldg256(rec);
+							r2[j] = __ldg(rec + 2);
+						}
+#pragma unroll
+						for (int j = 0; j < kVisBatch; ++j) {
+							float t;
+							if (moeller_trumbore(mk(r01[j].lo.x, r01[j].lo.y, r01[j].lo.z), mk(r01[j].hi.x, r01[j].hi.y, r01[j].hi.z),
+							                     mk(r2[j].x, r2[j].y, r2[j].z), pnt, d, t) &&
+							    t > 1e-5f && t < 1.0f) visible = false;
+						}
 					}
 				}
 			}

@@ -263,7 +263,13 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 // ---------------------------------------------------------------------------------------------------
 // K3 + K6 + K1: shade, refill, enqueue
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+#ifndef EARB_SHADE_MIN_BLOCKS
+#define EARB_SHADE_MIN_BLOCKS 4
+#endif
+#ifndef EARB_DEFER_NORMALISE
+#define EARB_DEFER_NORMALISE 1
+#endif
+__global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(SceneDev sc, WfPool pool, RenderParams p) {
 	const int slot = blockIdx.x * blockDim.x + threadIdx.x;   // n_slots is a multiple of the block size
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -341,6 +347,39 @@ __global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool po
 	// ---- Sample_Sphere / Sample_Hemi (src/Distributions.h:48-67) for every lane that needs a direction: ONE flat
 	// rejection loop (a try = one Philox block; sphere: 0.001 <= |v|^2 <= 1; hemisphere: n.v >= 0), so that a warp
 	// runs max-over-lanes tries once instead of nesting the two rejections ----
+#if EARB_DEFER_NORMALISE
+	V3 v = mk(0, 0, 0);
+	{
+		// The hemisphere test n.v >= 0 is on the NORMALISED candidate v = cand / |cand| in the reference.  Its outcome is
+		// decided on the unnormalised candidate whenever that is clear-cut: |cand| <= 1 and the float evaluation of
+		// n.v is off by ~4e-7 at most, so n.cand < -1e-5 means the exact test rejects and n.cand > 1e-5 means it accepts.
+		// Only in between (probability ~1e-5 per try) is the exact expression evaluated inside the loop.  The sqrt and
+		// the three divisions then run ONCE per lane after the loop, with the warp converged, instead of once per
+		// sphere-accepted try with ~5 lanes active (ncu: that block was 24 % of this kernel's instructions).
+		bool pending = mode != kNone;
+		V3 cand = mk(0, 0, 1);
+		float l = 1.0f;
+		while (pending) {   // one back edge, no break / continue: the warp reconverges every try
+			float u1, u2, u3;
+			rng.unit3(u1, u2, u3);
+			cand = mk(fsub(fmul(u1, 2.0f), 1.0f), fsub(fmul(u2, 2.0f), 1.0f), fsub(fmul(u3, 2.0f), 1.0f));
+			l = vdot(cand, cand);
+			const bool in_sphere = !(l < 0.001f || l > 1.0f);
+			const float dc = fmaf(n.x, cand.x, fmaf(n.y, cand.y, n.z * cand.z));
+			bool accept = in_sphere && (mode != kBounce || dc > 1e-5f);
+			if (in_sphere && mode == kBounce && fabsf(dc) <= 1e-5f) {   // too close to call on the unnormalised candidate
+				const float s = fsqrt(l);
+				accept = !(vdot(n, mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s))) < 0.0f);
+			}
+			pending = !accept;
+		}
+		__syncwarp();
+		if (mode != kNone) {
+			const float s = fsqrt(l);
+			v = mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s));
+		}
+	}
+#else
 	V3 v = mk(0, 0, 0);
 	{
 		bool pending = mode != kNone;
@@ -356,6 +395,7 @@ __global__ void __launch_bounds__(256, 3) wf_shade_kernel(SceneDev sc, WfPool po
 			}
 		}
 	}
+#endif
 	__syncwarp();
 
 	bool shaded = false;
