@@ -132,20 +132,12 @@ struct TravState {
 template <bool EXACT>
 __device__ __forceinline__ void pop_next(const SceneDev& sc, TravState& ts) {
 	const float limit = EXACT ? ts.best_t : fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
-#ifdef EARB_POP_SINGLE_EXIT
 	int32_t node = kEmptyChildDev;
-	while (ts.st.sp > 0 && node == kEmptyChildDev) {   // one exit test, no break: lanes reconverge every round
+	while (ts.st.sp > 0 && node == kEmptyChildDev) {   // one exit test, no break: the lanes reconverge every round (-1 %)
 		const int2 e = ts.st.pop();
 		if (__int_as_float(e.y) <= limit) node = e.x;
 	}
 	ts.node = node;
-#else
-	ts.node = kEmptyChildDev;
-	while (ts.st.sp > 0) {
-		const int2 e = ts.st.pop();
-		if (__int_as_float(e.y) <= limit) { ts.node = e.x; break; }
-	}
-#endif
 }
 
 __device__ __forceinline__ float half_bits_to_float(uint32_t h) {   // fp16 bits -> float (no inf/nan in the table)
