@@ -437,6 +437,7 @@ struct ear_b200_scene {
 	uint2* d_q_bvh = nullptr; size_t q_bvh_cap = 0;
 	float* d_post = nullptr; size_t post_cap = 0;   // post-chain scratch: [n_tracks] float + [n_tracks] uint32
 	int* d_vis_counts = nullptr; long long* d_vis_sums = nullptr; size_t vis_scratch_cap = 0;
+	size_t vis_budget = 0, vis_bytes = 0; bool vis_budget_spent = false;   // memory guard for the maps
 	std::vector<ear_b200_recorder> h_rec;   // host copy of the recorders of the current call
 	float maxabs = 0.0f;
 	// event pairs recorded around every engine launch, harvested at the engine's sync points
@@ -514,7 +515,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	const char* sl = std::getenv("EAR_B200_SLOTS");
 	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
 	s->dev.vis_cap = kVisMaxList;
-	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(255, std::atoi(vc)));
+	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
 	if (const char* rk = std::getenv("EAR_B200_RAY_KEY")) s->ray_key = std::max(0, std::min(4, std::atoi(rk)));
@@ -882,7 +883,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	}
 	for (size_t i = 0; i < s->vismaps.size(); ++i)
 		if (s->vismaps[i].res == res && std::memcmp(s->vismaps[i].x, x, 12) == 0) { *index = (int)i; return 0; }
-	if (s->vismaps.size() >= 64) return 0;   // plenty of distinct recorder positions: the rest use the BVH
+	if (s->vismaps.size() >= 64 || s->vis_budget_spent) return 0;   // the remaining recorder positions use the BVH
 	ear_b200_scene::VisMapHost m{};
 	std::memcpy(m.x, x, 12); m.res = res;
 	const int n_tex = 6 * res * res;
@@ -930,7 +931,21 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 		std::fprintf(stderr, "[ear_b200] vismap: %lld entries, longest list %d, %lld texels over the cap hold %lld entries, stored %d\n", sum, mx, over, over_sum, total);
 		t_prev = std::chrono::steady_clock::now();
 	}
-	if (total < 0) { cudaFree(m.d_offsets); return fail("visibility map overflow"); }
+	// memory guard: all maps of a scene together may take a quarter of the device memory that is free when the first
+	// one is built (a 1e7-triangle scene with 64 recorders would otherwise ask for hundreds of GB); beyond that, and
+	// when a single map's entries overflow 31 bits, the recorder's queries walk the BVH instead
+	if (s->vis_budget == 0) {
+		size_t free_b = 0, total_b = 0;
+		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+		s->vis_budget = std::max<size_t>(free_b / 4, 1);
+	}
+	const size_t map_bytes = ((size_t)n_tex + 1) * sizeof(int) + (total < 0 ? 0 : (size_t)total * sizeof(int));
+	if (total < 0 || s->vis_bytes + map_bytes > s->vis_budget) {
+		cudaFree(m.d_offsets);
+		s->vis_budget_spent = true;
+		return 0;
+	}
+	s->vis_bytes += map_bytes;
 	m.n_items = (size_t)total;
 	CUDA_TRY(cudaMalloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));

@@ -24,9 +24,10 @@ struct VisMapDev {
 #define EARB_VIS_BATCH 2
 #endif
 constexpr int kVisBatch = EARB_VIS_BATCH;   // candidates whose loads are issued together in the lookup loop      // candidates whose loads are issued together in the lookup loop
-constexpr int kVisMaxList = 96;   // longer texel lists are traced through the BVH instead (measured: 16 -> 523 ms,
-                                  // 48 -> 338, 96 -> 326, 192 -> 407 per 1.9e9 queries; binning queries by direction
-                                  // instead of origin cell made both the sort and the lookups slower)
+constexpr int kVisMaxList = 256;  // longer texel lists are not stored: those queries walk the BVH instead.  Per 2e7 rays, with
+                                  // conservative rasterisation and two-candidate rounds: 64 -> 125 ms, 96 -> 113.5, 128 -> 108,
+                                  // 192 -> 102, 255 -> 90 (the hall's longest list is 239: no fallback at all).  Before those two
+                                  // changes the optimum was 96.
 
 // face f: major axis m = f >> 1, sign = +1 (even) / -1 (odd); the other two axes in cyclic order
 __device__ __forceinline__ int vis_texel(const VisMapDev& mp, float dx, float dy, float dz) {

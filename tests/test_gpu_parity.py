@@ -246,3 +246,23 @@ def test_ties_degenerate_triangles_and_axis_aligned_rays(ob):
     assert np.array_equal(gt[hit].view(np.uint32), ct[hit].view(np.uint32))
     assert (ci[hit] < n_orig).mean() > 0.9                         # the duplicates (higher indices) lose the ties
     assert np.array_equal(gpu.occluded(p, x), cpu.occluded(p, x))
+
+
+@pytest.mark.parametrize("env", [{"EAR_B200_VISMAP_CAP": "3"}, {"EAR_B200_VISMAP_RES": "0"}, {"EAR_B200_VISMAP_RES": "64"},
+                                 {"EAR_B200_EXACT_SLACK": "1"}])
+def test_occlusion_paths_agree(ob, monkeypatch, env):
+    """The render loop answers occlusion queries three ways -- visibility-map lists, BVH any-hit for texels whose list
+    is over the cap, BVH any-hit when maps are off -- and in the rigorous-slack mode; every mix must give the oracle's
+    histogram (knobs are read at scene creation)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    sc = common.named_scene("hall20k")
+    sc.samples = 3000
+    gpu, cpu = _pair(ob, sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    ctxs, recs = ctxs[:1], recs[:1]
+    res = gpu.render(ctxs, recs, max_bounces=25, seed=13)
+    tracks, cnt = cpu.render(ctxs, recs, max_bounces=25, seed=13)
+    assert res.segments == cnt["segments"] and res.occlusion_queries == cnt["occlusion_queries"]
+    assert res.contributions == cnt["contributions"] and res.bin_updates == cnt["bin_updates"]
+    assert _compare_tracks(res, tracks) < REL_TOL
