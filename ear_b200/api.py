@@ -13,6 +13,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import sys
 from dataclasses import dataclass
 from typing import List, Optional, Sequence
 
@@ -350,12 +351,16 @@ class Scene:
 
     def render(self, contexts: Sequence[Context], recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0,
                first_ray: int = 0, ray_count: int = -1, finalise: bool = True) -> RenderResult:
+        import time
+        t0 = time.perf_counter()
         ctx = pack_contexts(contexts)
         rec, n_rec = pack_recorders(recorders, len(contexts))
         opt = make_options(max_bounces, n_bins, seed, first_ray, ray_count, finalise)
         res = C.POINTER(ResultC)()
+        t1 = time.perf_counter()
         _check(self.lib, self.lib.ear_b200_render(self.handle, ctx, len(contexts), rec, n_rec, C.byref(opt),
                                                    C.byref(res)))
+        t2 = time.perf_counter()
         try:
             r = res.contents
             tracks = []
@@ -366,14 +371,22 @@ class Scene:
                     n_tracks = 2 if rec[c * n_rec + k].kind == STEREO else 1
                     for tr in range(n_tracks):
                         t = r.tracks[(c * r.n_recorders + k) * 2 + tr]
-                        data = np.ctypeslib.as_array(t.data, shape=(t.length,)).copy()
+                        # one memcpy out of the library-owned buffer (np.ctypeslib.as_array on a pointer builds a ctypes
+                        # array type per call and is an order of magnitude slower for 1e6-sample tracks)
+                        data = np.empty((t.length,), np.float32)
+                        C.memmove(data.ctypes.data, t.data, t.length * 4)
                         pair.append(Track(data, int(t.first_sample), int(t.real_length)))
                     per_rec.append(pair)
                 tracks.append(per_rec)
-            return RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
-                                int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
+            out = RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
+                               int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
         finally:
             self.lib.ear_b200_result_free(res)
+        if os.environ.get("EAR_B200_DEBUG"):
+            t3 = time.perf_counter()
+            print(f"[ear_b200.api] render: pack {1e3 * (t1 - t0):.1f} ms, library call {1e3 * (t2 - t1):.1f} ms, "
+                  f"track copies {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
+        return out
 
 
 def contexts_from_def(scene_def, t60_only: bool = False, n_bands: int = 3, air_factors=None):

@@ -16,7 +16,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ear_b200.h"
@@ -483,6 +485,13 @@ static void image_layout(ImageHeader& h) {
 	h.bytes = h.off_materials + image_round((size_t)h.n_materials * h.n_bands * 4 * sizeof(float));
 }
 
+static void read_slot_knob(ear_b200_scene* s) {
+	const char* sl = std::getenv("EAR_B200_SLOTS");
+	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
+}
+
+static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries);
+
 // everything of scene creation that does not depend on where the image came from
 static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->n_tris = h.n_tris; s->n_materials = h.n_materials; s->n_bands = h.n_bands;
@@ -512,8 +521,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.fetch_vote = fv ? std::max(1, std::min(32, std::atoi(fv))) : 8;
 	const char* en = std::getenv("EAR_B200_ENGINE");
 	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
-	const char* sl = std::getenv("EAR_B200_SLOTS");
-	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
+	read_slot_knob(s);
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
@@ -552,9 +560,27 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
 	s->device = device;
 	const auto t0 = std::chrono::steady_clock::now();
+	// A big scene is built to be rendered with many rays: while the host cores build the BVH, a helper thread
+	// allocates the full-size ray pool (12 cudaMallocs, ~1.3 GB, ~60 ms) that the first render would otherwise wait for.
+	std::thread pool_alloc;
+	int32_t pool_rc = 0;
+	std::string pool_err;
+	if (n_tris >= (1 << 17)) {
+		read_slot_knob(s.get());
+		ear_b200_scene* raw = s.get();
+		pool_alloc = std::thread([raw, device, &pool_rc, &pool_err] {
+			if (cudaSetDevice(device) != cudaSuccess) { pool_rc = 1; pool_err = "cudaSetDevice failed"; return; }
+			pool_rc = ensure_pool(raw, (size_t)raw->max_slots, (size_t)raw->max_slots);
+			if (pool_rc) pool_err = g_last_error;
+		});
+	}
 	Bvh bvh;
 	build_bvh(verts, tri_material, n_tris, bvh);
 	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	if (pool_alloc.joinable()) {
+		pool_alloc.join();
+		if (pool_rc) return fail("scene_create: " + pool_err);
+	}
 	ImageHeader h{};
 	h.magic = kImageMagic; h.version = EAR_B200_ABI_VERSION;
 	h.n_tris = n_tris; h.n_materials = n_materials; h.n_bands = n_bands;
