@@ -217,6 +217,14 @@ def run_ours(args):
         e2e_ms.append((w1 - w0) * 1e3)
         if os.environ.get("EAR_BENCH_VERBOSE"):
             print(f"[bench] rank {rank} e2e step: create {e2e_create_ms[-1]:.1f} ms, render {(w1 - wc) * 1e3:.1f} ms", file=sys.stderr)
+            if os.environ.get("EAR_BENCH_VERBOSE") == "2":   # diagnosis only: the same render again on the now-warm scene
+                s3 = create_replicated_scene(verts, tri_mat, table, device=local)
+                for k in range(2):
+                    torch.cuda.synchronize(); wa = time.perf_counter()
+                    render_sharded(s3, ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234)
+                    torch.cuda.synchronize()
+                    print(f"[bench] rank {rank} render #{k + 1} on one scene: {(time.perf_counter() - wa) * 1e3:.1f} ms", file=sys.stderr)
+                s3.close()
     e2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     es = torch.tensor([e2e_segments], dtype=torch.int64, device=dev)
     if world > 1:
@@ -321,6 +329,7 @@ def reference_sample(sc, procs=None, budget=20):
     except OSError:
         pass
     return {"value": seg / secs, "unit": "segments/s", "cores": procs, "cpu_model": model, "nproc": cores, "kind": "reference",
+            "segments": int(seg), "render_seconds": secs,
             "sample": f"{procs} processes x 1 context, {budget} s budget each (reference's 1000-bounce loop), {int(seg)} segments, "
                       f"{secs:.1f} s render, {wall:.1f} s wall incl. parse"}
 
@@ -333,13 +342,14 @@ def run_reference(args):
     for _ in range(min(args.warmup, 1)):
         reference_sample(sc, procs=max(1, (os.cpu_count() or 1)))
     t0 = time.perf_counter()
-    seg = 0.0
+    seg = secs = 0.0
     last = None
     for _ in range(args.steps):
         last = reference_sample(sc)
-        seg += float(last["sample"].split("), ")[1].split(" segments")[0])
+        seg += last["segments"]
+        secs += last["render_seconds"]
     wall = time.perf_counter() - t0
-    value = last["value"]
+    value = seg / secs          # all steps: segments traced / time the slowest process of each step rendered
     line = {"impl": "reference", "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",

@@ -560,27 +560,9 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
 	s->device = device;
 	const auto t0 = std::chrono::steady_clock::now();
-	// A big scene is built to be rendered with many rays: while the host cores build the BVH, a helper thread
-	// allocates the full-size ray pool (12 cudaMallocs, ~1.3 GB, ~60 ms) that the first render would otherwise wait for.
-	std::thread pool_alloc;
-	int32_t pool_rc = 0;
-	std::string pool_err;
-	if (n_tris >= (1 << 17)) {
-		read_slot_knob(s.get());
-		ear_b200_scene* raw = s.get();
-		pool_alloc = std::thread([raw, device, &pool_rc, &pool_err] {
-			if (cudaSetDevice(device) != cudaSuccess) { pool_rc = 1; pool_err = "cudaSetDevice failed"; return; }
-			pool_rc = ensure_pool(raw, (size_t)raw->max_slots, (size_t)raw->max_slots);
-			if (pool_rc) pool_err = g_last_error;
-		});
-	}
 	Bvh bvh;
 	build_bvh(verts, tri_material, n_tris, bvh);
 	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-	if (pool_alloc.joinable()) {
-		pool_alloc.join();
-		if (pool_rc) return fail("scene_create: " + pool_err);
-	}
 	ImageHeader h{};
 	h.magic = kImageMagic; h.version = EAR_B200_ABI_VERSION;
 	h.n_tris = n_tris; h.n_materials = n_materials; h.n_bands = n_bands;
