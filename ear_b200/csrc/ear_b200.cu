@@ -32,6 +32,18 @@ using namespace earb;
 // ------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 static int32_t fail(const std::string& msg) { g_last_error = msg; return 1; }
+
+// call-scoped device buffer: freed on every return path (the ABI functions leave through CUDA_TRY on errors)
+template <class T>
+struct DevBuf {
+	T* p = nullptr;
+	DevBuf() = default;
+	DevBuf(const DevBuf&) = delete;
+	DevBuf& operator=(const DevBuf&) = delete;
+	~DevBuf() { if (p) cudaFree(p); }
+	cudaError_t alloc(size_t count) { return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+	operator T*() const { return p; }
+};
 #define CUDA_TRY(expr)                                                                          \
 	do {                                                                                        \
 		cudaError_t err__ = (expr);                                                             \
@@ -657,9 +669,10 @@ extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, c
 	if (n <= 0) return 0;
 	CUDA_TRY(cudaSetDevice(s->device));
 	const int64_t chunk = std::min<int64_t>(n, s->max_slots);
-	float *d_o = nullptr, *d_d = nullptr, *d_t = nullptr; int32_t* d_i = nullptr;
-	CUDA_TRY(cudaMalloc(&d_o, chunk * 12)); CUDA_TRY(cudaMalloc(&d_d, chunk * 12));
-	CUDA_TRY(cudaMalloc(&d_t, chunk * 4)); CUDA_TRY(cudaMalloc(&d_i, chunk * 4));
+	DevBuf<float> d_o, d_d, d_t;
+	DevBuf<int32_t> d_i;
+	CUDA_TRY(d_o.alloc((size_t)chunk * 3)); CUDA_TRY(d_d.alloc((size_t)chunk * 3));
+	CUDA_TRY(d_t.alloc((size_t)chunk)); CUDA_TRY(d_i.alloc((size_t)chunk));
 	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, 1)) return rc; }
 	RenderParams p{};
 	for (int64_t at = 0; at < n; at += chunk) {
@@ -683,7 +696,6 @@ extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, c
 		CUDA_TRY(cudaMemcpyAsync(t + at, d_t, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 	}
-	cudaFree(d_o); cudaFree(d_d); cudaFree(d_t); cudaFree(d_i);
 	return 0;
 }
 
@@ -692,9 +704,11 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 	if (n <= 0) return 0;
 	CUDA_TRY(cudaSetDevice(s->device));
 	const int64_t chunk = std::min<int64_t>(n, s->max_slots);
-	float *d_p = nullptr, *d_x = nullptr; uint8_t* d_out = nullptr; float4* d_qx = nullptr;
-	CUDA_TRY(cudaMalloc(&d_p, chunk * 12)); CUDA_TRY(cudaMalloc(&d_x, chunk * 12)); CUDA_TRY(cudaMalloc(&d_out, chunk));
-	CUDA_TRY(cudaMalloc(&d_qx, chunk * sizeof(float4)));
+	DevBuf<float> d_p, d_x;
+	DevBuf<uint8_t> d_out;
+	DevBuf<float4> d_qx;
+	CUDA_TRY(d_p.alloc((size_t)chunk * 3)); CUDA_TRY(d_x.alloc((size_t)chunk * 3)); CUDA_TRY(d_out.alloc((size_t)chunk));
+	CUDA_TRY(d_qx.alloc((size_t)chunk));
 	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, (size_t)chunk)) return rc; }
 	RenderParams p{};
 	// all segments end at one point (the render loop's case): answer through that point's visibility map,
@@ -742,7 +756,6 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 		CUDA_TRY(cudaMemcpyAsync(out + at, d_out, (size_t)m, cudaMemcpyDeviceToHost, s->stream));
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
 	}
-	cudaFree(d_p); cudaFree(d_x); cudaFree(d_out); cudaFree(d_qx);
 	return 0;
 }
 
@@ -1200,10 +1213,12 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, s->stream, p)) return rc;
 	const int32_t n_bins = ear_b200_default_bins(s, opt);
 	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
-	float* d_hist = nullptr; uint32_t* d_range = nullptr; unsigned long long* d_counters = nullptr;
-	CUDA_TRY(cudaMalloc(&d_hist, n_tracks * n_bins * sizeof(float)));
-	CUDA_TRY(cudaMalloc(&d_range, n_tracks * 2 * sizeof(uint32_t)));
-	CUDA_TRY(cudaMalloc(&d_counters, 8 * sizeof(unsigned long long)));
+	DevBuf<float> d_hist;
+	DevBuf<uint32_t> d_range;
+	DevBuf<unsigned long long> d_counters;
+	CUDA_TRY(d_hist.alloc(n_tracks * (size_t)n_bins));
+	CUDA_TRY(d_range.alloc(n_tracks * 2));
+	CUDA_TRY(d_counters.alloc(8));
 	CUDA_TRY(cudaMemsetAsync(d_hist, 0, n_tracks * n_bins * sizeof(float), s->stream));
 	CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
 	init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(d_range, (int)n_tracks);
@@ -1243,7 +1258,6 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
 	res->contributions = counters[3]; res->bin_updates = counters[4]; res->dropped_updates = counters[5];
 	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;
-	cudaFree(d_hist); cudaFree(d_range); cudaFree(d_counters);
 	*out = res;
 	return 0;
 }
@@ -1324,19 +1338,18 @@ extern "C" int32_t ear_b200_convolve(int32_t device, const float* response, uint
 	if (out_first) *out_first = std::min<uint32_t>(init_first, offset + first);
 	if (out_real) *out_real = (uint32_t)last;
 	if (last + 1 > out_len) return fail("convolve: output buffer shorter than n_dry - 1 + offset + real_length");
-	float *d_r1 = nullptr, *d_r2 = nullptr, *d_dry = nullptr, *d_out = nullptr;
+	DevBuf<float> d_r1, d_r2, d_dry, d_out;
 	const uint32_t n1 = std::min(length, len), n2 = fade ? std::min(length2, len) : 0;
-	CUDA_TRY(cudaMalloc(&d_r1, std::max<size_t>(n1, 1) * 4)); CUDA_TRY(cudaMalloc(&d_dry, (size_t)n_dry * 4));
-	CUDA_TRY(cudaMalloc(&d_out, (size_t)(last + 1) * 4));
+	CUDA_TRY(d_r1.alloc(n1)); CUDA_TRY(d_dry.alloc(n_dry));
+	CUDA_TRY(d_out.alloc((size_t)(last + 1)));
 	CUDA_TRY(cudaMemcpy(d_r1, response, (size_t)n1 * 4, cudaMemcpyHostToDevice));
 	CUDA_TRY(cudaMemcpy(d_dry, dry, (size_t)n_dry * 4, cudaMemcpyHostToDevice));
-	if (fade) { CUDA_TRY(cudaMalloc(&d_r2, std::max<size_t>(n2, 1) * 4)); CUDA_TRY(cudaMemcpy(d_r2, response2, (size_t)n2 * 4, cudaMemcpyHostToDevice)); }
+	if (fade) { CUDA_TRY(d_r2.alloc(n2)); CUDA_TRY(cudaMemcpy(d_r2, response2, (size_t)n2 * 4, cudaMemcpyHostToDevice)); }
 	const unsigned grid = (unsigned)((last + 1 + kConvTile - 1) / kConvTile);
 	if (fade) convolve_kernel<true><<<grid, kConvTile>>>(d_r1, n1, d_r2, n2, first, len, d_dry, n_dry, offset, d_out, (uint32_t)(last + 1));
-	else convolve_kernel<false><<<grid, kConvTile>>>(d_r1, n1, nullptr, 0, first, len, d_dry, n_dry, offset, d_out, (uint32_t)(last + 1));
+	else convolve_kernel<false><<<grid, kConvTile>>>(d_r1, n1, (const float*)nullptr, 0, first, len, d_dry, n_dry, offset, d_out, (uint32_t)(last + 1));
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpy(out, d_out, (size_t)(last + 1) * 4, cudaMemcpyDeviceToHost));
-	cudaFree(d_r1); cudaFree(d_r2); cudaFree(d_dry); cudaFree(d_out);
 	return 0;
 }
 
@@ -1380,8 +1393,9 @@ extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_contex
 	RenderParams p{};
 	if (int32_t rc = upload_params(s, cs.data(), ctx_index + 1, rs.data(), 1, opt, s->stream, p, prefix.data())) return rc;
 	p.first_ray = opt->first_ray;
-	int32_t* d_hits = nullptr; float* d_state = nullptr;
-	CUDA_TRY(cudaMalloc(&d_hits, (size_t)n * max_b * 4)); CUDA_TRY(cudaMalloc(&d_state, (size_t)n * 32));
+	DevBuf<int32_t> d_hits;
+	DevBuf<float> d_state;
+	CUDA_TRY(d_hits.alloc((size_t)n * max_b)); CUDA_TRY(d_state.alloc((size_t)n * 8));
 	CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)n * 32, s->stream));
 	if (s->engine == 0) {
 		wf_fill_int_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(d_hits, (long long)n * max_b, -2);
@@ -1398,6 +1412,5 @@ extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_contex
 	CUDA_TRY(cudaMemcpyAsync(hits, d_hits, (size_t)n * max_b * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (final_state) CUDA_TRY(cudaMemcpyAsync(final_state, d_state, (size_t)n * 32, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
-	cudaFree(d_hits); cudaFree(d_state);
 	return 0;
 }
