@@ -3,8 +3,9 @@
 mkdir -p gpurun_out
 export EAR_BENCH_RAYS=2e7
 ARGS="bench.py --steps 1 --warmup 0 --no-e2e --no-cpu-baseline"
-for k in wf_vismap_kernel wf_shade_kernel; do
-  timeout 170 ncu --set full --clock-control none --import-source on -k regex:$k -s 20 -c 1 -f -o gpurun_out/r1_$k python $ARGS > gpurun_out/ncu_$k.log 2>&1
+for k in wf_traverse_kernel wf_vismap_kernel wf_shade_kernel wf_splat_kernel; do
+  skip=20; [ $k = wf_traverse_kernel ] && skip=40
+  timeout 170 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o gpurun_out/r1_final_$k python $ARGS > gpurun_out/ncu_$k.log 2>&1
   echo "$k rc=$?"
 done
-ls -la gpurun_out | grep r1_wf
+ls -la gpurun_out | grep r1_final

@@ -1,6 +1,6 @@
 #!/bin/bash
 # A/B of compile-time variants (build_variants/*.so, see DESIGN.md "how it got here")
-for v in cur two; do
+for v in cur prefetch; do
   EAR_B200_LIB=$PWD/build_variants/libear_b200_$v.so EAR_BENCH_RAYS=2e7 timeout 200 python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "
 import sys,json
 d=json.loads(sys.stdin.readline()); k=d['kernel_ms_per_step']
