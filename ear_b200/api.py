@@ -34,7 +34,7 @@ class RecorderC(C.Structure):
 
 
 class ContextC(C.Structure):
-    _fields_ = [("band", C.c_int32), ("reserved", C.c_int32), ("num_samples", C.c_int64),
+    _fields_ = [("band", C.c_int32), ("stream_id", C.c_int32), ("num_samples", C.c_int64),
                 ("absorption_factor", C.c_float), ("dry_level", C.c_float), ("gain", C.c_float),
                 ("source_position", C.c_float * 3)]
 
@@ -137,10 +137,12 @@ class Context:
     source_position: Sequence[float]
     dry_level: float = 1.0
     gain: float = 1.0
+    stream_id: int = 0      # 0: position in the call keys the random streams; k > 0: key k - 1 (see include/ear_b200.h)
 
     def to_c(self) -> ContextC:
         c = ContextC()
         c.band, c.num_samples = int(self.band), int(self.num_samples)
+        c.stream_id = int(self.stream_id)
         c.absorption_factor = float(np.float32(self.absorption_factor))
         c.dry_level, c.gain = float(self.dry_level), float(self.gain)
         c.source_position[:] = [float(x) for x in self.source_position]

@@ -74,6 +74,12 @@ struct LocalCounters {
 	unsigned long long rays, segments, occlusion, contributions, bin_updates, dropped;
 };
 
+// Philox "context" word of a ray's streams: the context's position in the call unless the caller pinned it
+__device__ __forceinline__ uint32_t stream_key(const RenderParams& p, int c) {
+	const int32_t id = p.ctx[c].stream_id;
+	return id > 0 ? (uint32_t)(id - 1) : (uint32_t)c;
+}
+
 #define PI_F 3.14159265f  /* src/Distributions.h:37 */
 
 // FloatBuffer::operator[] bookkeeping (src/Recorder.cpp:52-59): first_sample = min touched index,
@@ -187,7 +193,7 @@ __device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderPara
 				band = p.ctx[c].band;
 				af = p.ctx[c].absorption_factor;
 				log2_af = log2_ref(af);
-				rng.start(p.seed, (uint32_t)c, ray);
+				rng.start(p.seed, stream_key(p, c), ray);
 				++lc.rays;
 				// bounce 0: AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226); intensity 1 is
 				// FP_NORMAL and >= 1e-8 and nothing is recorded for point sources (src/Scene.cpp:185), so the
@@ -787,6 +793,7 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	for (int32_t c = 0; c < n_ctx; ++c) {
 		if (ctx[c].band < 0 || ctx[c].band >= s->n_bands) return fail("render: context band outside the material table");
 		if (ctx[c].num_samples < 0) return fail("render: negative num_samples");
+		if (ctx[c].stream_id < 0) return fail("render: negative stream_id");
 	}
 	for (int32_t i = 0; i < n_ctx * n_rec; ++i)
 		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("render: unknown recorder kind");

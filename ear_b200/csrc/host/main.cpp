@@ -137,6 +137,8 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 		const Source& src = sf.sources[ctxs[c].sound];
 		std::memset(&cc[c], 0, sizeof(cc[c]));
 		cc[c].band = ctxs[c].band;
+		cc[c].stream_id = c + 1;   // random streams keyed by the global context index: the result does not depend on how
+		                           // the contexts are dealt to GPUs
 		cc[c].num_samples = num_samples;
 		cc[c].absorption_factor = 1.0f - air[ctxs[c].band];
 		cc[c].dry_level = dry_level;
@@ -190,10 +192,7 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 			if (g > 0 && ear_b200_scene_clone(scenes[0], g, &scenes[g])) { errors[g] = ear_b200_last_error(); return; }
 			ear_b200_scene* scene = scenes[g];
 			ear_b200_result* res = nullptr;
-			// the Philox stream is keyed by the context's position in the call: keep the global index
-			// stable by rendering each context as its own call slot would be -- contexts of one GPU
-			// are passed together, keyed 0..k-1; different GPUs use different seeds
-			ear_b200_options o = opt; o.seed = opt.seed + 0x9E3779B97F4A7C15ull * (uint64_t)g;
+			ear_b200_options o = opt;   // same seed everywhere: the contexts carry their global stream ids
 			if (ear_b200_render(scene, lc.data(), (int32_t)lc.size(), lr.data(), n_rec, &o, &res)) { errors[g] = ear_b200_last_error(); return; }
 			for (size_t i = 0; i < mine.size(); ++i) {
 				Context& c = ctxs[mine[i]];

@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	bool refract = false;
 	unsigned long long ray = ((unsigned long long)m.y << 32) | m.x;
 	Rng rng;
-	rng.start(p.seed, (uint32_t)c, ray, m.w);
+	rng.start(p.seed, stream_key(p, c), ray, m.w);
 
 	// ---- K6 + K1 (first half): slots that are empty on entry take the next ray id of the shard.  (A ray that ends in
 	// this launch frees its slot for the NEXT launch: one idle iteration per ~50, and emission shares the sampling
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			c = 0;
 			while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
 			ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
-			rng.start(p.seed, (uint32_t)c, ray, 0);
+			rng.start(p.seed, stream_key(p, c), ray, 0);
 			m.x = (uint32_t)ray; m.y = (uint32_t)(ray >> 32);
 			++lc.rays;
 			mode = kEmit;

@@ -54,7 +54,9 @@ typedef struct ear_b200_recorder {
 /* One SceneContext (src/SceneContext.h:28-45): a (sound, keyframe, band) render. */
 typedef struct ear_b200_context {
 	int32_t band;                 /* column of the material table */
-	int32_t reserved;
+	int32_t stream_id;            /* 0: the context's position in the call keys its random streams; k > 0: key k - 1 is used
+	                                 instead, so a context traced alone or on another GPU follows the paths it has inside
+	                                 the full call (the CLI deals contexts to GPUs and passes the global index + 1) */
 	int64_t num_samples;          /* rays; the CLI passes settings "samples"/10 (src/EAR.cpp:81) */
 	float absorption_factor;      /* 1 - air absorption[band] per metre (src/EAR.cpp:180) */
 	float dry_level;              /* direct-sound gain (src/Scene.cpp:308-309) */

@@ -266,3 +266,25 @@ def test_occlusion_paths_agree(ob, monkeypatch, env):
     assert res.segments == cnt["segments"] and res.occlusion_queries == cnt["occlusion_queries"]
     assert res.contributions == cnt["contributions"] and res.bin_updates == cnt["bin_updates"]
     assert _compare_tracks(res, tracks) < REL_TOL
+
+
+def test_stream_id_pins_the_random_streams(ob):
+    """A context rendered alone with stream_id = k + 1 follows the paths it has as context k of the full call
+    (how the CLI keeps its output independent of the number of GPUs the contexts are dealt to)."""
+    sc = common.named_scene("example1")
+    sc.samples = 8000
+    gpu, cpu = _pair(ob, sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    full = gpu.render(ctxs, recs, max_bounces=60, seed=4)
+    segs = 0
+    for k in range(len(ctxs)):
+        ctxs[k].stream_id = k + 1
+        alone = gpu.render([ctxs[k]], [recs[k]], max_bounces=60, seed=4)
+        segs += alone.segments
+        for a, f in zip(alone.tracks[0][0], full.tracks[k][0]):
+            assert (a.first_sample, a.real_length) == (f.first_sample, f.real_length)
+            assert np.abs(a.data - f.data).max() <= 1e-4 * np.abs(f.data).max()
+    assert segs == full.segments
+    ctxs[1].stream_id = 0
+    other = gpu.render([ctxs[1]], [recs[1]], max_bounces=60, seed=4)      # keyed as context 0 now: different paths
+    assert not np.array_equal(other.tracks[0][0][0].data, full.tracks[1][0][0].data)
