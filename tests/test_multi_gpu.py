@@ -58,3 +58,38 @@ def test_replicated_scene_and_sharded_render_match_one_gpu(tmp_path):
     assert np.array_equal(got["real"], [t.real_length for t in flat])
     ref = np.stack([t.data for t in flat])
     assert np.abs(got["hist"] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_cli_output_does_not_depend_on_gpu_count(tmp_path):
+    """18 contexts dealt to 1 GPU and to 2 GPUs: the contexts carry their global stream ids, so both runs trace the
+    same paths and the written wav agrees to the last bit or two of the 16-bit samples (float atomics reorder sums)."""
+    import subprocess
+    import wave
+
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from ear_b200 import scenes
+    from ear_b200.earfile import SourceDef
+    from tests.test_cli_animated_gpu import EAR, _read, _tone
+    sc = scenes.example1_scene(samples=8000, wav=_tone(str(tmp_path / "a.wav"), 440.0), stereo=False)
+    sc.keys = [0.0, 0.05, 0.1]
+    sc.sources[0].position = None
+    sc.sources[0].animation = np.array([[-5, 5, 1.6], [-4, 5, 1.6], [-3, 5, 1.6]], np.float32)
+    sc.sources.append(SourceDef([_tone(str(tmp_path / "lo.wav"), 120.0), _tone(str(tmp_path / "mid.wav"), 1000.0),
+                                 _tone(str(tmp_path / "hi.wav"), 5000.0)],
+                                animation=np.array([[8, -8, 1.2]] * 3, np.float32), gain=0.5, offset=0.02))
+    sc.recorders[0].position = None
+    sc.recorders[0].animation = np.array([[5, -5, 1.6], [5, -4, 1.6], [5, -3, 1.6]], np.float32)
+    sc.recorders[0].filename = str(tmp_path / "out.wav")
+    path = str(tmp_path / "anim.ear")
+    sc.write(path)
+    outs = []
+    for gpus in ("1", "2"):
+        env = dict(os.environ, EAR_SEED="9", EAR_MAX_BOUNCES="80", EAR_GPUS=gpus)
+        r = subprocess.run([EAR, "render", path], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-800:]
+        assert f"on {gpus} GPU(s)" in r.stdout
+        outs.append(_read(sc.recorders[0].filename)[0])
+    assert outs[0].shape == outs[1].shape
+    assert np.abs(outs[0].astype(np.int32) - outs[1]).max() <= 2
