@@ -439,7 +439,9 @@ struct ear_b200_scene {
 	int sm_count = 148;
 	int min_blocks = 4;
 	int engine = 0;                 // 0 = wavefront (default), 1 = fused kernel (EAR_B200_ENGINE=mega)
-	int max_slots = 1 << 23;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS)
+	int max_slots = 1 << 24;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS); per 8e7 rays: 8 Mi 1.50e9,
+	                                // 16 Mi 1.55e9, 32 Mi 1.56e9, 64 Mi 1.55e9 seg/s (bigger launches amortise the persistent
+	                                // kernels' tails and sort better, but the shade kernel walks every slot)
 	bool slots_forced = false;
 	int check_every = 8;            // iterations between host checks for completion
 	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
@@ -505,7 +507,7 @@ static void image_layout(ImageHeader& h) {
 
 static void read_slot_knob(ear_b200_scene* s) {
 	const char* sl = std::getenv("EAR_B200_SLOTS");
-	if (sl) { s->max_slots = std::max(256, std::min(1 << kSlotBits, std::atoi(sl))); s->slots_forced = true; }
+	if (sl) { s->max_slots = std::max(256, std::min(1 << kMaxSlotBits, std::atoi(sl))); s->slots_forced = true; }
 }
 
 static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries);
@@ -889,6 +891,7 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
+	pl.slot_bits = kMaxSlotBits;   // harness calls: one implicit recorder
 	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, kBinsTotal * sizeof(int)));
 	pl.ray_key = s->ray_key;
 	pl.sort_queries = s->sort_queries;
@@ -1021,6 +1024,13 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	// should host several rays in turn or the run ends in a long half-empty decay: a quarter of the shard's rays
 	long long slots = std::min<long long>(std::max<long long>(p.total_work, 1), s->max_slots);
 	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / 4));
+	// a query word holds slot | recorder << slot_bits
+	int rec_bits = 0;
+	while ((1 << rec_bits) < p.n_rec) ++rec_bits;
+	const int slot_bits = std::min(kMaxSlotBits, 32 - rec_bits);
+	slots = std::min<long long>(slots, 1LL << slot_bits);
+	// the query lists are indexed with 32-bit ints and cost 24 bytes per (slot, recorder): at most 2^29 queries in flight
+	slots = std::min<long long>(slots, std::max<long long>(256, (1LL << 29) / std::max(1, p.n_rec)));
 	slots = (slots + 255) / 256 * 256;
 	if (int32_t rc = ensure_pool(s, (size_t)slots, (size_t)slots * std::max(1, p.n_rec))) return rc;
 	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
@@ -1037,6 +1047,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	}
 	WfPool pl = s->pool;
 	pl.n_slots = (int)slots;
+	pl.slot_bits = slot_bits;
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	WfPool pl_fb = pl;   // the map fallback list, traced by the BVH any-hit kernel
 	pl_fb.q_list = s->d_q_bvh; pl_fb.q_count_idx = 5; pl_fb.q_cursor_idx = 6;

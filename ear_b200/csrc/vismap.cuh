@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 		uint2 q = make_uint2(0u, 0u);
 		if (i < total) {
 			q = pool.q_list[i];
-			const uint32_t slot = q.x & kSlotMask, r = q.x >> kSlotBits, c = q.y & 0xffffu;
+			const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u), r = q.x >> pool.slot_bits, c = q.y & 0xffffu;
 			const int mi = map_of[c * p.n_rec + r];
 			if (mi < 0) fallback = true;
 			else {

@@ -36,6 +36,7 @@ struct WfPool {
 	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
 	int* bins;          // [kRayBins + kSortBins (+ block sums)] histogram -> offsets of the two counting sorts (closest rays, queries)
 	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
+	int slot_bits;      // split of the query word between slot index and recorder index (see kMaxSlotBits)
 	int sort_queries;   // 0: occlusion queries keep their slot order (EAR_B200_SORT_QUERIES)
 	int ray_key;        // how closest-hit rays are binned (EAR_B200_RAY_KEY): 0 octant+cell12, 1 octant+axis order+cell12, 2 octant+cell15
 	double* ctx_log2af; // [n_ctx] log2(absorption_factor), hoisted out of pow(af, length)
@@ -55,8 +56,7 @@ constexpr int kScanBlocks = kRayScanBlocks + kQueryScanBlocks;
 // bins layout: [0, kRayBins) rays | [kRayBins, +kSortBins) queries | [.., +kScanBlocks) prefixes of the 1024-bin blocks
 constexpr int kBinsTotal = kRayBins + kSortBins + kScanBlocks;
 constexpr int32_t kWaitLeaf = 0x7ffffffe;   // closest-hit lane waiting for its parked leaf (kEmptyChildDev - 1)
-constexpr int kSlotBits = 24;
-constexpr uint32_t kSlotMask = (1u << kSlotBits) - 1u;
+constexpr int kMaxSlotBits = 28;   // a query word is slot | recorder << slot_bits; slot_bits = min(28, 32 - bits(n_rec)) per call
 
 // ---------------------------------------------------------------------------------------------------
 // K2 / K4: persistent traversal with dynamic fetch
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 				if (has_job) {
 					if (ANY_HIT) {
 						job = pool.q_list[my];
-						const uint32_t slot = job.x & kSlotMask, r = job.x >> kSlotBits, c = job.y & 0xffffu;
+						const uint32_t slot = job.x & ((1u << pool.slot_bits) - 1u), r = job.x >> pool.slot_bits, c = job.y & 0xffffu;
 						const float4 s0 = pool.sh0[slot];
 						V3 x;
 						if (pool.qx) { const float4 e = pool.qx[my]; x = mk(e.x, e.y, e.z); }
@@ -455,10 +455,10 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 					const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
 					atomicAdd(pool.bins + kRayBins + bin, 1);
 					pool.q_tmp[base + __popc(mq & lt_mask)] =
-					    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
+					    make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
 				} else {
 					pool.q_list[base + __popc(mq & lt_mask)] =
-					    make_uint2((uint32_t)slot | ((uint32_t)r << kSlotBits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
+					    make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
 				}
 			}
 		}
@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(256) wf_splat_kernel(WfPool pool, RenderParams
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
 		const uint2 q = pool.vis_list[i];
-		const uint32_t slot = q.x & kSlotMask, r = q.x >> kSlotBits, c = q.y & 0xffffu;
+		const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u), r = q.x >> pool.slot_bits, c = q.y & 0xffffu;
 		const float4 s0 = pool.sh0[slot], s1 = pool.sh1[slot], s2 = pool.sh2[slot];
 		const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
 		const V3 pnt = mk(s0.x, s0.y, s0.z), n = mk(s1.x, s1.y, s1.z), prev_dir = mk(s2.x, s2.y, s2.z);
@@ -565,7 +565,7 @@ __global__ void wf_load_segments_kernel(WfPool pool, float4* qx, const float* pp
 }
 __global__ void wf_mark_visible_kernel(WfPool pool, uint8_t* out) {
 	const int total = pool.counts[2];
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[pool.vis_list[i].x & kSlotMask] = 0;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) out[pool.vis_list[i].x & ((1u << pool.slot_bits) - 1u)] = 0;
 }
 __global__ void wf_ctx_table_kernel(WfPool pool, RenderParams p) {
 	const int c = blockIdx.x * blockDim.x + threadIdx.x;
