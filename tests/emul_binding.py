@@ -12,7 +12,8 @@ LIB = os.path.join(HERE, "host_emul", "libemul.so")
 
 def build():
     srcs = [os.path.join(HERE, "host_emul", "emul.cpp"), os.path.join(ROOT, "ear_b200", "csrc", "bvh_build.cpp")]
-    deps = srcs + [os.path.join(ROOT, "ear_b200", "csrc", f) for f in ("traverse.cuh", "device_exact.cuh", "bvh_build.h")]
+    deps = srcs + [os.path.join(ROOT, "ear_b200", "csrc", f) for f in ("traverse.cuh", "device_exact.cuh", "bvh_build.h", "vismap_geom.cuh")]
+    deps.append(os.path.join(HERE, "host_emul", "cuda_shim.h"))
     if os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-shared", "-include",
@@ -52,6 +53,17 @@ class EmulScene:
         t = np.empty(o.shape[0], np.float32)
         self.l.emul_first_hit(self.h, o.ctypes.data, d.ctypes.data, o.shape[0], idx.ctypes.data, t.ctypes.data)
         return idx, t
+
+    def vismap_violations(self, x, res, points):
+        """(violations, accepted, listed) of the visibility-map superset check for recorder position x."""
+        x = np.ascontiguousarray(x, np.float32).reshape(3)
+        p = np.ascontiguousarray(points, np.float32).reshape(-1, 3)
+        acc, lst = C.c_int64(), C.c_int64()
+        self.l.emul_vismap_violations.restype = C.c_int64
+        self.l.emul_vismap_violations.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int64,
+                                                  C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        bad = self.l.emul_vismap_violations(self.h, x.ctypes.data, res, p.ctypes.data, p.shape[0], C.byref(acc), C.byref(lst))
+        return int(bad), int(acc.value), int(lst.value)
 
     def occluded(self, p, x):
         p = np.ascontiguousarray(p, np.float32).reshape(-1, 3)

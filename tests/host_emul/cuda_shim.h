@@ -26,6 +26,8 @@ static inline int2 make_int2(int x, int y) { int2 r = {x, y}; return r; }
 static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline unsigned __ballot_sync(unsigned, bool p) { return p ? 1u : 0u; }   // a one-lane warp
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline float __double2float_ru(double x) { float f = (float)x; return (double)f < x ? nextafterf(f, INFINITY) : f; }
+static inline float __double2float_rd(double x) { float f = (float)x; return (double)f > x ? nextafterf(f, -INFINITY) : f; }
 using std::min;
 using std::max;
 #define EARB_HOST_EMULATION 1

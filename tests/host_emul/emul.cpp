@@ -3,6 +3,7 @@
 #include "cuda_shim.h"
 #include "../../ear_b200/csrc/bvh_build.h"
 #include "../../ear_b200/csrc/traverse.cuh"
+#include "../../ear_b200/csrc/vismap_geom.cuh"
 #include <vector>
 #include <chrono>
 using namespace earb;
@@ -42,5 +43,47 @@ void emul_occluded(void* h, const float* p, const float* x, int64_t n, uint8_t* 
 		else traverse_warp<true, false>(e->dev, stack, 1, true, a, vsub(b, a), bt, bi, slot);
 		out[i] = (uint8_t)bi;
 	}
+}
+
+// Visibility-map superset property (vismap_geom.cuh): for each point P, every triangle the reference's float test
+// accepts on the segment P -> X (1e-5 < t < 1) must be among the candidates of P's texel.  Returns the number of
+// accepted triangles that are NOT candidates (must be 0); *accepted = accepted triangles, *listed = candidates seen.
+int64_t emul_vismap_violations(void* h, const float* X, int32_t res, const float* P, int64_t n, int64_t* accepted, int64_t* listed) {
+	Emul* e = (Emul*)h;
+	const int T = e->dev.n_tris;
+	float maxabs = 0.0f;
+	for (int k = 0; k < 3; ++k) maxabs = std::max(maxabs, std::max(std::fabs(e->bvh.lo[k]), std::fabs(e->bvh.hi[k])));
+	const double reach = 2.0 * (double)e->bvh.diagonal + 1.0;
+	const double Xd[3] = {X[0], X[1], X[2]};
+	struct Foot { int i0, i1, j0, j1; float edge[9]; bool valid, has_edges; };
+	std::vector<Foot> foot((size_t)T * 6);
+	for (int t = 0; t < T; ++t)
+		for (int f = 0; f < 6; ++f) {
+			Foot& ft = foot[(size_t)t * 6 + f];
+			ft.valid = vis_footprint(e->dev, t, Xd, res, f, reach, (double)maxabs, ft.i0, ft.i1, ft.j0, ft.j1, ft.edge, ft.has_edges);
+		}
+	VisMapDev mp;
+	mp.offsets = nullptr; mp.items = nullptr; mp.res = res;
+	for (int k = 0; k < 3; ++k) mp.x[k] = X[k];
+	int64_t bad = 0, acc = 0, lst = 0;
+	const V3 x = mk(X[0], X[1], X[2]);
+	for (int64_t q = 0; q < n; ++q) {
+		const V3 pnt = mk(P[3 * q], P[3 * q + 1], P[3 * q + 2]);
+		const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
+		const int f = texel / (res * res), j = (texel / res) % res, i = texel % res;
+		const V3 d = vsub(x, pnt);
+		for (int t = 0; t < T; ++t) {
+			const Foot& ft = foot[(size_t)t * 6 + f];
+			const bool in_list = ft.valid && i >= ft.i0 && i <= ft.i1 && j >= ft.j0 && j <= ft.j1 && (!ft.has_edges || vis_covers(ft.edge, res, i, j));
+			lst += in_list ? 1 : 0;
+			const float4* rec = e->dev.tris + 4 * (size_t)t;
+			float tt;
+			const bool hit = moeller_trumbore(mk(rec[0].x, rec[0].y, rec[0].z), mk(rec[1].x, rec[1].y, rec[1].z), mk(rec[2].x, rec[2].y, rec[2].z), pnt, d, tt) &&
+			                 tt > 1e-5f && tt < 1.0f;
+			if (hit) { ++acc; if (!in_list) ++bad; }
+		}
+	}
+	*accepted = acc; *listed = lst;
+	return bad;
 }
 }

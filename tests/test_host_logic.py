@@ -112,6 +112,27 @@ def test_bvh_ties_and_degenerate_triangles_on_host(oracle_lib):
     assert np.array_equal(em.occluded(p, x), cpu.occluded(p, x))
 
 
+@pytest.mark.parametrize("name,res", [("rt60", 64), ("example1", 256), ("soup", 256), ("hall20k", 128), ("hall20k", 1024)])
+def test_visibility_map_lists_are_supersets_on_host(oracle_lib, name, res):
+    """The recorder visibility maps answer occlusion queries from per-texel candidate lists.  Compiled for the host
+    (vismap_geom.cuh): for segments from surface points, vertex / edge points, free-space points and plane-grazing
+    points to the recorder -- and to a second end point one centimetre off a wall --, every triangle the reference's
+    float test accepts (1e-5 < t < 1) is a candidate of the query's texel."""
+    sc = common.named_scene(name)
+    em = eb.EmulScene(sc.triangles())
+    tris = sc.triangles().reshape(-1, 3)
+    lo, hi = tris.min(0), tris.max(0)
+    near_wall = np.array([lo[0] + 0.01 * (hi[0] - lo[0]) + 0.01, 0.5 * (lo[1] + hi[1]), lo[2] + 0.37 * (hi[2] - lo[2])], np.float32)
+    total_accepted = 0
+    for x in (np.asarray(sc.recorders[0].position, np.float32), near_wall):
+        p, _ = common.make_segments_to_point(sc, 1200, x, seed=int(res))
+        bad, accepted, listed = em.vismap_violations(x, res, p)
+        assert bad == 0, f"{bad} accepted triangles missing from their texel list"
+        assert listed >= accepted
+        total_accepted += accepted
+    assert total_accepted > 50      # the check saw real occluders
+
+
 def test_bvh_margins_are_load_bearing(oracle_lib):
     """With pad and slack switched off the edge-aimed rays DO lose their reference winner: the
     adversarial set exercises exactly what the margins are there for."""
