@@ -1242,8 +1242,12 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(d_range, (int)n_tracks);
 	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = d_counters;
 	lap("upload + histogram alloc");
-	cudaEvent_t e0, e1;
-	CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+	struct Events {   // destroyed on every return path
+		cudaEvent_t a = nullptr, b = nullptr;
+		~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+	} ev;
+	CUDA_TRY(cudaEventCreate(&ev.a)); CUDA_TRY(cudaEventCreate(&ev.b));
+	cudaEvent_t e0 = ev.a, e1 = ev.b;
 	CUDA_TRY(cudaEventRecord(e0, s->stream));
 	if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
 	CUDA_TRY(cudaEventRecord(e1, s->stream));
@@ -1256,11 +1260,15 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	float ms = 0.0f;
 	CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
-	cudaEventDestroy(e0); cudaEventDestroy(e1);
 
-	ear_b200_result* res = (ear_b200_result*)calloc(1, sizeof(ear_b200_result));
+	// the result is the caller's once it is handed out; until then every error path frees it
+	std::unique_ptr<ear_b200_result, void (*)(ear_b200_result*)> holder((ear_b200_result*)calloc(1, sizeof(ear_b200_result)),
+	                                                                    ear_b200_result_free);
+	ear_b200_result* res = holder.get();
+	if (!res) return fail("render: out of host memory");
 	res->n_contexts = n_ctx; res->n_recorders = n_rec;
 	res->tracks = (ear_b200_track*)calloc(n_tracks, sizeof(ear_b200_track));
+	if (!res->tracks) return fail("render: out of host memory");
 	for (size_t k = 0; k < n_tracks; ++k) {
 		ear_b200_track& tr = res->tracks[k];
 		const bool used = !(k & 1) || rec[k / 2].kind == EAR_B200_STEREO;
@@ -1276,7 +1284,7 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
 	res->contributions = counters[3]; res->bin_updates = counters[4]; res->dropped_updates = counters[5];
 	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;
-	*out = res;
+	*out = holder.release();
 	return 0;
 }
 
