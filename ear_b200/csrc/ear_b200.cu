@@ -443,6 +443,7 @@ struct ear_b200_scene {
 	                                // 16 Mi 1.55e9, 32 Mi 1.56e9, 64 Mi 1.55e9 seg/s (bigger launches amortise the persistent
 	                                // kernels' tails and sort better, but the shade kernel walks every slot)
 	bool slots_forced = false;
+	int pool_generations = 0;       // 0: choose from the bounce cap; k: pool = work / k slots (EAR_B200_GENERATIONS)
 	int check_every = 8;            // iterations between host checks for completion
 	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
 	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
@@ -546,6 +547,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
+	if (const char* pg = std::getenv("EAR_B200_GENERATIONS")) s->pool_generations = std::max(0, std::atoi(pg));
 	if (const char* rk = std::getenv("EAR_B200_RAY_KEY")) s->ray_key = std::max(0, std::min(4, std::atoi(rk)));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
@@ -1020,10 +1022,14 @@ static int32_t prepare_vismaps(ear_b200_scene* s, int n_ctx, int n_rec, cudaStre
 static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
 	if (p.n_rec > 255) return fail("render: more than 255 recorders per context are not supported");
 	if (p.n_ctx > 65535) return fail("render: more than 65535 contexts per call are not supported");
-	// pool size: large launches amortise the persistent kernels' tails (8 Mi slots: +4 % over 4 Mi), but every slot
-	// should host several rays in turn or the run ends in a long half-empty decay: a quarter of the shard's rays
+	// pool size: large launches amortise the persistent kernels' tails and the ~9 launches of an iteration (8 Mi slots:
+	// +4 % over 4 Mi, 16 Mi: +3 % more).  With a short bounce cap nearly every ray lives for exactly max_bounces
+	// iterations, the pool turns over in lockstep and one generation is best (8 GPUs x 1.25e7 work items each ran
+	// 200 iterations of 3.1 M rays under the old work/4 rule and were 10 % slower per segment than one GPU).  With
+	// long paths rays die at random times; the shade kernel walks every slot, so several generations keep it full.
 	long long slots = std::min<long long>(std::max<long long>(p.total_work, 1), s->max_slots);
-	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / 4));
+	const long long generations = (s->pool_generations > 0) ? s->pool_generations : (p.max_bounces <= 100 ? 1 : 4);
+	if (!s->slots_forced) slots = std::min<long long>(slots, std::max<long long>(1 << 18, p.total_work / generations));
 	// a query word holds slot | recorder << slot_bits
 	int rec_bits = 0;
 	while ((1 << rec_bits) < p.n_rec) ++rec_bits;
