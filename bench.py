@@ -9,8 +9,11 @@ rank g traces ray ids [g*R/N, (g+1)*R/N) of every context into its own partial h
 NCCL reduce (sum) of the histograms (+ min/max of the track ranges) to rank 0, which finalises.
 
   value : segments / second, whole job, scene + contexts already resident in HBM
-  e2e   : same metric through the C ABI with host buffers: ear_b200_scene_create (triangle upload +
-          BVH build) + ear_b200_render (context upload, trace, finalise, track download) every step
+  e2e   : same metric through the public API with host buffers, every step: sharding.create_replicated_scene
+          (triangle upload + BVH build on rank 0, scene image broadcast) + sharding.render_sharded (context upload,
+          visibility maps, trace, one reduce, finalise, track download); at N=1 that is ear_b200_scene_create +
+          ear_b200_render
+  roofline : closest-hit traversal kernel; traffic from the committed ncu capture (profiles/r1_traffic.json)
   --impl reference : the reference's own CPU render (oracle/_ref/ref_harness, built from the
           unmodified sources) on this host's cores, one 50-ray context per process
           (50 is the reference's minimum: DrawProgressBar divides by samples/50).
