@@ -501,8 +501,8 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 
 	// Collapse to 4-wide nodes laid out depth-first with siblings adjacent: a node's inner children take
 	// consecutive numbers, then follow the descendants of its last inner child, of the one before it, ...
-	// Pass 1 (serial, children have larger build ids than their parent) counts the wide descendants of every
-	// inner build node; with those known, pass 2 numbers, quantises and writes each subtree independently.
+	// Pass 1 counts the wide descendants of every node that becomes a wide node (recursive, big subtrees as pool
+	// tasks); with those known, pass 2 numbers, quantises and writes each subtree independently.
 	out.nodes.clear();
 	out.depth = 0;
 	const BuildNode* root_node = &b.nodes[root];
@@ -537,17 +537,34 @@ void build_bvh(const float* verts, const int32_t* tri_material, int32_t n, Bvh& 
 		return n_kids;
 	};
 	const int32_t n_build = b.next_node.load();
-	RawVector<int32_t> desc((size_t)n_build);
-	for (int32_t id = n_build - 1; id >= 0; --id) {
+	RawVector<int32_t> desc((size_t)n_build);   // written for the nodes that become wide nodes only
+	std::function<int32_t(int32_t)> count_desc = [&](int32_t id) -> int32_t {
 		const BuildNode& bn = b.nodes[id];
-		int32_t d = 0;
-		if (bn.left >= 0) {
-			int32_t kid[4];
-			const int n_kids = expand(bn, kid);
-			for (int k = 0; k < n_kids; ++k) if (b.nodes[kid[k]].left >= 0) d += 1 + desc[(size_t)kid[k]];
+		int32_t kid[4];
+		const int n_kids = expand(bn, kid);
+		int32_t part[4] = {0, 0, 0, 0};
+		if (bn.count >= Builder::kTaskThreshold) {
+			// big subtree: the inner children are counted as separate tasks; this thread helps until they are done
+			std::atomic<int> left{0};
+			int last = -1;
+			for (int k = 0; k < n_kids; ++k) if (b.nodes[kid[k]].left >= 0) last = k;
+			for (int k = 0; k < n_kids; ++k) {
+				if (b.nodes[kid[k]].left < 0 || k == last) continue;
+				left.fetch_add(1);
+				const int32_t c_id = kid[k];
+				int32_t* slot = &part[k];
+				pool.submit([&count_desc, &left, c_id, slot] { *slot = 1 + count_desc(c_id); left.fetch_sub(1); });
+			}
+			if (last >= 0) part[last] = 1 + count_desc(kid[last]);
+			pool.help_until([&left] { return left.load() == 0; });
+		} else {
+			for (int k = 0; k < n_kids; ++k) if (b.nodes[kid[k]].left >= 0) part[k] = 1 + count_desc(kid[k]);
 		}
+		const int32_t d = part[0] + part[1] + part[2] + part[3];
 		desc[(size_t)id] = d;
-	}
+		return d;
+	};
+	count_desc(root);
 	out.nodes.resize((size_t)desc[(size_t)root] + 1);
 	std::atomic<int> max_depth{0};
 	std::function<void(int32_t, int32_t, int32_t, int)> emit = [&](int32_t id, int32_t out_id, int32_t block, int depth) {
