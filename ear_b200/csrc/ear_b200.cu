@@ -1055,15 +1055,16 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	pl.n_slots = (int)slots;
 	pl.slot_bits = slot_bits;
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
-	WfPool pl_fb = pl;   // the map fallback list, traced by the BVH any-hit kernel
-	pl_fb.q_list = s->d_q_bvh; pl_fb.q_count_idx = 5; pl_fb.q_cursor_idx = 6;
 	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
 	if ((size_t)p.n_ctx > s->log2af_cap) {
 		cudaFree(s->pool.ctx_log2af);
+		s->pool.ctx_log2af = nullptr; s->log2af_cap = 0;
 		CUDA_TRY(cudaMalloc(&s->pool.ctx_log2af, sizeof(double) * p.n_ctx));
 		s->log2af_cap = p.n_ctx;
 		pl.ctx_log2af = s->pool.ctx_log2af;
 	}
+	WfPool pl_fb = pl;   // the map fallback list, traced by the BVH any-hit kernel
+	pl_fb.q_list = s->d_q_bvh; pl_fb.q_count_idx = 5; pl_fb.q_cursor_idx = 6;
 	wf_ctx_table_kernel<<<(p.n_ctx + 127) / 128, 128, 0, stream>>>(pl, p);
 	void (*closest)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<false, true> : wf_traverse_kernel<false, false>;
 	void (*anyhit)(SceneDev, WfPool, RenderParams) = s->dev.exact ? wf_traverse_kernel<true, true> : wf_traverse_kernel<true, false>;
