@@ -133,6 +133,22 @@ def test_visibility_map_lists_are_supersets_on_host(oracle_lib, name, res):
     assert total_accepted > 50      # the check saw real occluders
 
 
+def test_oracle_honours_stream_id(oracle_lib):
+    """ear_b200_context.stream_id pins the context word of the Philox key (the CLI uses it when it deals contexts to
+    several GPUs): context k rendered alone with stream_id = k + 1 gives the track it has inside the full call."""
+    sc = common.named_scene("example1")
+    sc.samples = 2000
+    cpu = ob.OracleScene.from_def(sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    full, _ = cpu.render(ctxs, recs, max_bounces=30, seed=4)
+    ctxs[1].stream_id = 2
+    alone, _ = cpu.render([ctxs[1]], [recs[1]], max_bounces=30, seed=4)
+    assert np.array_equal(alone[0][0][0].data, full[1][0][0].data)
+    ctxs[1].stream_id = 0
+    other, _ = cpu.render([ctxs[1]], [recs[1]], max_bounces=30, seed=4)
+    assert not np.array_equal(other[0][0][0].data, full[1][0][0].data)
+
+
 def test_bvh_margins_are_load_bearing(oracle_lib):
     """With pad and slack switched off the edge-aimed rays DO lose their reference winner: the
     adversarial set exercises exactly what the margins are there for."""
