@@ -19,6 +19,11 @@
  * results are owned by the library until ear_b200_result_free().  There is no CPU fallback:
  * without a CUDA device every compute entry point fails.
  *
+ * Threading: a scene holds per-scene scratch (ray pool, visibility maps, launch statistics), so calls on ONE scene
+ * must not overlap; different scenes (e.g. one per GPU, as the CLI does) may be driven from different host threads.
+ * ear_b200_last_error() is per host thread.  Tuning knobs (EAR_B200_* environment variables, README.md) are read
+ * when a scene is created.
+ *
  * All arithmetic is IEEE float32 with the reference's operation order (no FMA contraction
  * on the geometry path); indices are int32.  Triangle index == position in `verts`, which
  * must be the concatenation of the scene's MESH blocks in file order (src/Scene.cpp:103-106).
@@ -32,7 +37,7 @@
 extern "C" {
 #endif
 
-#define EAR_B200_ABI_VERSION 1
+#define EAR_B200_ABI_VERSION 2        /* 2: ear_b200_context.stream_id, scene images, device post chain */
 #define EAR_B200_MAX_BANDS 8          /* the .ear format carries 3; up to 8 through the ABI */
 #define EAR_B200_SAMPLE_RATE 44100    /* src/Recorder.h:35 */
 #define EAR_B200_MONO 1               /* OUT1, MonoRecorder  (src/MonoRecorder.cpp:83-97)   */

@@ -57,7 +57,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == sorted(api.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ear_b200_abi_version() == 1
+    assert lib.ear_b200_abi_version() == 2
     assert ctypes.sizeof(api.ContextC) == 40 and ctypes.sizeof(api.RecorderC) == 64 and ctypes.sizeof(api.OptionsC) == 40
 
 
