@@ -54,6 +54,11 @@ class EmulScene:
         self.l.emul_first_hit(self.h, o.ctypes.data, d.ctypes.data, o.shape[0], idx.ctypes.data, t.ctypes.data)
         return idx, t
 
+    def layout_hash(self) -> int:
+        self.l.emul_hash.restype = C.c_uint64
+        self.l.emul_hash.argtypes = [C.c_void_p]
+        return int(self.l.emul_hash(self.h))
+
     def vismap_violations(self, x, res, points):
         """(violations, accepted, listed) of the visibility-map superset check for recorder position x."""
         x = np.ascontiguousarray(x, np.float32).reshape(3)

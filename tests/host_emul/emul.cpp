@@ -25,6 +25,16 @@ void emul_set_exact(void* h, int32_t exact) { ((Emul*)h)->dev.exact = exact; }
 void emul_stats(void* h, int32_t* n_nodes, int32_t* depth, double* build_ms) {
 	Emul* e = (Emul*)h; *n_nodes = (int32_t)e->bvh.nodes.size(); *depth = e->bvh.depth; *build_ms = e->build_ms;
 }
+// FNV-1a over the node and triangle-record arrays: the layout the GPU would be handed
+uint64_t emul_hash(void* h) {
+	Emul* e = (Emul*)h;
+	uint64_t x = 1469598103934665603ull;
+	const unsigned char* p = (const unsigned char*)e->bvh.nodes.data();
+	for (size_t i = 0; i < e->bvh.nodes.size() * sizeof(Node); ++i) { x ^= p[i]; x *= 1099511628211ull; }
+	p = (const unsigned char*)e->bvh.tris.data();
+	for (size_t i = 0; i < e->bvh.tris.size() * sizeof(TriRecord); ++i) { x ^= p[i]; x *= 1099511628211ull; }
+	return x;
+}
 void emul_first_hit(void* h, const float* o, const float* d, int64_t n, int32_t* idx, float* t) {
 	Emul* e = (Emul*)h;
 	for (int64_t i = 0; i < n; ++i) {

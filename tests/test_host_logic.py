@@ -149,6 +149,18 @@ def test_oracle_honours_stream_id(oracle_lib):
     assert not np.array_equal(other[0][0][0].data, full[1][0][0].data)
 
 
+def test_bvh_build_does_not_depend_on_the_thread_count(oracle_lib, monkeypatch):
+    """The builder forks subtrees over a worker pool and chunks its passes over big nodes; the node and triangle-record
+    arrays must come out byte-identical whatever the number of threads (one rank builds, the others adopt its image)."""
+    sc, _ = scenes.synthetic_hall(n_tris=300000, n_obstacles=500, n_bands=3)
+    tris = sc.triangles()
+    hashes = []
+    for threads in ("1", "3", "8"):
+        monkeypatch.setenv("EAR_B200_BUILD_THREADS", threads)
+        hashes.append(eb.EmulScene(tris).layout_hash())
+    assert hashes[0] == hashes[1] == hashes[2]
+
+
 def test_bvh_margins_are_load_bearing(oracle_lib):
     """With pad and slack switched off the edge-aimed rays DO lose their reference winner: the
     adversarial set exercises exactly what the margins are there for."""
