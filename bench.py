@@ -342,13 +342,16 @@ def run_reference(args):
     if rank != 0:
         return
     sc, table, ctxs, recs = build_workload()
+    # each sample is a time-boxed run of the reference; the whole arm stays within ~3 minutes whatever --steps is
+    samples = args.steps + min(args.warmup, 1)
+    budget = max(4, min(20, int(160 / max(1, samples))))
     for _ in range(min(args.warmup, 1)):
-        reference_sample(sc, procs=max(1, (os.cpu_count() or 1)))
+        reference_sample(sc, procs=max(1, (os.cpu_count() or 1)), budget=budget)
     t0 = time.perf_counter()
     seg = secs = 0.0
     last = None
     for _ in range(args.steps):
-        last = reference_sample(sc)
+        last = reference_sample(sc, budget=budget)
         seg += last["segments"]
         secs += last["render_seconds"]
     wall = time.perf_counter() - t0
