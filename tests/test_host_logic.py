@@ -70,6 +70,38 @@ def test_no_gpu_means_loud_failure_not_fallback():
         api.Scene.from_def(sc)
 
 
+def test_cli_survives_corrupt_ear_files(tmp_path):
+    """Truncated files, flipped bytes, wild lengths: the bounds-checked reader must turn every one of them into the
+    reference's "Error: <what>" line (src/EAR.cpp:404-408) and a normal exit -- never a crash.  (Files that still
+    parse end at "no CUDA device" here, which is an Error line too.)"""
+    exe = os.path.join(ROOT, "ear_b200", "csrc", "EAR")
+    wav = scenes.write_click_wav(str(tmp_path / "click.wav"))
+    sc = scenes.example1_scene(samples=1000, wav=wav)
+    good = str(tmp_path / "good.ear")
+    sc.write(good)
+    data = open(good, "rb").read()
+    rng = np.random.default_rng(0)
+    seen = set()
+    for k in range(60):
+        d = bytearray(data)
+        if k % 3 == 0:
+            d = d[: int(rng.integers(4, len(d)))]
+        elif k % 3 == 1:
+            for _ in range(int(rng.integers(1, 8))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+        else:
+            i = int(rng.integers(0, len(d) - 8))
+            d[i: i + 4] = int(rng.integers(0, 2 ** 31)).to_bytes(4, "little")
+        bad = str(tmp_path / "bad.ear")
+        open(bad, "wb").write(bytes(d))
+        r = subprocess.run([exe, "calc", "T60", bad], capture_output=True, timeout=60)
+        out = r.stdout.decode("utf8", "replace")
+        assert r.returncode in (0, 1), (k, r.returncode)
+        assert "Error:" in out, (k, out[-300:])
+        seen.add(out.split("Error:")[1].strip().split("\n")[0][:12])
+    assert len(seen) >= 4      # several different diagnoses, not one catch-all
+
+
 def test_product_never_imports_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "ear_b200")):
         for f in files:
