@@ -33,11 +33,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_TRIS = int(os.environ.get("EAR_BENCH_TRIS", 1_000_000))
-N_BANDS = 8
-TOTAL_RAYS = int(float(os.environ.get("EAR_BENCH_RAYS", 1e8)))
 MAX_BOUNCES = 50
-WORKLOAD = f"synthetic {N_TRIS}-triangle hall, {N_BANDS} bands, {TOTAL_RAYS:.0e} rays, {MAX_BOUNCES} bounces, 1 mono recorder"
+# workload -> (triangles, bands, rays, recorders); C4 is the headline (BASELINE.json configs[3]), C5 = configs[4]
+WORKLOADS = {"c4": (1_000_000, 8, 1e8, 1), "c5": (10_000_000, 3, 1e9, 64)}
+N_TRIS, N_BANDS, TOTAL_RAYS, N_RECORDERS, WORKLOAD, WORKLOAD_KEY = 0, 0, 0, 0, "", "c4"
+
+
+def select_workload(key, rays=None, tris=None):
+    global N_TRIS, N_BANDS, TOTAL_RAYS, N_RECORDERS, WORKLOAD, WORKLOAD_KEY
+    t, b, r, n = WORKLOADS[key]
+    WORKLOAD_KEY = key
+    N_TRIS = int(float(tris if tris is not None else os.environ.get("EAR_BENCH_TRIS", t)))
+    N_BANDS, N_RECORDERS = b, n
+    TOTAL_RAYS = int(float(rays if rays is not None else os.environ.get("EAR_BENCH_RAYS", r)))
+    what = "hall" if key == "c4" else "complex of 8 coupled halls"
+    WORKLOAD = (f"synthetic {N_TRIS}-triangle {what}, {N_BANDS} bands, {TOTAL_RAYS:.0e} rays, {MAX_BOUNCES} bounces, "
+                f"{N_RECORDERS} mono recorder{'s' if N_RECORDERS > 1 else ''}")
+    if TOTAL_RAYS != int(r) or N_TRIS != t:
+        WORKLOAD += f" [REDUCED from the named {t} triangles / {r:.0e} rays]"
 
 
 def algorithmic_bytes(n_tris, segments, occlusion, bin_updates):
@@ -91,11 +104,15 @@ class ClockSampler(threading.Thread):
 def build_workload():
     import numpy as np
     from ear_b200 import api, scenes
-    sc, table = scenes.synthetic_hall(n_tris=N_TRIS, n_obstacles=max(1, N_TRIS // 500), n_bands=N_BANDS, seed=0)
+    if WORKLOAD_KEY == "c5":
+        sc, table = scenes.synthetic_complex(n_tris=N_TRIS, n_obstacles=max(8, N_TRIS // 500), n_bands=N_BANDS, seed=0,
+                                             n_recorders=N_RECORDERS)
+    else:
+        sc, table = scenes.synthetic_hall(n_tris=N_TRIS, n_obstacles=max(1, N_TRIS // 500), n_bands=N_BANDS, seed=0)
     af = scenes.air_factors(N_BANDS)
     rays_per_ctx = TOTAL_RAYS // N_BANDS
     ctxs = [api.Context(b, rays_per_ctx, float(af[b]), sc.sources[0].position, 1.0, 1.0) for b in range(N_BANDS)]
-    recs = [api.Recorder(sc.recorders[0].position)]
+    recs = [api.Recorder(r.position) for r in sc.recorders[:N_RECORDERS]]
     return sc, np.ascontiguousarray(table, np.float32), ctxs, recs
 
 
@@ -131,7 +148,7 @@ def run_ours(args):
     lo, hi = shard_bounds(rays_per_ctx, rank, world)
     opt = api.make_options(max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo, finalise=False)
     n_bins = scene.default_bins(opt)
-    n_tracks = n_ctx * n_rec * 2
+    n_tracks = n_ctx * n_rec * api.tracks_per_recorder(rec_c)
     hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
     rng_first = torch.empty((n_tracks,), dtype=torch.int32, device=dev)
     rng_real = torch.empty((n_tracks,), dtype=torch.int32, device=dev)
@@ -187,9 +204,6 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     st = scene.stats()
     n_launch = sum(st["launches"].values())
-    # dominant kernel of the step: the closest-hit traversal (wf_traverse_kernel<false>), this rank's launches
-    trav_ms = st["ms"]["closest"] + st["ms"]["fused"]
-    trav_launches = st["launches"]["closest"] + st["launches"]["fused"]
     total_ms = float(ms.item())
     segments, occl, bins, dropped = (int(x) for x in tot.tolist())
     value = segments / (total_ms * 1e-3)
@@ -200,7 +214,7 @@ def run_ours(args):
     h2d = verts.nbytes + tri_mat.nbytes + table.nbytes + C.sizeof(ctx_c) + C.sizeof(rec_c)
     d2h = 0
     e2e_segments = 0
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 2))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
     from ear_b200.sharding import create_replicated_scene, render_sharded
     for _ in range(e2e_steps):
         barrier()
@@ -242,18 +256,29 @@ def run_ours(args):
             cpu_base = {"error": str(exc)[:200]}
     if rank == 0:
         peak, which = measured_peak()
-        # dominant kernel = the BVH traversal kernels (closest-hit + any-hit launches of this rank).  Algorithmic
-        # bytes they move: Q(T) per query + 32 B ray in / 8 B hit out per query; duration: CUDA events
-        # recorded by the library around every launch on the launch stream, summed over the timed region.
+        # Dominant kernel class of the step and its SURVEY 8(d) per-unit bytes: C4 -- the closest-hit traversal, Q(T) per
+        # segment; C5 -- the occlusion queries (visibility-map lookups + BVH any-hit fallback), Q(T) per query.
+        # Duration: CUDA events recorded by the library around every launch on the launch stream, summed over the
+        # timed region (this rank's launches).
         depth = math.ceil(math.log2(max(2, math.ceil(N_TRIS / 4))))
-        q_bytes = 32 * depth + 192 + 40
-        trav_bytes = q_bytes * segments / world                      # all closest-hit launches of one rank
-        achieved = trav_bytes / (trav_ms * 1e-3) / 1e9
-        traffic = None
-        try:   # DRAM bytes of one steady-state launch from the committed ncu --set full capture (never measured here)
-            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)
-            traffic = int(tj["dram_bytes_read_per_launch"]) + int(tj["dram_bytes_write_per_launch"])
+        q_bytes = 32 * depth + 192
+        if WORKLOAD_KEY == "c5":
+            dom, dom_name, units = "anyhit", "wf_vismap_kernel + wf_traverse_kernel<true> (occlusion queries)", occl / world
+        else:
+            dom, dom_name, units = "closest", "wf_traverse_kernel<false> (closest hit)", segments / world
+        dom_ms = st["ms"][dom]
+        dom_launches = st["launches"]["closest"]      # one launch of every class per iteration
+        dom_bytes = q_bytes * units
+        achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        # DRAM bytes and issue statistics of ONE mid-step launch of that kernel on this configuration, from the committed
+        # ncu --set full capture (scripts/capture_traffic.sh writes the entry; never measured inside a bench run)
+        traffic, ncu_info = None, None
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                tj = json.load(f).get(f"{WORKLOAD_KEY}_n{world}")
+            if tj:
+                traffic = int(tj["dram_bytes_read"]) + int(tj["dram_bytes_write"])
+                ncu_info = {k: tj[k] for k in tj if k not in ("dram_bytes_read", "dram_bytes_write")}
         except Exception:
             traffic = None
         whole = algorithmic_bytes(N_TRIS, segments / world, occl / world, bins / world) / (total_ms * 1e-3) / 1e9
@@ -262,25 +287,29 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
-                       "max_bounces": MAX_BOUNCES, "recorders": 1, "bins_per_track": n_bins,
+                       "max_bounces": MAX_BOUNCES, "recorders": N_RECORDERS, "bins_per_track": n_bins,
                        "sharding": f"ray ranges over {world} GPU(s), one NCCL reduce",
                        "l2": "flushed by a 256 MiB memset before every step"},
             "segments_per_step": segments // args.steps, "occlusion_queries_per_step": occl // args.steps,
             "bin_updates_per_step": bins // args.steps, "dropped_updates": dropped,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "includes": "scene upload + BVH build (rank 0) + image broadcast + trace + reduce + finalise + track download",
+                    "includes": "scene upload + BVH build + image broadcast + visibility maps + trace + reduce + finalise + track download",
+                    "steps": e2e_steps,
                     "ms_per_step": sum(e2e_ms) / max(1, len(e2e_ms)), "scene_create_ms": sum(e2e_create_ms) / max(1, len(e2e_create_ms))},
             "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
             "launches_per_step": {k: v / args.steps for k, v in st["launches"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum, profiles/r1_traffic.json)",
-                         "algorithmic_bytes_per_launch": trav_bytes / max(1, trav_launches),
-                         "kernel": "wf_traverse_kernel<false> (closest hit)",
-                         "kernel_ms": trav_ms / max(1, trav_launches), "kernel_launches": trav_launches,
+                         "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum of one "
+                                                             "mid-step launch on this configuration, profiles/r2_traffic.json)",
+                         "ncu": ncu_info,
+                         "algorithmic_bytes_per_launch": dom_bytes / max(1, dom_launches),
+                         "kernel": dom_name,
+                         "kernel_ms": dom_ms / max(1, dom_launches), "kernel_launches": dom_launches,
+                         "kernel_share_of_step": dom_ms / total_ms,
                          "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                          "peak_source": which,
-                         "bytes_model": "closest-hit launches: (32*ceil(log2(ceil(T/4)))+192 + 40)*S; whole step: "
-                                        "64*S + (32*ceil(log2(ceil(T/4)))+192)*(S+O) + 8*U (SURVEY 8d)"},
+                         "bytes_model": "dominant kernel: (32*ceil(log2(ceil(T/4)))+192) B per query it answers (SURVEY 8d Q(T)); "
+                                        "whole step: 64*S + Q(T)*(S+O) + 8*U"},
             "cpu_baseline": cpu_base, "clocks": clocks,
         }
         print(json.dumps(line))
@@ -360,7 +389,7 @@ def run_reference(args):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
-                       "max_bounces": MAX_BOUNCES, "recorders": 1},
+                       "max_bounces": MAX_BOUNCES, "recorders": N_RECORDERS},
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": "segments/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -372,9 +401,13 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c4", choices=sorted(WORKLOADS), help="c4 (headline, default) or c5")
+    ap.add_argument("--rays", default=None, help="override the workload's ray budget (the line then says REDUCED)")
+    ap.add_argument("--tris", default=None, help="override the workload's triangle count (the line then says REDUCED)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
+    select_workload(args.workload, args.rays, args.tris)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -22,6 +22,7 @@ import numpy as np
 MAX_BANDS = 8
 SAMPLE_RATE = 44100
 MONO, STEREO = 1, 2
+POINT_SOURCE, MESH_SOURCE = 0, 1
 FIRST_SAMPLE_INIT = 3 * SAMPLE_RATE - 1   # FloatBuffer ctor, src/Recorder.cpp:43-48
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -36,7 +37,8 @@ class RecorderC(C.Structure):
 class ContextC(C.Structure):
     _fields_ = [("band", C.c_int32), ("stream_id", C.c_int32), ("num_samples", C.c_int64),
                 ("absorption_factor", C.c_float), ("dry_level", C.c_float), ("gain", C.c_float),
-                ("source_position", C.c_float * 3)]
+                ("source_position", C.c_float * 3), ("source_kind", C.c_int32), ("emitter_first", C.c_int32),
+                ("emitter_count", C.c_int32), ("reserved", C.c_int32)]
 
 
 class OptionsC(C.Structure):
@@ -69,7 +71,8 @@ EXPORTS = [
     "ear_b200_render", "ear_b200_result_free", "ear_b200_trace_device", "ear_b200_finalise_device",
     "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset", "ear_b200_convolve",
     "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
-    "ear_b200_post_power_device", "ear_b200_post_truncate_device",
+    "ear_b200_post_power_device", "ear_b200_post_truncate_device", "ear_b200_tracks_per_recorder",
+    "ear_b200_scene_set_emitters",
 ]
 
 _lib = None
@@ -109,6 +112,9 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
                                           C.POINTER(OptionsC), i32, vp, vp, vp, vp]
     lib.ear_b200_finalise_device.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(RecorderC), i32, i32, vp, vp, vp]
     lib.ear_b200_default_bins.argtypes = [vp, C.POINTER(OptionsC)]
+    lib.ear_b200_tracks_per_recorder.argtypes = [C.POINTER(RecorderC), i32]
+    lib.ear_b200_tracks_per_recorder.restype = i32
+    lib.ear_b200_scene_set_emitters.argtypes = [vp, vp, i32]
     lib.ear_b200_scene_stats.argtypes = [vp, C.POINTER(StatsC)]
     lib.ear_b200_scene_stats_reset.argtypes = [vp]
     lib.ear_b200_scene_stats_reset.restype = None
@@ -138,6 +144,7 @@ class Context:
     dry_level: float = 1.0
     gain: float = 1.0
     stream_id: int = 0      # 0: position in the call keys the random streams; k > 0: key k - 1 (see include/ear_b200.h)
+    emitter: Optional[Sequence[int]] = None   # mesh source: (first, count) into the scene's emitter-triangle table
 
     def to_c(self) -> ContextC:
         c = ContextC()
@@ -146,6 +153,8 @@ class Context:
         c.absorption_factor = float(np.float32(self.absorption_factor))
         c.dry_level, c.gain = float(self.dry_level), float(self.gain)
         c.source_position[:] = [float(x) for x in self.source_position]
+        if self.emitter is not None:
+            c.source_kind, c.emitter_first, c.emitter_count = MESH_SOURCE, int(self.emitter[0]), int(self.emitter[1])
         return c
 
 
@@ -187,6 +196,11 @@ def make_options(max_bounces=1000, n_bins=0, seed=1, first_ray=0, ray_count=-1, 
     o.max_bounces, o.n_bins, o.seed = int(max_bounces), int(n_bins), int(seed)
     o.first_ray, o.ray_count, o.finalise = int(first_ray), int(ray_count), 1 if finalise else 0
     return o
+
+
+def tracks_per_recorder(rec_c) -> int:
+    """Tracks each recorder owns in the device buffers of a call (2 if any recorder of the call is stereo, else 1)."""
+    return 2 if any(r.kind == STEREO for r in rec_c) else 1
 
 
 def pack_contexts(contexts: Sequence[Context]):
@@ -298,6 +312,11 @@ class Scene:
     def image_write(self, dst_ptr: int, dst_bytes: int) -> None:
         """Copies the scene image into device memory at dst_ptr (e.g. a torch uint8 tensor's data_ptr())."""
         _check(self.lib, self.lib.ear_b200_scene_image_write(self.handle, C.c_void_p(dst_ptr), dst_bytes))
+
+    def set_emitters(self, verts: np.ndarray) -> None:
+        """Emitter triangles of the scene's mesh sources, all of them concatenated ([n][3][3])."""
+        v = np.ascontiguousarray(verts, np.float32).reshape(-1, 3, 3)
+        _check(self.lib, self.lib.ear_b200_scene_set_emitters(self.handle, v.ctypes.data, v.shape[0]))
 
     def close(self):
         if getattr(self, "handle", None):

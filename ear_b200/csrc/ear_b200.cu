@@ -2,11 +2,11 @@
 //
 // Replaces the reference's Scene::Render bounce loop (src/Scene.cpp:111-318) and what it calls.
 // Kernels (names follow SURVEY.md section 2.3):
-//   K1 emission + K2 closest hit + K3 material/resample + K4 occlusion + K5 weight/splat + K6 ray
-//   refill live in ONE persistent kernel (`render_kernel`): a ray's state never leaves registers
-//   between bounces, so the per-segment HBM traffic is BVH nodes, triangle records and histogram
-//   atomics only.  K7 (`scale_kernel`, `direct_kernel`) finalises tracks.  H1 harness kernels
-//   (`first_hit_kernel`, `occluded_kernel`, `paths_kernel`) expose K2/K4/K1-K3 for parity tests.
+//   K1 emission + K3 material/resample + K6 refill/compaction (`wf_shade_kernel`), K2 closest hit and K4 any hit
+//   (`wf_traverse_kernel`, `wf_vismap_kernel`), K5 weight/splat (`wf_splat_kernel`) form the wavefront engine
+//   (wavefront.cuh); K0 builds the BVH on the device (bvh_device.cuh); K7 (`scale_kernel`, `direct_kernel`)
+//   finalises tracks.  The harness entry points (first_hit, occluded, trace_paths) run the production kernels
+//   over explicit rays / segments / ray ids.
 // There is no CPU fallback anywhere in this file.
 #include <cuda_runtime.h>
 
@@ -59,11 +59,12 @@ struct RenderParams {
 	const ear_b200_recorder* rec;    // [n_ctx][n_rec]
 	const long long* work_prefix;    // [n_ctx + 1] rays of this shard, prefix-summed over contexts
 	int32_t n_ctx, n_rec, max_bounces, n_bins;
+	int32_t tpr;                     // tracks per recorder in hist / range: 2 when the call has a stereo recorder, else 1
 	unsigned long long seed;
 	long long first_ray;
 	long long total_work;
-	float* hist;                     // [n_ctx][n_rec][2][n_bins]
-	uint32_t* range;                 // [n_ctx][n_rec][2][2] {first_sample, real_length}
+	float* hist;                     // [n_ctx][n_rec][tpr][n_bins]
+	uint32_t* range;                 // [n_ctx][n_rec][tpr][2] {first_sample, real_length}
 	unsigned long long* counters;    // [8]
 	unsigned long long* next_work;   // work-queue head
 	int32_t* hits;                   // parity harness: [rays][max_bounces] triangle hit per bounce (or null)
@@ -90,27 +91,52 @@ __device__ __forceinline__ void touch_range(uint32_t* range, int lo, int hi) {
 	if ((uint32_t)hi > cur_real) atomicMax(range + 1, (uint32_t)hi);
 }
 
+// Where Record() adds its samples.  GlobalSink: straight into the HBM/L2-resident histogram (one RED.ADD.F32 per bin).
+// WindowSink (wf_splat_window_kernel): into a per-block shared-memory copy of a time window of the recorder's tracks,
+// flushed once per block; samples outside the window fall through to the global histogram.
+struct GlobalSink {
+	float* tracks;      // [tpr][n_bins] of this (context, recorder)
+	uint32_t* range;    // [tpr][2]
+	int n_bins;
+	__device__ __forceinline__ void add(int k, int idx, float v) { atomicAdd(tracks + (size_t)k * n_bins + idx, v); }
+	__device__ __forceinline__ void touched(int k, int lo, int hi) { touch_range(range + 2 * k, lo, hi); }
+};
+struct WindowSink {
+	float* tracks;
+	int n_bins;
+	float* win;         // shared memory: [tracks of the recorder][width]
+	int lo, width;      // the window covers bins [lo, lo + width) of each track
+	int t_lo[2], t_hi[2];   // bins this thread touched, per track (merged per block at the flush)
+	__device__ __forceinline__ void add(int k, int idx, float v) {
+		const unsigned rel = (unsigned)(idx - lo);
+		if (rel < (unsigned)width) atomicAdd(win + k * width + (int)rel, v);
+		else atomicAdd(tracks + (size_t)k * n_bins + idx, v);
+	}
+	__device__ __forceinline__ void touched(int k, int lo_bin, int hi_bin) { t_lo[k] = min(t_lo[k], lo_bin); t_hi[k] = max(t_hi[k], hi_bin); }
+};
+
 // One linearly decaying ramp of `w` bins starting at bin `s` (the USE_FILTER splat shared by
 // MonoRecorder::Record, src/MonoRecorder.cpp:83-97, and StereoRecorder::Record, :120-129).
-__device__ __forceinline__ void splat_ramp(float* track, uint32_t* range, int n_bins, int s, int w, float ampl,
-                                           float step, LocalCounters& lc) {
+template <class Sink>
+__device__ __forceinline__ void splat_ramp(Sink& sink, int k, int n_bins, int s, int w, float ampl, float step, LocalCounters& lc) {
 	int lo = 0x7fffffff, hi = -1;
 	for (int i = 0; i < w; ++i) {
 		const int idx = s + i;
 		if (idx >= 0) {                         // StereoRecorder::_Sample drops negative bins (:93)
 			if (idx < n_bins) {
-				atomicAdd(track + idx, ampl);   // RED.ADD.F32 to the L2-resident histogram
+				sink.add(k, idx, ampl);
 				lo = min(lo, idx); hi = max(hi, idx);
 				++lc.bin_updates;
 			} else ++lc.dropped;
 		}
 		ampl = fsub(ampl, step);
 	}
-	if (hi >= 0) touch_range(range, lo, hi);
+	if (hi >= 0) sink.touched(k, lo, hi);
 }
 
-__device__ __forceinline__ void record(const ear_b200_recorder& rec, float* tracks /* 2 x n_bins */, uint32_t* range,
-                                       int n_bins, V3 dir, float a, float t, float dist, int band, LocalCounters& lc) {
+template <class Sink>
+__device__ __forceinline__ void record(const ear_b200_recorder& rec, Sink& sink, int n_bins, V3 dir, float a, float t, float dist,
+                                       int band, LocalCounters& lc) {
 	++lc.contributions;
 	const float width = fsqrt(dist);
 	const float ampl = fdiv(fmul(2.0f, a), width);
@@ -124,11 +150,11 @@ __device__ __forceinline__ void record(const ear_b200_recorder& rec, float* trac
 		const float factor = pow_ref(rec.head_absorption[band], fmul(fabsf(dt), rec.head_size));
 		if (dt < 0) ampl_right = fmul(ampl_right, fmul(factor, factor));
 		else ampl_left = fmul(ampl_left, fmul(factor, factor));
-		splat_ramp(tracks, range, n_bins, s_left, w, ampl_left, fdiv(ampl_left, (float)w), lc);
-		splat_ramp(tracks + n_bins, range + 2, n_bins, s_right, w, ampl_right, fdiv(ampl_right, (float)w), lc);
+		splat_ramp(sink, 0, n_bins, s_left, w, ampl_left, fdiv(ampl_left, (float)w), lc);
+		splat_ramp(sink, 1, n_bins, s_right, w, ampl_right, fdiv(ampl_right, (float)w), lc);
 	} else {
 		const int s = __double2int_rz((double)t * 44100.0);
-		splat_ramp(tracks, range, n_bins, s, w, ampl, fdiv(ampl, (float)w), lc);
+		splat_ramp(sink, 0, n_bins, s, w, ampl, fdiv(ampl, (float)w), lc);
 	}
 }
 
@@ -140,276 +166,62 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 
 constexpr int kBlock = 128;
 
-// The bounce loop of Scene::Render (src/Scene.cpp:124-284), one ray per lane, warp-synchronous.
-// Every iteration of the outer loop advances every live lane by exactly one bounce:
-//   K6 refill    dead lanes take fresh ray ids (one ballot + one queue atomic per warp, ranks by popc)
-//   K2 closest   Scene::Bounce -> Mesh::RayIntersection            (traverse_warp<false>)
-//   K3 shade     Material::Bounce, reflect, Sample_Hemi, air + surface absorption
-//   K4 occlusion Scene::Connect per recorder                        (traverse_warp<true>)
-//   K5 splat     contribution weight + Recorder::Record
-// so lanes of one warp may be at different bounce numbers of different rays (even of different
-// contexts) but always in the same phase.  PATHS = true replays explicit ray ids and logs the
-// triangle hit at each bounce instead of recording (parity harness).
-template <bool PATHS, bool EXACT>
-__device__ __forceinline__ void bounce_loop(const SceneDev& sc, const RenderParams& p, int2* stack, int stride,
-                                            LocalCounters& lc, int paths_ctx, long long paths_n, int32_t* hits,
-                                            float* final_state) {
-	const int lane = threadIdx.x & 31;
-	const unsigned lt_mask = (1u << lane) - 1u;
-	bool alive = false, queue_empty = false, has_ray = false;
-	int c = 0, b = 1;
-	long long ray_slot = 0;   // PATHS: index of this lane's ray in the output arrays
-	V3 o = mk(0, 0, 0), d = mk(0, 0, 0), prev_dir = mk(0, 0, 0);
-	float intensity = 1.0f, path = 0.0f, af = 1.0f;
-	double log2_af = 0.0;
-	int band = 0;
-	Rng rng;
-	rng.start(0, 0, 0);
-	for (;;) {
-		// ---------------- K6: refill dead lanes ----------------
-		const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-		if (dead != 0u && !queue_empty) {
-			const int want = __popc(dead);
-			long long base = 0;
-			if (PATHS) {
-				// harness: thread i owns ray i, handed out once
-				base = (long long)(blockIdx.x * blockDim.x + (threadIdx.x & ~31));
-				queue_empty = true;
-			} else {
-				if (lane == 0) base = (long long)atomicAdd(p.next_work, (unsigned long long)want);
-				base = __shfl_sync(0xffffffffu, base, 0);
-				if (base + want >= p.total_work) queue_empty = true;
-			}
-			const long long w = PATHS ? base + lane : base + __popc(dead & lt_mask);
-			const long long limit = PATHS ? paths_n : p.total_work;
-			if (!alive && w < limit) {
-				unsigned long long ray;
-				if (PATHS) { c = paths_ctx; ray = (unsigned long long)(p.first_ray + w); ray_slot = w; }
-				else {
-					c = 0;
-					while (c + 1 < p.n_ctx && w >= p.work_prefix[c + 1]) ++c;
-					ray = (unsigned long long)(p.first_ray + (w - p.work_prefix[c]));
-				}
-				band = p.ctx[c].band;
-				af = p.ctx[c].absorption_factor;
-				log2_af = log2_ref(af);
-				rng.start(p.seed, stream_key(p, c), ray);
-				++lc.rays;
-				// bounce 0: AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226); intensity 1 is
-				// FP_NORMAL and >= 1e-8 and nothing is recorded for point sources (src/Scene.cpp:185), so the
-				// iteration only leaves prev_ray_dir = normalize(dir) behind (:277)
-				o = mk(p.ctx[c].source_position[0], p.ctx[c].source_position[1], p.ctx[c].source_position[2]);
-				d = sample_sphere(rng);
-				prev_dir = vnormalized(d);
-				intensity = 1.0f; path = 0.0f; b = 1;
-				alive = b < p.max_bounces;
-				has_ray = true;
-				if (PATHS && !alive && final_state) {
-					float* fs = final_state + 8 * ray_slot;
-					fs[0] = o.x; fs[1] = o.y; fs[2] = o.z; fs[3] = d.x; fs[4] = d.y; fs[5] = d.z; fs[6] = intensity; fs[7] = path;
-				}
-			}
-		}
-		__syncwarp();
-		if (!__any_sync(0xffffffffu, alive)) break;
-
-		// ---------------- K2: Scene::Bounce -> closest hit (src/Scene.cpp:49-58) ----------------
-		float t; int32_t idx, slot;
-		traverse_warp<false, EXACT>(sc, stack, stride, alive, o, d, t, idx, slot);
-		bool shade = alive && idx >= 0;
-		bool refract = false;
-		float spec = 0.0f;
-		V3 n = mk(0, 0, 0);
-		if (alive) {
-			++lc.segments;
-			if (PATHS) hits[ray_slot * p.max_bounces + b] = idx;
-			if (idx < 0) alive = false;
-		}
-		// ---------------- K3: material + resample (src/Scene.cpp:60-82, 154-175) ----------------
-		if (shade) {
-			const float4 r1 = __ldg(sc.tris + 4 * (size_t)slot + 1);
-			const float4 r3 = __ldg(sc.tris + 4 * (size_t)slot + 3);
-			const V3 tri_n = mk(r3.x, r3.y, r3.z);                                       // Triangle::normal
-			const V3 pnt = vadd(o, vscale(d, t));                                        // src/Mesh.cpp:48
-			n = (vdot(tri_n, d) > 0.0f) ? vscale(tri_n, -1.0f) : tri_n;                  // :49-53
-			const float4 m = __ldg(sc.materials + (size_t)__float_as_int(r1.w) * sc.n_bands + band);
-			// Material::Bounce (src/Material.cpp:76-83); its comparisons against 0.0001 are in double
-			if ((double)m.x < 0.0001 && (double)m.y < 0.0001) refract = false;
-			else refract = !(rng.unit1() <= fdiv(m.x, fadd(m.x, m.y)));
-			spec = m.w;
-			V3 v;
-			if (refract) { n = vneg(n); v = sample_hemi_blend(rng, n, d, spec); }
-			else v = sample_hemi_blend(rng, n, vreflect(d, n), spec);
-			const float seg = vlength(vsub(pnt, o));
-			intensity = fmul(intensity, pow_ref_hoisted(af, log2_af, seg));                               // src/Scene.cpp:154
-			path = fadd(path, seg);
-			o = pnt; d = v;
-			intensity = fmul(intensity, m.z);                                            // :169-171
-			if (invalid_float(intensity)) { alive = false; shade = false; }              // :175
-		}
-		__syncwarp();
-		// ---------------- K4 + K5: connect to every recorder, weight, splat (src/Scene.cpp:185-268) ----------------
-		if (!PATHS) {
-			for (int r = 0; r < p.n_rec; ++r) {
-				const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
-				const V3 x = mk(rec.position[0], rec.position[1], rec.position[2]);
-				const V3 segv = vsub(x, o);   // LineSeg(p, x) = Ray(p, x - p)
-				// Scene::Connect is evaluated for every live lane in the reference (:194); its answer is only used
-				// when dot(lsdir, n) > 0 (:209), so lanes failing that test skip the traversal (same result)
-				const V3 lsdir = vnormalized(segv);
-				const bool facing = shade && vdot(lsdir, n) > 0.0f;
-				float tt; int32_t occluded, ss;
-				traverse_warp<true, EXACT>(sc, stack, stride, facing, o, segv, tt, occluded, ss);
-				if (shade) {
-					++lc.occlusion;
-					if (facing && !occluded) {                                               // :197-209
-						float factor;
-						if (!refract) {                                                      // :219-235
-							const V3 rv = vreflect(prev_dir, n);
-							const float diff = -vdot(n, prev_dir);
-							const float dsp = vdot(rv, lsdir);
-							const float specf = (0.0f < dsp) ? dsp : 0.0f;
-							factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
-						} else {                                                             // :236-247
-							const float diff = vdot(n, prev_dir);
-							const float dsp = vdot(prev_dir, lsdir);
-							const float specf = (0.0f < dsp) ? dsp : 0.0f;
-							factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
-						}
-						float contrib = fmul(intensity, factor);
-						const float l = vlength(segv);                                       // :250
-						contrib = fmul(contrib, pow_ref_hoisted(af, log2_af, l));
-						contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));   // INV_HEMI_2, :252
-						if (!invalid_float(contrib)) {
-							if (b & 1) contrib = fmul(contrib, -1.0f);                       // :257
-							const size_t slot2 = ((size_t)c * p.n_rec + r) * 2;
-							record(rec, p.hist + slot2 * p.n_bins, p.range + slot2 * 2, p.n_bins, lsdir, contrib,
-							       fdiv(fadd(path, l), 343.0f), fadd(path, l), band, lc);
-						}
-					}
-				}
-				__syncwarp();
-			}
-		}
-		// ---------------- end of this bounce (src/Scene.cpp:275-277) ----------------
-		if (shade) {
-			if ((double)intensity < 0.00000001) alive = false;
-			else {
-				prev_dir = vnormalized(d);
-				++b;
-				if (b >= p.max_bounces) alive = false;
-			}
-		}
-		if (PATHS && final_state && has_ray && !alive) {
-			// a finished ray writes its last state once (later iterations see alive == false and ray_slot unchanged,
-			// rewriting the same values is harmless)
-			float* fs = final_state + 8 * ray_slot;
-			if (ray_slot < paths_n) { fs[0] = o.x; fs[1] = o.y; fs[2] = o.z; fs[3] = d.x; fs[4] = d.y; fs[5] = d.z; fs[6] = intensity; fs[7] = path; }
-		}
-	}
-}
-
 #include "wavefront.cuh"
 #include "vismap.cuh"
 #include "post.cuh"
-
-// Fused single-kernel engine (EAR_B200_ENGINE=mega): grid = SMs x resident blocks; warps pull ray ids from a
-// global queue until it is dry.
-template <bool EXACT, int MIN_BLOCKS>
-__global__ void __launch_bounds__(kBlock, MIN_BLOCKS) render_kernel(SceneDev sc, RenderParams p) {
-	extern __shared__ int2 stack_smem[];
-	const int lane = threadIdx.x & 31;
-	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	bounce_loop<false, EXACT>(sc, p, stack_smem + threadIdx.x, blockDim.x, lc, 0, 0, nullptr, nullptr);
-	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
-	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
-	if (lane == 0) {
-		atomicAdd(p.counters + 0, v0); atomicAdd(p.counters + 1, v1); atomicAdd(p.counters + 2, v2);
-		atomicAdd(p.counters + 3, v3); atomicAdd(p.counters + 4, v4); atomicAdd(p.counters + 5, v5);
-	}
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kBlock) paths_kernel(SceneDev sc, RenderParams p, int c, long long n, int32_t* hits, float* final_state) {
-	extern __shared__ int2 stack_smem[];
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n) for (int b = 0; b < p.max_bounces; ++b) hits[(size_t)i * p.max_bounces + b] = -2;
-	__syncwarp();
-	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	bounce_loop<true, EXACT>(sc, p, stack_smem + threadIdx.x, blockDim.x, lc, c, n, hits, final_state);
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kBlock) first_hit_kernel(SceneDev sc, const float* origins, const float* dirs, long long n, int32_t* tri_index,
-                                 float* t_out) {
-	extern __shared__ int2 stack_smem[];
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = i < n;
-	const long long j = active ? i : 0;
-	float t; int32_t idx, slot;
-	traverse_warp<false, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, mk(origins[3 * j], origins[3 * j + 1], origins[3 * j + 2]),
-	                            mk(dirs[3 * j], dirs[3 * j + 1], dirs[3 * j + 2]), t, idx, slot);
-	if (active) { tri_index[i] = idx; t_out[i] = t; }
-}
-
-template <bool EXACT>
-__global__ void __launch_bounds__(kBlock) occluded_kernel(SceneDev sc, const float* pp, const float* xx, long long n, uint8_t* out) {
-	extern __shared__ int2 stack_smem[];
-	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = i < n;
-	const long long j = active ? i : 0;
-	const V3 p = mk(pp[3 * j], pp[3 * j + 1], pp[3 * j + 2]);
-	const V3 x = mk(xx[3 * j], xx[3 * j + 1], xx[3 * j + 2]);
-	float t; int32_t occ, slot;
-	traverse_warp<true, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, p, vsub(x, p), t, occ, slot);
-	if (active) out[i] = (uint8_t)occ;
-}
 
 // ---- K7: Scene::Render's tail, src/Scene.cpp:286-316 ----
 // FloatBuffer::Multiply over [first_sample, real_length) -- the last touched bin is NOT scaled
 // (src/Recorder.cpp:85-89).  mode 0: x 1/amount, mode 1: x gain^2.
 __global__ void scale_kernel(RenderParams p, int mode) {
-	const int track = blockIdx.y;  // (ctx * n_rec + rec) * 2 + k
-	const int c = track / (2 * p.n_rec);
-	const int r = (track / 2) % p.n_rec;
-	if ((track & 1) && p.rec[(size_t)c * p.n_rec + r].kind != EAR_B200_STEREO) return;
-	const uint32_t first = p.range[2 * track], real = p.range[2 * track + 1];
-	float f;
-	if (mode == 0) {
-		// `amount` is a float bumped by 1.0f per ray (src/Scene.cpp:122,127): it saturates at 2^24
-		const long long ns = p.ctx[c].num_samples;
-		f = fdiv(1.0f, (float)(ns < 16777216 ? ns : 16777216));
-	} else f = fmul(p.ctx[c].gain, p.ctx[c].gain);
-	float* tr = p.hist + (size_t)track * p.n_bins;
-	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < real; i += gridDim.x * blockDim.x)
-		tr[i] = fmul(tr[i], f);
+	const int n_tracks = p.n_ctx * p.n_rec * p.tpr;
+	for (int track = blockIdx.y; track < n_tracks; track += gridDim.y) {   // (ctx * n_rec + rec) * tpr + k
+		const int c = track / (p.tpr * p.n_rec);
+		const int r = (track / p.tpr) % p.n_rec;
+		if ((track % p.tpr) && p.rec[(size_t)c * p.n_rec + r].kind != EAR_B200_STEREO) continue;
+		const uint32_t first = p.range[2 * track], real = p.range[2 * track + 1];
+		float f;
+		if (mode == 0) {
+			// `amount` is a float bumped by 1.0f per ray (src/Scene.cpp:122,127): it saturates at 2^24
+			const long long ns = p.ctx[c].num_samples;
+			f = fdiv(1.0f, (float)(ns < 16777216 ? ns : 16777216));
+		} else f = fmul(p.ctx[c].gain, p.ctx[c].gain);
+		float* tr = p.hist + (size_t)track * p.n_bins;
+		for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < real; i += gridDim.x * blockDim.x)
+			tr[i] = fmul(tr[i], f);
+	}
 }
 // Direct sound (src/Scene.cpp:299-311): one lane per (context, recorder).
 template <bool EXACT>
 __global__ void __launch_bounds__(kBlock) direct_kernel(SceneDev sc, RenderParams p) {
 	extern __shared__ int2 stack_smem[];
-	const int i = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool active = i < p.n_ctx * p.n_rec;
-	const int j = active ? i : 0;
-	const int c = j / p.n_rec;
-	const ear_b200_context cx = p.ctx[c];
-	const ear_b200_recorder& rec = p.rec[j];
-	const V3 listener = mk(rec.position[0], rec.position[1], rec.position[2]);
-	const V3 source = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
-	float t; int32_t occ, slot;
-	traverse_warp<true, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active, listener, vsub(source, listener), t, occ, slot);
-	if (!active || occ) return;
-	const V3 dist = vsub(listener, source);
-	const float len = vlength(dist);
-	const V3 dir = vnormalized(dist);
-	const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), pow_ref(cx.absorption_factor, len)),
-	                     cx.dry_level);
-	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	record(rec, p.hist + (size_t)j * 2 * p.n_bins, p.range + (size_t)j * 4, p.n_bins, dir, a, fdiv(len, 343.0f), len,
-	       cx.band, lc);
-	if (p.counters) {   // the direct lobe is a Record() call like any other (src/Scene.cpp:308)
-		atomicAdd(p.counters + 3, lc.contributions); atomicAdd(p.counters + 4, lc.bin_updates);
-		atomicAdd(p.counters + 5, lc.dropped);
+	const int n_pairs = p.n_ctx * p.n_rec;
+	for (int base = blockIdx.x * blockDim.x; base < n_pairs; base += gridDim.x * blockDim.x) {   // block-uniform trip count
+		const int i = base + threadIdx.x;
+		const bool active = i < n_pairs;
+		const int j = active ? i : 0;
+		const int c = j / p.n_rec;
+		const ear_b200_context cx = p.ctx[c];
+		const ear_b200_recorder& rec = p.rec[j];
+		const V3 listener = mk(rec.position[0], rec.position[1], rec.position[2]);
+		const V3 source = mk(cx.source_position[0], cx.source_position[1], cx.source_position[2]);
+		float t; int32_t occ, slot;
+		traverse_warp<true, EXACT>(sc, stack_smem + threadIdx.x, blockDim.x, active && cx.source_kind == EAR_B200_POINT_SOURCE,
+		                           listener, vsub(source, listener), t, occ, slot);
+		// "not a mesh source" (src/Scene.cpp:299): mesh emitters have no direct lobe
+		if (!active || occ || cx.source_kind != EAR_B200_POINT_SOURCE) continue;
+		const V3 dist = vsub(listener, source);
+		const float len = vlength(dist);
+		const V3 dir = vnormalized(dist);
+		const float a = fmul(fmul(fdiv(1.0f, fmul(fmul(fmul(4.0f, PI_F), len), len)), pow_ref(cx.absorption_factor, len)),
+		                     cx.dry_level);
+		LocalCounters lc = {0, 0, 0, 0, 0, 0};
+		GlobalSink sink = {p.hist + (size_t)j * p.tpr * p.n_bins, p.range + (size_t)j * p.tpr * 2, p.n_bins};
+		record(rec, sink, p.n_bins, dir, a, fdiv(len, 343.0f), len, cx.band, lc);
+		if (p.counters) {   // the direct lobe is a Record() call like any other (src/Scene.cpp:308)
+			atomicAdd(p.counters + 3, lc.contributions); atomicAdd(p.counters + 4, lc.bin_updates);
+			atomicAdd(p.counters + 5, lc.dropped);
+		}
 	}
 }
 __global__ void init_range_kernel(uint32_t* range, int n_tracks) {
@@ -427,6 +239,10 @@ struct ear_b200_scene {
 	SceneDev dev{};
 	unsigned char* d_image = nullptr;   // [header | nodes | tris | materials], one allocation
 	size_t image_bytes = 0;
+	int2* d_spill = nullptr;            // traversal-stack overflow (SceneDev::spill)
+	float4* d_emitters = nullptr;       // emitter triangles of mesh sources, 4 float4 each (ear_b200_scene_set_emitters)
+	int32_t n_emitters = 0;
+	std::vector<float> emitter_area;    // host copy of the areas: Mesh::total_area per context is summed on the host
 	float4* d_nodes = nullptr;          // views into d_image
 	float4* d_tris = nullptr;
 	float4* d_materials = nullptr;
@@ -438,7 +254,6 @@ struct ear_b200_scene {
 	cudaStream_t stream = nullptr;
 	int sm_count = 148;
 	int min_blocks = 4;
-	int engine = 0;                 // 0 = wavefront (default), 1 = fused kernel (EAR_B200_ENGINE=mega)
 	int max_slots = 1 << 24;        // most rays in flight in the wavefront pool (EAR_B200_SLOTS); per 8e7 rays: 8 Mi 1.50e9,
 	                                // 16 Mi 1.55e9, 32 Mi 1.56e9, 64 Mi 1.55e9 seg/s (bigger launches amortise the persistent
 	                                // kernels' tails and sort better, but the shade kernel walks every slot)
@@ -446,6 +261,7 @@ struct ear_b200_scene {
 	int pool_generations = 0;       // 0: choose from the bounce cap; k: pool = work / k slots (EAR_B200_GENERATIONS)
 	int check_every = 8;            // iterations between host checks for completion
 	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
+	int splat_mode = 0;             // 0: one RED per ramp sample; 1: shared-memory time-window privatisation (EAR_B200_SPLAT=window)
 	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
@@ -530,6 +346,11 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
 	s->dev.n_tris = h.n_tris; s->dev.n_materials = h.n_materials; s->dev.n_bands = h.n_bands;
 	s->dev.s0 = h.s0;
+	// overflow rows of the traversal stacks: a walk holds at most 3 entries per level of the 4-wide tree (+ slack)
+	s->dev.spill_threads = s->sm_count * 16 * kBlock;   // 16 blocks of kBlock threads is the most an SM can hold
+	s->dev.spill_rows = std::max(1, 3 * h.depth + 4 - kStackEntries);
+	CUDA_TRY(cudaMalloc(&s->d_spill, (size_t)s->dev.spill_rows * s->dev.spill_threads * sizeof(int2)));
+	s->dev.spill = s->d_spill;
 	// EAR_B200_EXACT_SLACK=1 selects the rigorous per-child interval bound (about 2x the node visits)
 	const char* ex = std::getenv("EAR_B200_EXACT_SLACK");
 	s->dev.exact = (ex && std::atoi(ex) != 0) ? 1 : 0;
@@ -540,18 +361,17 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->min_blocks = mb ? std::atoi(mb) : 5;
 	const char* fv = std::getenv("EAR_B200_FETCH_VOTE");
 	s->dev.fetch_vote = fv ? std::max(1, std::min(32, std::atoi(fv))) : 8;
-	const char* en = std::getenv("EAR_B200_ENGINE");
-	s->engine = (en && std::string(en) == "mega") ? 1 : 0;
 	read_slot_knob(s);
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
+	if (const char* sm = std::getenv("EAR_B200_SPLAT")) s->splat_mode = std::string(sm) == "window" ? 1 : 0;
 	if (const char* pg = std::getenv("EAR_B200_GENERATIONS")) s->pool_generations = std::max(0, std::atoi(pg));
 	if (const char* rk = std::getenv("EAR_B200_RAY_KEY")) s->ray_key = std::max(0, std::min(4, std::atoi(rk)));
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
-	CUDA_TRY(cudaMallocHost(&s->h_counts, 8 * sizeof(int)));
+	CUDA_TRY(cudaMallocHost(&s->h_counts, 16 * sizeof(int)));   // 8 pool counters + the queue head
 	CUDA_TRY(cudaMalloc(&s->d_scratch_counters, 8 * sizeof(unsigned long long)));
 	return 0;
 }
@@ -606,6 +426,49 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	return 0;
 }
 
+// Emitter triangles of mesh sources.  Record: (v0, area) (v1, 0) (v2, 0) (unit normal, 0); normal and area in the
+// float order of Triangle's constructor (src/Triangle.cpp:26-34: gmtl::normal = normalize(edge(0) x (v2 - v0))... as
+// fixed by oracle/shim/gmtl/gmtl.h; area = |edge(0) x edge(1)| / 2 with edge(i) = v[(i+1)%3] - v[i]).  This file is
+// compiled with -ffp-contract=off, so the host arithmetic below rounds once per operation.
+extern "C" int32_t ear_b200_scene_set_emitters(ear_b200_scene* s, const float* verts, int32_t n) {
+	if (!s) return fail("scene_set_emitters: null scene");
+	if (n < 0 || (n > 0 && !verts)) return fail("scene_set_emitters: bad arguments");
+	CUDA_TRY(cudaSetDevice(s->device));
+	cudaFree(s->d_emitters); s->d_emitters = nullptr; s->n_emitters = 0; s->emitter_area.clear();
+	s->dev.emitters = nullptr;
+	if (n == 0) return 0;
+	std::vector<float> rec((size_t)n * 16, 0.0f);
+	s->emitter_area.resize((size_t)n);
+	for (int32_t i = 0; i < n; ++i) {
+		const float* p = verts + 9 * (size_t)i;
+		float* r = rec.data() + 16 * (size_t)i;
+		float e1[3], e2[3], e12[3];
+		for (int k = 0; k < 3; ++k) { e1[k] = p[3 + k] - p[k]; e2[k] = p[6 + k] - p[k]; e12[k] = p[6 + k] - p[3 + k]; }
+		// gmtl::normal(tri): cross(v1 - v0, v2 - v0), normalised by division
+		const float cx = (e1[1] * e2[2]) - (e1[2] * e2[1]);
+		const float cy = (e1[2] * e2[0]) - (e1[0] * e2[2]);
+		const float cz = (e1[0] * e2[1]) - (e1[1] * e2[0]);
+		float l2 = cx * cx; l2 = l2 + cy * cy; l2 = l2 + cz * cz;
+		const float len = std::sqrt(l2);
+		float nx = cx, ny = cy, nz = cz;
+		if (len != 0.0f) { nx = cx / len; ny = cy / len; nz = cz / len; }
+		// Triangle::calcArea: cross(edge(0), edge(1)) = (v1 - v0) x (v2 - v1)
+		const float ax = (e1[1] * e12[2]) - (e1[2] * e12[1]);
+		const float ay = (e1[2] * e12[0]) - (e1[0] * e12[2]);
+		const float az = (e1[0] * e12[1]) - (e1[1] * e12[0]);
+		float a2 = ax * ax; a2 = a2 + ay * ay; a2 = a2 + az * az;
+		const float area = std::sqrt(a2) / 2.0f;
+		for (int k = 0; k < 3; ++k) { r[k] = p[k]; r[4 + k] = p[3 + k]; r[8 + k] = p[6 + k]; }
+		r[3] = area; r[12] = nx; r[13] = ny; r[14] = nz;
+		s->emitter_area[(size_t)i] = area;
+	}
+	CUDA_TRY(cudaMalloc(&s->d_emitters, rec.size() * sizeof(float)));
+	CUDA_TRY(cudaMemcpy(s->d_emitters, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
+	s->n_emitters = n;
+	s->dev.emitters = s->d_emitters;
+	return 0;
+}
+
 extern "C" int32_t ear_b200_scene_image_size(ear_b200_scene* s, uint64_t* bytes) {
 	if (!s || !bytes) return fail("scene_image_size: null argument");
 	*bytes = (uint64_t)s->image_bytes;
@@ -655,12 +518,13 @@ extern "C" int32_t ear_b200_scene_clone(ear_b200_scene* s, int32_t device, ear_b
 extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	cudaFree(s->d_image);
+	cudaFree(s->d_image); cudaFree(s->d_spill); cudaFree(s->d_emitters);
 	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue);
 	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
 	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
 	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins); cudaFree(s->pool.ctx_log2af);
+	cudaFree(s->pool.pair_count); cudaFree(s->pool.pair_base);
 	cudaFree(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -683,14 +547,14 @@ extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, c
 	DevBuf<int32_t> d_i;
 	CUDA_TRY(d_o.alloc((size_t)chunk * 3)); CUDA_TRY(d_d.alloc((size_t)chunk * 3));
 	CUDA_TRY(d_t.alloc((size_t)chunk)); CUDA_TRY(d_i.alloc((size_t)chunk));
-	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, 1)) return rc; }
+	if (int32_t rc = ensure_pool(s, (size_t)chunk, 1)) return rc;
 	RenderParams p{};
 	for (int64_t at = 0; at < n; at += chunk) {
 		const int m = (int)std::min<int64_t>(chunk, n - at);
 		const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
 		CUDA_TRY(cudaMemcpyAsync(d_o, origins + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
 		CUDA_TRY(cudaMemcpyAsync(d_d, dirs + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
-		if (s->engine == 0) {
+		{
 			// the production closest-hit kernel (persistent, dynamic fetch) over an explicit ray list
 			WfPool pl = s->pool;
 			wf_load_rays_kernel<<<grid, kBlock, 0, s->stream>>>(pl, d_o, d_d, m);
@@ -699,8 +563,7 @@ extern "C" int32_t ear_b200_first_hit(ear_b200_scene* s, const float* origins, c
 			CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, closest, kBlock, kStackBytes));
 			closest<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
 			wf_store_hits_kernel<<<grid, kBlock, 0, s->stream>>>(s->dev, pl, m, d_i, d_t);
-		} else if (s->dev.exact) first_hit_kernel<true><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, m, d_i, d_t);
-		else first_hit_kernel<false><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_o, d_d, m, d_i, d_t);
+		}
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaMemcpyAsync(tri_index + at, d_i, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
 		CUDA_TRY(cudaMemcpyAsync(t + at, d_t, (size_t)m * 4, cudaMemcpyDeviceToHost, s->stream));
@@ -719,11 +582,11 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 	DevBuf<float4> d_qx;
 	CUDA_TRY(d_p.alloc((size_t)chunk * 3)); CUDA_TRY(d_x.alloc((size_t)chunk * 3)); CUDA_TRY(d_out.alloc((size_t)chunk));
 	CUDA_TRY(d_qx.alloc((size_t)chunk));
-	if (s->engine == 0) { if (int32_t rc = ensure_pool(s, (size_t)chunk, (size_t)chunk)) return rc; }
+	if (int32_t rc = ensure_pool(s, (size_t)chunk, (size_t)chunk)) return rc;
 	RenderParams p{};
 	// all segments end at one point (the render loop's case): answer through that point's visibility map,
 	// exactly as the render does, with the BVH any-hit kernel for the texels whose lists are too long
-	bool same_x = s->engine == 0;
+	bool same_x = true;
 	for (int64_t i = 1; i < n && same_x; ++i) same_x = std::memcmp(x, x + 3 * i, 12) == 0;
 	int n_mapped = 0;
 	if (same_x) {
@@ -746,7 +609,7 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 		const unsigned grid = (unsigned)((m + kBlock - 1) / kBlock);
 		CUDA_TRY(cudaMemcpyAsync(d_p, p_in + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
 		CUDA_TRY(cudaMemcpyAsync(d_x, x + 3 * at, (size_t)m * 12, cudaMemcpyHostToDevice, s->stream));
-		if (s->engine == 0) {
+		{
 			WfPool pl = s->pool;
 			pl.qx = d_qx;
 			wf_load_segments_kernel<<<grid, kBlock, 0, s->stream>>>(pl, d_qx, d_p, d_x, m, d_out);
@@ -760,8 +623,7 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 				anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl_fb, p);
 			} else anyhit<<<s->sm_count * std::max(1, bps), kBlock, kStackBytes, s->stream>>>(s->dev, pl, p);
 			wf_mark_visible_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(pl, d_out);
-		} else if (s->dev.exact) occluded_kernel<true><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
-		else occluded_kernel<false><<<grid, kBlock, kStackBytes, s->stream>>>(s->dev, d_p, d_x, m, d_out);
+		}
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaMemcpyAsync(out + at, d_out, (size_t)m, cudaMemcpyDeviceToHost, s->stream));
 		CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -783,6 +645,10 @@ static int32_t default_bins(const ear_b200_scene* s, int32_t max_bounces) {
 	bins = std::min(bins, 64.0 * 1024.0 * 1024.0);
 	bins = std::max(bins, 3.0 * 44100.0);               // FloatBuffer starts at 3 s (src/Recorder.h:36)
 	return (int32_t)bins;
+}
+extern "C" int32_t ear_b200_tracks_per_recorder(const ear_b200_recorder* rec, int32_t n) {
+	for (int32_t i = 0; rec && i < n; ++i) if (rec[i].kind == EAR_B200_STEREO) return 2;
+	return 1;
 }
 extern "C" int32_t ear_b200_default_bins(ear_b200_scene* s, const ear_b200_options* opt) {
 	if (!s) return 0;
@@ -827,7 +693,10 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	CUDA_TRY(cudaStreamSynchronize(stream));  // `prefix` is a stack temporary
 	p.ctx = s->d_ctx; p.rec = s->d_rec; p.work_prefix = s->d_prefix;
 	p.n_ctx = n_ctx; p.n_rec = n_rec;
+	p.tpr = ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
 	p.max_bounces = (opt && opt->max_bounces > 0) ? opt->max_bounces : 1000;
+	// the pool keeps a ray's bounce number in 16 bits (wavefront.cuh, rm.z)
+	if (p.max_bounces > 65535) return fail("render: max_bounces above 65535 is not supported");
 	p.seed = opt ? opt->seed : 1;
 	p.first_ray = first;
 	p.total_work = prefix[n_ctx];
@@ -857,22 +726,6 @@ struct LaunchTimer {   // records an event pair around one launch
 	~LaunchTimer() { cudaEventRecord(s->ev_pool[slot].b, stream); }
 };
 
-// Fused single-kernel engine.
-static int32_t launch_mega(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
-	void (*kern)(SceneDev, RenderParams) = nullptr;
-	if (s->dev.exact) kern = render_kernel<true, 4>;
-	else if (s->min_blocks == 4) kern = render_kernel<false, 4>;
-	else if (s->min_blocks == 6) kern = render_kernel<false, 6>;
-	else kern = render_kernel<false, 5>;
-	int blocks_per_sm = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kBlock, kStackBytes));
-	const long long want = (p.total_work + kBlock - 1) / kBlock;
-	const int grid = (int)std::max<long long>(1, std::min<long long>(want, (long long)s->sm_count * std::max(1, blocks_per_sm)));
-	{ LaunchTimer t(s, stream, 4); kern<<<grid, kBlock, kStackBytes, stream>>>(s->dev, p); }
-	CUDA_TRY(cudaGetLastError());
-	return 0;
-}
-
 static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	WfPool& pl = s->pool;
 	if (slots > s->pool_slots) {
@@ -892,6 +745,11 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 		s->pool_queries = queries;
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
+	if (!pl.pair_count) {
+		CUDA_TRY(cudaMalloc(&pl.pair_count, kPrivMaxPairs * sizeof(int)));
+		CUDA_TRY(cudaMalloc(&pl.pair_base, (kPrivMaxPairs + 1) * sizeof(int)));
+	}
+	pl.vis_sorted = pl.q_tmp;   // the pre-binning query list is dead once the queries are scattered
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	pl.slot_bits = kMaxSlotBits;   // harness calls: one implicit recorder
 	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, kBinsTotal * sizeof(int)));
@@ -1073,8 +931,12 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	const int trav_grid = s->sm_count * std::max(1, bps);
 	const int shade_grid = (int)(slots / 256);
 	const int splat_grid = s->sm_count * 8;
+	const int n_pairs = p.n_ctx * p.n_rec;
+	const bool windowed = s->splat_mode == 1 && n_pairs <= kPrivMaxPairs && p.n_rec > 0;
+	if (windowed) CUDA_TRY(cudaFuncSetAttribute(wf_splat_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPrivWindow * sizeof(float))));
 	// upper bound on iterations: every slot hosts ceil(work/slots) rays of at most max_bounces iterations each
-	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 2) + 4;
+	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 2) + 4 + s->check_every;
+	bool finished = false;
 	for (long long it = 0; it < max_iter;) {
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
 			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
@@ -1095,35 +957,61 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 					wf_vismap_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh);
 					anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl_fb, p);
 				} else { LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
-				{ LaunchTimer t(s, stream, 3); wf_splat_kernel<<<splat_grid, 256, 0, stream>>>(pl, p); }
+				if (windowed) {
+					LaunchTimer t(s, stream, 3);
+					s->stats.launches[3] += 3;
+					CUDA_TRY(cudaMemsetAsync(pl.pair_count, 0, (size_t)n_pairs * sizeof(int), stream));
+					wf_vis_count_kernel<<<splat_grid, 256, 0, stream>>>(pl, p);
+					wf_vis_scan_kernel<<<1, 1024, 0, stream>>>(pl, n_pairs);
+					wf_vis_scatter_kernel<<<splat_grid, 256, 0, stream>>>(pl, p);
+					wf_splat_window_kernel<<<s->sm_count * 3, 256, kPrivWindow * sizeof(float), stream>>>(pl, p);
+				} else { LaunchTimer t(s, stream, 3); wf_splat_kernel<<<splat_grid, 256, 0, stream>>>(pl, p); }
 			}
 			++s->stats.iterations;
 		}
 		CUDA_TRY(cudaGetLastError());
 		CUDA_TRY(cudaMemcpyAsync(s->h_counts, pl.counts, 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaMemcpyAsync(s->h_counts + 8, s->d_queue, sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
 		CUDA_TRY(cudaStreamSynchronize(stream));
-		if (std::getenv("EAR_B200_DEBUG"))
-			std::fprintf(stderr, "[ear_b200] it %lld: trav %d queries %d visible %d map-fallback %d\n", it, s->h_counts[0], s->h_counts[1], s->h_counts[2], s->h_counts[5]);
+		unsigned long long queue_head;
+		std::memcpy(&queue_head, s->h_counts + 8, sizeof(queue_head));
+		if (dbg)
+			std::fprintf(stderr, "[ear_b200] it %lld: trav %d queries %d visible %d map-fallback %d queue %llu/%lld\n", it, s->h_counts[0], s->h_counts[1], s->h_counts[2], s->h_counts[5], queue_head, p.total_work);
 		harvest_events(s);
-		if (s->h_counts[0] == 0) break;   // nothing left to trace after the last shade
+		// Done when the last shade left no ray to trace AND the shard's queue is dry.  A slot whose ray ends in launch k
+		// is refilled in launch k + 1, so "no live ray" alone also holds between two generations of a pool that turns
+		// over in lockstep (every ray reaching the bounce cap in the same iteration).
+		if (s->h_counts[0] == 0 && (long long)queue_head >= p.total_work) { finished = true; break; }
 	}
+	if (!finished) return fail("render: the wavefront loop hit its iteration bound with rays left (internal error)");
 	return 0;
 }
 
 static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
 	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
 	if (p.total_work <= 0) return 0;
-	return s->engine == 1 ? launch_mega(s, p, stream) : launch_wavefront(s, p, stream);
+	// every ray of the shard must have been emitted when the engine returns: the caller's `rays` counter (which may
+	// already hold earlier shards) has to advance by exactly total_work
+	unsigned long long rays_before = 0, rays_after = 0;
+	CUDA_TRY(cudaMemcpyAsync(&rays_before, p.counters, sizeof(rays_before), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	if (int32_t rc = launch_wavefront(s, p, stream)) return rc;
+	CUDA_TRY(cudaMemcpyAsync(&rays_after, p.counters, sizeof(rays_after), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	if ((long long)(rays_after - rays_before) != p.total_work)
+		return fail("render: traced " + std::to_string(rays_after - rays_before) + " of " + std::to_string(p.total_work) + " rays (internal error)");
+	return 0;
 }
 
 static int32_t launch_finalise(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
-	const int n_tracks = p.n_ctx * p.n_rec * 2;
-	dim3 grid(64, n_tracks);
+	const int n_tracks = p.n_ctx * p.n_rec * p.tpr;
+	dim3 grid(64, (unsigned)std::min(n_tracks, 32768));
+	const int direct_grid = std::max(1, std::min((p.n_ctx * p.n_rec + kBlock - 1) / kBlock, s->dev.spill_threads / kBlock));
 	LaunchTimer t(s, stream, 5);
 	s->stats.launches[5] += 2;
 	scale_kernel<<<grid, 256, 0, stream>>>(p, 0);
-	if (s->dev.exact) direct_kernel<true><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
-	else direct_kernel<false><<<(p.n_ctx * p.n_rec + kBlock - 1) / kBlock, kBlock, kStackBytes, stream>>>(s->dev, p);
+	if (s->dev.exact) direct_kernel<true><<<direct_grid, kBlock, kStackBytes, stream>>>(s->dev, p);
+	else direct_kernel<false><<<direct_grid, kBlock, kStackBytes, stream>>>(s->dev, p);
 	scale_kernel<<<grid, 256, 0, stream>>>(p, 1);
 	CUDA_TRY(cudaGetLastError());
 	return 0;
@@ -1171,7 +1059,7 @@ static int32_t upload_recorders(ear_b200_scene* s, const ear_b200_recorder* rec,
 static int32_t ensure_post_scratch(ear_b200_scene* s, size_t n_tracks) {
 	if (n_tracks > s->post_cap) {
 		cudaFree(s->d_post); s->d_post = nullptr; s->post_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->d_post, n_tracks * 2 * sizeof(float)));   // [track_max or t60 | track_len]
+		CUDA_TRY(cudaMalloc(&s->d_post, n_tracks * 3 * sizeof(float)));   // [track_max or t60 | track_len | real_length snapshot]
 		s->post_cap = n_tracks;
 	}
 	return 0;
@@ -1184,10 +1072,11 @@ extern "C" int32_t ear_b200_post_power_device(ear_b200_scene* s, const ear_b200_
 	if (!rec || n_ctx <= 0 || n_rec <= 0 || n_bins <= 0 || !d_hist || !d_range) return fail("post_power_device: bad arguments");
 	CUDA_TRY(cudaSetDevice(s->device));
 	cudaStream_t st = (cudaStream_t)stream;
-	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	const int tpr = ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
+	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
 	if (int32_t rc = upload_recorders(s, rec, (size_t)n_ctx * n_rec, st)) return rc;
 	if (int32_t rc = ensure_post_scratch(s, n_tracks)) return rc;
-	post_power_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, exponent, s->d_post);
+	post_power_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, tpr, exponent, s->d_post);
 	CUDA_TRY(cudaGetLastError());
 	std::vector<float> mx(n_tracks);
 	CUDA_TRY(cudaMemcpyAsync(mx.data(), s->d_post, n_tracks * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1205,12 +1094,14 @@ extern "C" int32_t ear_b200_post_truncate_device(ear_b200_scene* s, const ear_b2
 	if (!rec || n_ctx <= 0 || n_rec <= 0 || n_bins <= 0 || !d_hist || !d_range) return fail("post_truncate_device: bad arguments");
 	CUDA_TRY(cudaSetDevice(s->device));
 	cudaStream_t st = (cudaStream_t)stream;
-	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	const int tpr = ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
+	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
 	if (int32_t rc = upload_recorders(s, rec, (size_t)n_ctx * n_rec, st)) return rc;
 	if (int32_t rc = ensure_post_scratch(s, n_tracks)) return rc;
 	uint32_t* d_len = (uint32_t*)(s->d_post + n_tracks);
-	post_length_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, threshold, d_len);
-	post_truncate_t60_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, d_len, s->d_post);
+	uint32_t* d_real = (uint32_t*)(s->d_post + 2 * n_tracks);
+	post_length_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, tpr, threshold, d_len, d_real);
+	post_truncate_t60_kernel<<<(unsigned)n_tracks, kPostBlock, 0, st>>>(d_hist, d_range, s->d_rec, n_bins, tpr, d_len, d_real, s->d_post);
 	CUDA_TRY(cudaGetLastError());
 	std::vector<float> h(n_tracks);
 	CUDA_TRY(cudaMemcpyAsync(h.data(), s->d_post, n_tracks * sizeof(float), cudaMemcpyDeviceToHost, st));
@@ -1237,7 +1128,8 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	RenderParams p{};
 	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, s->stream, p)) return rc;
 	const int32_t n_bins = ear_b200_default_bins(s, opt);
-	const size_t n_tracks = (size_t)n_ctx * n_rec * 2;
+	const int tpr = p.tpr;
+	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
 	DevBuf<float> d_hist;
 	DevBuf<uint32_t> d_range;
 	DevBuf<unsigned long long> d_counters;
@@ -1274,18 +1166,22 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	ear_b200_result* res = holder.get();
 	if (!res) return fail("render: out of host memory");
 	res->n_contexts = n_ctx; res->n_recorders = n_rec;
-	res->tracks = (ear_b200_track*)calloc(n_tracks, sizeof(ear_b200_track));
+	// the result keeps the [context][recorder][2] shape whatever the device layout was (mono: slot 0 only)
+	res->tracks = (ear_b200_track*)calloc((size_t)n_ctx * n_rec * 2, sizeof(ear_b200_track));
 	if (!res->tracks) return fail("render: out of host memory");
-	for (size_t k = 0; k < n_tracks; ++k) {
-		ear_b200_track& tr = res->tracks[k];
-		const bool used = !(k & 1) || rec[k / 2].kind == EAR_B200_STEREO;
-		tr.first_sample = range[2 * k]; tr.real_length = range[2 * k + 1]; tr.length = used ? (uint32_t)n_bins : 0;
-		if (!used) continue;
-		tr.data = (float*)calloc((size_t)n_bins, sizeof(float));
-		if (!tr.data) return fail("render: out of host memory");
-		const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
-		CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + k * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-	}
+	for (size_t j = 0; j < (size_t)n_ctx * n_rec; ++j)
+		for (int k = 0; k < 2; ++k) {
+			ear_b200_track& tr = res->tracks[2 * j + k];
+			const bool used = k == 0 || rec[j].kind == EAR_B200_STEREO;
+			tr.first_sample = 3 * EAR_B200_SAMPLE_RATE - 1; tr.real_length = 0; tr.length = 0;
+			if (!used) continue;
+			const size_t t = j * tpr + k;   // device track
+			tr.first_sample = range[2 * t]; tr.real_length = range[2 * t + 1]; tr.length = (uint32_t)n_bins;
+			tr.data = (float*)calloc((size_t)n_bins, sizeof(float));
+			if (!tr.data) return fail("render: out of host memory");
+			const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
+			CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + t * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+		}
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	lap("finalise + track download");
 	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
@@ -1430,17 +1326,11 @@ extern "C" int32_t ear_b200_trace_paths(ear_b200_scene* s, const ear_b200_contex
 	DevBuf<float> d_state;
 	CUDA_TRY(d_hits.alloc((size_t)n * max_b)); CUDA_TRY(d_state.alloc((size_t)n * 8));
 	CUDA_TRY(cudaMemsetAsync(d_state, 0, (size_t)n * 32, s->stream));
-	if (s->engine == 0) {
-		wf_fill_int_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(d_hits, (long long)n * max_b, -2);
-		CUDA_TRY(cudaMemsetAsync(s->d_scratch_counters, 0, 8 * sizeof(unsigned long long), s->stream));
-		p.n_rec = 0;   // paths only: no occlusion queries, nothing recorded
-		p.hits = d_hits; p.final_state = d_state; p.counters = s->d_scratch_counters;
-		if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
-	} else {
-		CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), s->stream));
-		if (s->dev.exact) paths_kernel<true><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
-		else paths_kernel<false><<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, kStackBytes, s->stream>>>(s->dev, p, ctx_index, n, d_hits, d_state);
-	}
+	wf_fill_int_kernel<<<s->sm_count * 4, 256, 0, s->stream>>>(d_hits, (long long)n * max_b, -2);
+	CUDA_TRY(cudaMemsetAsync(s->d_scratch_counters, 0, 8 * sizeof(unsigned long long), s->stream));
+	p.n_rec = 0;   // paths only: no occlusion queries, nothing recorded
+	p.hits = d_hits; p.final_state = d_state; p.counters = s->d_scratch_counters;
+	if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaMemcpyAsync(hits, d_hits, (size_t)n * max_b * 4, cudaMemcpyDeviceToHost, s->stream));
 	if (final_state) CUDA_TRY(cudaMemcpyAsync(final_state, d_state, (size_t)n * 32, cudaMemcpyDeviceToHost, s->stream));

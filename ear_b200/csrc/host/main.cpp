@@ -34,7 +34,7 @@ namespace {
 const char* kBanner =
     "  ______                      _____  \n |  ____|         /\\         |  __ \\ \n | |__           /  \\        | |__) | \n"
     " |  __|         / /\\ \\       |  _  / \n | |____       / ____ \\      | | \\ \\ \n |______| (_) /_/    \\_\\ (_) |_|  \\_\\\n"
-    " Evaluation of Acoustics using Ray-tracing\n ear_b200: B200-native render path (ABI v1)";
+    " Evaluation of Acoustics using Ray-tracing\n ear_b200: B200-native render path (ABI v3)";
 
 struct Context {
 	int sound, keyframe, band;

@@ -33,19 +33,19 @@ __device__ __forceinline__ int block_max_i(int v, int* scratch) {
 }
 __device__ __forceinline__ int block_min_i(int v, int* scratch) { return -block_max_i(-v, scratch); }
 
-// track t exists iff it is the first track of its recorder or the recorder is stereo
-__device__ __forceinline__ bool track_exists(const ear_b200_recorder* rec, int t) {
-	return !(t & 1) || rec[t >> 1].kind == EAR_B200_STEREO;
+// track t = (context * n_rec + recorder) * tpr + k exists iff it is the first track of its recorder or the recorder is stereo
+__device__ __forceinline__ bool track_exists(const ear_b200_recorder* rec, int t, int tpr) {
+	return (t % tpr) == 0 || rec[t / tpr].kind == EAR_B200_STEREO;
 }
 
 // FloatBuffer::Power (src/Recorder.cpp:101-106) in place + FloatBuffer::Maximum (:76-83) of the result.
 // track_max[t] = max |x| over [first_sample, real_length), 0 for tracks that do not exist.
 __global__ void __launch_bounds__(kPostBlock) post_power_kernel(float* hist, const uint32_t* range, const ear_b200_recorder* rec,
-                                                                int n_bins, float exponent, float* track_max) {
+                                                                int n_bins, int tpr, float exponent, float* track_max) {
 	__shared__ float scratch[32];
 	const int t = blockIdx.x;
 	float mx = 0.0f;
-	if (track_exists(rec, t)) {
+	if (track_exists(rec, t, tpr)) {
 		float* x = hist + (size_t)t * n_bins;
 		const uint32_t first = range[2 * t], real = min(range[2 * t + 1], (uint32_t)n_bins);
 		for (uint32_t i = first + threadIdx.x; i < real; i += kPostBlock) {
@@ -62,18 +62,22 @@ __global__ void __launch_bounds__(kPostBlock) post_power_kernel(float* hist, con
 // FloatBuffer::getLength(threshold) (src/Recorder.cpp:108-118): 1 + the last i in [first_sample, length) with
 // |x[i]| >= threshold (1 when there is none); real_length when threshold < 0.
 __global__ void __launch_bounds__(kPostBlock) post_length_kernel(const float* hist, const uint32_t* range, const ear_b200_recorder* rec,
-                                                                 int n_bins, float threshold, uint32_t* track_len) {
+                                                                 int n_bins, int tpr, float threshold, uint32_t* track_len,
+                                                                 uint32_t* track_real) {
 	__shared__ int scratch[32];
 	const int t = blockIdx.x;
 	int last = 0;
-	const bool exists = track_exists(rec, t);
+	const bool exists = track_exists(rec, t, tpr);
 	if (exists && !(threshold < 0.0f)) {
 		const float* x = hist + (size_t)t * n_bins;
 		for (uint32_t i = range[2 * t] + threadIdx.x; i < (uint32_t)n_bins; i += kPostBlock)
 			if (fabsf(x[i]) >= threshold) last = (int)i;
 	}
 	last = block_max_i(last, scratch);
-	if (threadIdx.x == 0) track_len[t] = !exists ? 0u : (threshold < 0.0f ? range[2 * t + 1] : (uint32_t)last + 1u);
+	if (threadIdx.x == 0) {
+		track_len[t] = !exists ? 0u : (threshold < 0.0f ? range[2 * t + 1] : (uint32_t)last + 1u);
+		track_real[t] = range[2 * t + 1];   // snapshot: the truncate kernel overwrites real_length while sibling blocks still need it
+	}
 }
 
 // Recorder::getLength / Recorder::Truncate (src/Recorder.cpp:399-430): the recorder's length is the longest of its
@@ -82,13 +86,14 @@ __global__ void __launch_bounds__(kPostBlock) post_length_kernel(const float* hi
 // lobe, min_gain = predecessor / 10^(60/20), the last later sample above min_gain ends the tail.  When a track has no
 // such samples the reference reads uninitialised offsets; like the host port (host/tracks.cpp) this uses 0 for both.
 __global__ void __launch_bounds__(kPostBlock) post_truncate_t60_kernel(const float* hist, uint32_t* range, const ear_b200_recorder* rec,
-                                                                       int n_bins, const uint32_t* track_len, float* t60) {
+                                                                       int n_bins, int tpr, const uint32_t* track_len,
+                                                                       const uint32_t* track_real, float* t60) {
 	__shared__ int scratch[32];
 	__shared__ float s_min_gain;
-	const int t = blockIdx.x, t0 = t & ~1;
-	if (!track_exists(rec, t)) { if (threadIdx.x == 0) t60[t] = 0.0f; return; }
-	const bool stereo = rec[t >> 1].kind == EAR_B200_STEREO;
-	bool has_samples = range[2 * t0 + 1] > 0 || (stereo && range[2 * t0 + 3] > 0);
+	const int t = blockIdx.x, t0 = t - t % tpr;
+	if (!track_exists(rec, t, tpr)) { if (threadIdx.x == 0) t60[t] = 0.0f; return; }
+	const bool stereo = rec[t / tpr].kind == EAR_B200_STEREO;
+	bool has_samples = track_real[t0] > 0 || (stereo && track_real[t0 + 1] > 0);
 	uint32_t len = 0;
 	if (has_samples) len = max(track_len[t0], stereo ? track_len[t0 + 1] : 0u);
 	if (len == 0) len = 1;

@@ -31,14 +31,27 @@ struct SceneDev {
 	int32_t leaf_vote;        // lanes that must wait on a leaf before the warp runs a leaf step
 	int32_t fetch_vote;       // idle lanes that trigger a fetch of new work in the persistent kernels
 	int32_t vis_cap;          // visibility-map texel lists longer than this are traced through the BVH instead
+	int2* spill;              // [spill_rows][spill_threads] overflow of the shared-memory traversal stacks
+	int32_t spill_threads;    // columns of `spill`; kernels that walk the BVH launch at most this many threads
+	int32_t spill_rows;       // sized at scene creation from the depth of the tree: 3 pushes per level at most
+	const float4* emitters;   // emitter triangles of mesh sources: (v0, area) (v1, 0) (v2, 0) (normal, 0), or null
 };
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
-constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes spill to local memory
-constexpr int kStackSpill = 40;
+constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes go to SceneDev::spill
+constexpr int kStackSpill = 160;        // host emulation only: rows of its local overflow array
 constexpr int kLeafVote = 12;           // do a leaf step once this many lanes wait on a leaf
 constexpr float kKappa = 1.0f / 1024.0f;
 
+// L2 residency (EARB_L2_HINTS, default on): the scene image (nodes + triangle records, 85 MB for the 1M-triangle
+// hall) is re-read by every ray and fits the 126 MB L2, while the ray pool and the work lists (GBs per launch) stream
+// through once.  Image loads ask L2 to keep their lines (evict_last), stream loads / stores to drop theirs first
+// (evict_first); without the hints the streams evicted the tree (L2 hit rate 62 % in the closest-hit kernel,
+// profiles/r1_ncu_final_wf_traverse_kernel_16mi.txt).  256-bit accesses carry the priority in the instruction,
+// narrower ones take it from a createpolicy descriptor.
+#ifndef EARB_L2_HINTS
+#define EARB_L2_HINTS 1
+#endif
 struct F8 { float4 lo, hi; };
 __device__ __forceinline__ F8 ldg256(const float4* p) {
 	F8 r;
@@ -46,12 +59,89 @@ __device__ __forceinline__ F8 ldg256(const float4* p) {
 	r.lo = p[0]; r.hi = p[1];
 	return r;
 #else
+#if EARB_L2_HINTS
+	asm volatile("ld.global.nc.L2::evict_last.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#else
 	asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+#endif
 	             : "=f"(r.lo.x), "=f"(r.lo.y), "=f"(r.lo.z), "=f"(r.lo.w), "=f"(r.hi.x), "=f"(r.hi.y), "=f"(r.hi.z), "=f"(r.hi.w)
 	             : "l"(p));
 	return r;
 #endif
 }
+#ifndef EARB_HOST_EMULATION
+__device__ __forceinline__ uint64_t l2_policy_keep() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_stream() {
+	uint64_t pol;
+	asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+	return pol;
+}
+#endif
+// 128-bit load of scene-image data (third quarter of a triangle record, normals, materials)
+__device__ __forceinline__ float4 ldg_keep(const float4* p) {
+#if defined(EARB_HOST_EMULATION) || !EARB_L2_HINTS
+	return __ldg(p);
+#else
+	float4 r;
+	asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+	             : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(l2_policy_keep()));
+	return r;
+#endif
+}
+#ifndef EARB_HOST_EMULATION
+// streamed pool / list accesses: 16-, 8- and 4-byte forms
+template <class T> __device__ __forceinline__ T ld_stream(const T* p);
+template <class T> __device__ __forceinline__ void st_stream(T* p, T v);
+#if EARB_L2_HINTS
+template <> __device__ __forceinline__ float4 ld_stream<float4>(const float4* p) {
+	float4 r;
+	asm volatile("ld.global.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p), "l"(l2_policy_stream()));
+	return r;
+}
+template <> __device__ __forceinline__ uint4 ld_stream<uint4>(const uint4* p) {
+	uint4 r;
+	asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(l2_policy_stream()));
+	return r;
+}
+template <> __device__ __forceinline__ uint2 ld_stream<uint2>(const uint2* p) {
+	uint2 r;
+	asm volatile("ld.global.L2::cache_hint.v2.u32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_policy_stream()));
+	return r;
+}
+template <> __device__ __forceinline__ int2 ld_stream<int2>(const int2* p) {
+	int2 r;
+	asm volatile("ld.global.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(l2_policy_stream()));
+	return r;
+}
+template <> __device__ __forceinline__ int ld_stream<int>(const int* p) {
+	int r;
+	asm volatile("ld.global.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(l2_policy_stream()));
+	return r;
+}
+template <> __device__ __forceinline__ void st_stream<float4>(float4* p, float4 v) {
+	asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(l2_policy_stream()) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<uint4>(uint4* p, uint4 v) {
+	asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(l2_policy_stream()) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<uint2>(uint2* p, uint2 v) {
+	asm volatile("st.global.L2::cache_hint.v2.u32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(l2_policy_stream()) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<int2>(int2* p, int2 v) {
+	asm volatile("st.global.L2::cache_hint.v2.s32 [%0], {%1,%2}, %3;" ::"l"(p), "r"(v.x), "r"(v.y), "l"(l2_policy_stream()) : "memory");
+}
+template <> __device__ __forceinline__ void st_stream<int>(int* p, int v) {
+	asm volatile("st.global.L2::cache_hint.s32 [%0], %1, %2;" ::"l"(p), "r"(v), "l"(l2_policy_stream()) : "memory");
+}
+#else
+template <class T> __device__ __forceinline__ T ld_stream(const T* p) { return *p; }
+template <class T> __device__ __forceinline__ void st_stream(T* p, T v) { *p = v; }
+#endif
+#endif
 
 struct RaySetup { float idx, idy, idz, oox, ooy, ooz; };
 __device__ __forceinline__ RaySetup make_setup(V3 o, V3 d) {
@@ -65,20 +155,22 @@ __device__ __forceinline__ RaySetup make_setup(V3 o, V3 d) {
 	return s;
 }
 
-// per-lane stack: shared memory first, local memory beyond kStackEntries (never reached by SAH trees
-// of realistic scenes; the builder bounds the depth so even adversarial input cannot overflow both)
 // Per-lane traversal stack: kStackEntries entries in shared memory (column `threadIdx.x` of an [entry][thread]
-// array: conflict-free), deeper pushes spill to a local array.  On the device the shared part is addressed through
-// explicit shared-space instructions: stores through a generic pointer made the compiler assume they might alias the
-// struct itself (which lives in local memory because of the spill array), so it kept `sp` in local memory and
-// re-loaded it around every push and pop.
+// array: conflict-free), addressed through explicit shared-space instructions.  Deeper pushes (never seen with SAH
+// trees of the benchmark scenes; a 4-wide node pushes at most 3 entries per level, and scene creation checks
+// 3 * depth against the total capacity) overflow into a GLOBAL side buffer, one column per thread.  The first
+// version spilled into a local array: indexing it dynamically forced the whole traversal state into a 400-byte
+// local frame (33.8 M local stores per launch, profiles/r1_ncu_final_wf_traverse_kernel_16mi.txt).
 struct LaneStack {
 #ifdef EARB_HOST_EMULATION
 	int2* smem;       // this lane's column: entry k at smem[k * stride]
 	int stride;
+	int2 spill[kStackSpill];
 	__device__ __forceinline__ void bind(int2* column, int stride_entries) { smem = column; stride = stride_entries; }
 	__device__ __forceinline__ void put(int k, int2 e) { smem[k * stride] = e; }
 	__device__ __forceinline__ int2 get(int k) const { return smem[k * stride]; }
+	__device__ __forceinline__ void put_deep(const SceneDev&, int k, int2 e) { spill[k] = e; }
+	__device__ __forceinline__ int2 get_deep(const SceneDev&, int k) const { return spill[k]; }
 #else
 	uint32_t base;    // shared-space byte address of this lane's column
 	uint32_t pitch;   // bytes between consecutive entries of a column
@@ -94,18 +186,22 @@ struct LaneStack {
 		asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(base + (uint32_t)k * pitch));
 		return e;
 	}
+	static __device__ __forceinline__ size_t deep_at(const SceneDev& sc, int k) {
+		return (size_t)k * (size_t)sc.spill_threads + (size_t)(blockIdx.x * blockDim.x + threadIdx.x);
+	}
+	__device__ __forceinline__ void put_deep(const SceneDev& sc, int k, int2 e) { sc.spill[deep_at(sc, k)] = e; }
+	__device__ __forceinline__ int2 get_deep(const SceneDev& sc, int k) const { return sc.spill[deep_at(sc, k)]; }
 #endif
-	int2 spill[kStackSpill];
 	int sp;
-	__device__ __forceinline__ void push(int32_t node, float key) {
+	__device__ __forceinline__ void push(const SceneDev& sc, int32_t node, float key) {
 		const int2 e = make_int2(node, __float_as_int(key));
 		if (sp < kStackEntries) put(sp, e);
-		else if (sp < kStackEntries + kStackSpill) spill[sp - kStackEntries] = e;
+		else if (sp < kStackEntries + sc.spill_rows) put_deep(sc, sp - kStackEntries, e);
 		++sp;
 	}
-	__device__ __forceinline__ int2 pop() {
+	__device__ __forceinline__ int2 pop(const SceneDev& sc) {
 		--sp;
-		return sp < kStackEntries ? get(sp) : spill[min(sp - kStackEntries, kStackSpill - 1)];
+		return sp < kStackEntries ? get(sp) : get_deep(sc, min(sp - kStackEntries, sc.spill_rows - 1));
 	}
 };
 
@@ -134,7 +230,7 @@ __device__ __forceinline__ void pop_next(const SceneDev& sc, TravState& ts) {
 	const float limit = EXACT ? ts.best_t : fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
 	int32_t node = kEmptyChildDev;
 	while (ts.st.sp > 0 && node == kEmptyChildDev) {   // one exit test, no break: the lanes reconverge every round (-1 %)
-		const int2 e = ts.st.pop();
+		const int2 e = ts.st.pop(sc);
 		if (__int_as_float(e.y) <= limit) node = e.x;
 	}
 	ts.node = node;
@@ -148,6 +244,22 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {   // fp16 bits
 __device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) { const uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
 __device__ __forceinline__ int32_t pick4(int32_t c0, int32_t c1, int32_t c2, int32_t c3, uint32_t k) {
 	return k == 0u ? c0 : k == 1u ? c1 : k == 2u ? c2 : c3;
+}
+
+#ifndef EARB_DECODE_PRMT
+#define EARB_DECODE_PRMT 1
+#endif
+#ifdef EARB_HOST_EMULATION
+static float g_emul_decode_bias = 0.00390625f;
+#endif
+// float 2^15 + byte k of w (see node_step)
+__device__ __forceinline__ float plane_byte(uint32_t w, int k) {
+#ifdef EARB_HOST_EMULATION
+	return __uint_as_float(0x47000000u | (((w >> (8 * k)) & 0xffu) << 8));
+#else
+	// result bytes (low to high): 0x00, byte k of w, 0x00, 0x47  <-  selector nibbles 4, k, 5, 7 over {w, 0x47000000}
+	return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504u | ((uint32_t)k << 4)));
+#endif
 }
 
 // one inner-node step for a lane sitting on an inner (4-wide, 8-bit quantised) node
@@ -171,13 +283,39 @@ __device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
 	const uint32_t nz = ngz ? qhz : qlz, fz = ngz ? qlz : qhz;
 	const float hi_rel = fmaf(ts.best_t, kKappa, ts.best_t) + sc.s0;
 	const uint32_t sl01 = __float_as_uint(n1.hi.z), sl23 = __float_as_uint(n1.hi.w);
+#if EARB_DECODE_PRMT
+	// Plane bytes become floats without the conversion unit: one byte permute builds the bit pattern of 2^15 + q
+	// (exponent 0x47, the byte in mantissa bits 8..15, where one ulp of 2^15 is 2^-8 ... so q lands on weight 1) and the
+	// offset 2^15 * a is folded into the per-axis constant.  Folding rounds that constant at magnitude 2^15 |a|
+	// (error <= 2^-9 grid steps in t); the near constant is lowered and the far one raised by 2^-8 grid steps --
+	// -(2^15 +- 2^-8) are exact floats -- so the decoded slab still contains the quantised box.  (I2F.U8 runs on
+	// the quarter-rate XU pipe: 24 per node step kept it 45 % busy.)
+#ifdef EARB_HOST_EMULATION
+	const float bias = g_emul_decode_bias;   // test knob: 0 shows that the margin is load-bearing (tests/test_host_logic.py)
+#else
+	const float bias = 0.00390625f;          // 2^-8 grid steps
+#endif
+	const float m_lo = -(32768.0f + bias), m_hi = -(32768.0f - bias);
+	const float m_near_x = ngx ? m_hi : m_lo, m_far_x = ngx ? m_lo : m_hi;
+	const float m_near_y = ngy ? m_hi : m_lo, m_far_y = ngy ? m_lo : m_hi;
+	const float m_near_z = ngz ? m_hi : m_lo, m_far_z = ngz ? m_lo : m_hi;
+	const float bnx = fmaf(ax, m_near_x, bx), bfx = fmaf(ax, m_far_x, bx);
+	const float bny = fmaf(ay, m_near_y, by), bfy = fmaf(ay, m_far_y, by);
+	const float bnz = fmaf(az, m_near_z, bz), bfz = fmaf(az, m_far_z, bz);
+#endif
 	uint32_t key[4];
 #pragma unroll
 	for (int k = 0; k < 4; ++k) {
+#if EARB_DECODE_PRMT
+		const float tnx = fmaf(plane_byte(nx, k), ax, bnx), tfx = fmaf(plane_byte(fx, k), ax, bfx);
+		const float tny = fmaf(plane_byte(ny, k), ay, bny), tfy = fmaf(plane_byte(fy, k), ay, bfy);
+		const float tnz = fmaf(plane_byte(nz, k), az, bnz), tfz = fmaf(plane_byte(fz, k), az, bfz);
+#else
 		const int sh = 8 * k;
 		const float tnx = fmaf((float)((nx >> sh) & 0xffu), ax, bx), tfx = fmaf((float)((fx >> sh) & 0xffu), ax, bx);
 		const float tny = fmaf((float)((ny >> sh) & 0xffu), ay, by), tfy = fmaf((float)((fy >> sh) & 0xffu), ay, by);
 		const float tnz = fmaf((float)((nz >> sh) & 0xffu), az, bz), tfz = fmaf((float)((fz >> sh) & 0xffu), az, bz);
+#endif
 		float slack = 0.0f;
 		if (EXACT) slack = half_bits_to_float(((k < 2 ? sl01 : sl23) >> (16 * (k & 1))) & 0xffffu);
 		const float lo_t = EXACT ? -slack : -sc.s0;
@@ -209,9 +347,9 @@ __device__ __forceinline__ void node_step(const SceneDev& sc, TravState& ts) {
 		sp += h1 ? 1 : 0;
 		ts.st.sp = sp;
 	} else {
-		if (h3) ts.st.push(e3.x, __int_as_float(e3.y));
-		if (h2) ts.st.push(e2.x, __int_as_float(e2.y));
-		if (h1) ts.st.push(e1.x, __int_as_float(e1.y));
+		if (h3) ts.st.push(sc, e3.x, __int_as_float(e3.y));
+		if (h2) ts.st.push(sc, e2.x, __int_as_float(e2.y));
+		if (h1) ts.st.push(sc, e1.x, __int_as_float(e1.y));
 	}
 	ts.node = pick4(c0, c1, c2, c3, key[0] & 3u);
 }
@@ -225,7 +363,7 @@ __device__ __forceinline__ void leaf_step(const SceneDev& sc, TravState& ts) {
 	const int32_t first = code >> 3, rest = code & 7;
 	const float4* rec = sc.tris + 4 * (size_t)first;
 	const F8 r01 = ldg256(rec);
-	const float4 r2 = __ldg(rec + 2);
+	const float4 r2 = ldg_keep(rec + 2);
 	float t;
 	if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
 		if (ANY_HIT) {
@@ -251,7 +389,7 @@ __device__ __forceinline__ void pend_step(const SceneDev& sc, TravState& ts, int
 	const int32_t first = code >> 3, rest = code & 7;
 	const float4* rec = sc.tris + 4 * (size_t)first;
 	const F8 r01 = ldg256(rec);
-	const float4 r2 = __ldg(rec + 2);
+	const float4 r2 = ldg_keep(rec + 2);
 	float t;
 	if (moeller_trumbore(mk(r01.lo.x, r01.lo.y, r01.lo.z), mk(r01.hi.x, r01.hi.y, r01.hi.z), mk(r2.x, r2.y, r2.z), ts.o, ts.d, t)) {
 		if (ANY_HIT) {

@@ -155,13 +155,13 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 		bool visible = false, fallback = false;
 		uint2 q = make_uint2(0u, 0u);
 		if (i < total) {
-			q = pool.q_list[i];
+			q = ld_stream(pool.q_list + i);
 			const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u), r = q.x >> pool.slot_bits, c = q.y & 0xffffu;
 			const int mi = map_of[c * p.n_rec + r];
 			if (mi < 0) fallback = true;
 			else {
 				const VisMapDev mp = maps[mi];
-				const float4 s0 = pool.sh0[slot];
+				const float4 s0 = ld_stream(pool.sh0 + slot);
 				const V3 pnt = mk(s0.x, s0.y, s0.z), x = mk(mp.x[0], mp.x[1], mp.x[2]);
 				const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
 				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1] & ~kVisOverlong;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 						for (int j = 0; j < kVisBatch; ++j) {
 							const float4* rec = sc.tris + 4 * (size_t)item[j];
 							r01[j] = ldg256(rec);
-							r2[j] = __ldg(rec + 2);
+							r2[j] = ldg_keep(rec + 2);
 						}
 #pragma unroll
 						for (int j = 0; j < kVisBatch; ++j) {
@@ -201,13 +201,13 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 			int b = 0;
 			if (lane == 0) b = atomicAdd(pool.counts + 2, __popc(m_vis));
 			b = __shfl_sync(0xffffffffu, b, 0);
-			if (visible) pool.vis_list[b + __popc(m_vis & lt_mask)] = q;
+			if (visible) st_stream(pool.vis_list + b + __popc(m_vis & lt_mask), q);
 		}
 		if (m_fb) {
 			int b = 0;
 			if (lane == 0) b = atomicAdd(pool.counts + 5, __popc(m_fb));
 			b = __shfl_sync(0xffffffffu, b, 0);
-			if (fallback) q_bvh[b + __popc(m_fb & lt_mask)] = q;
+			if (fallback) st_stream(q_bvh + b + __popc(m_fb & lt_mask), q);
 		}
 	}
 }

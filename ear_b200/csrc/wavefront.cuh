@@ -43,6 +43,9 @@ struct WfPool {
 	uint2* q_list;      // [N*R] occlusion queries: x = slot | recorder << 24, y = context | (bounce & 1) << 31
 	uint2* vis_list;    // [N*R] the unoccluded ones
 	int* counts;        // 0 trav_count, 1 q_count, 2 vis_count, 3 trav_cursor, 4 q_cursor
+	uint2* vis_sorted;  // [N*R] vis_list counting-sorted by (context, recorder) for the windowed splat (aliases q_tmp, dead by then)
+	int* pair_count;    // [pairs] entries per (context, recorder) / scatter cursor
+	int* pair_base;     // [pairs + 1] exclusive scan of the counts
 	const float4* qx;   // harness only: explicit segment end point per query (else the recorder position)
 	int q_count_idx, q_cursor_idx;   // which counters the any-hit kernel uses (1, 4 normally; 5, 6 for the map fallback list)
 	int n_slots;
@@ -61,8 +64,11 @@ constexpr int kMaxSlotBits = 28;   // a query word is slot | recorder << slot_bi
 // ---------------------------------------------------------------------------------------------------
 // K2 / K4: persistent traversal with dynamic fetch
 // ---------------------------------------------------------------------------------------------------
+#ifndef EARB_TRAV_MIN_BLOCKS
+#define EARB_TRAV_MIN_BLOCKS 8
+#endif
 template <bool ANY_HIT, bool EXACT>
-__global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+__global__ void __launch_bounds__(kBlock, ANY_HIT || EXACT ? 6 : EARB_TRAV_MIN_BLOCKS) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {
 	extern __shared__ int2 stack_smem[];
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
@@ -100,10 +106,10 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 					int base = 0;
 					if (lane == 0) base = atomicAdd(pool.counts + 2, __popc(m_vis));
 					base = __shfl_sync(0xffffffffu, base, 0);
-					if (visible) pool.vis_list[base + __popc(m_vis & lt_mask)] = job;
+					if (visible) st_stream(pool.vis_list + base + __popc(m_vis & lt_mask), job);
 				}
 			} else if (idle && has_job) {
-				pool.hit[job.x] = make_int2(__float_as_int(ts.best_t), ts.best_slot);
+				st_stream(pool.hit + job.x, make_int2(__float_as_int(ts.best_t), ts.best_slot));
 			}
 			int base = 0;
 			const int want = __popc(m_idle);
@@ -115,17 +121,17 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 				has_job = my < total;
 				if (has_job) {
 					if (ANY_HIT) {
-						job = pool.q_list[my];
+						job = ld_stream(pool.q_list + my);
 						const uint32_t slot = job.x & ((1u << pool.slot_bits) - 1u), r = job.x >> pool.slot_bits, c = job.y & 0xffffu;
-						const float4 s0 = pool.sh0[slot];
+						const float4 s0 = ld_stream(pool.sh0 + slot);
 						V3 x;
 						if (pool.qx) { const float4 e = pool.qx[my]; x = mk(e.x, e.y, e.z); }
 						else { const float* rp = p.rec[(size_t)c * p.n_rec + r].position; x = mk(rp[0], rp[1], rp[2]); }
 						const V3 pnt = mk(s0.x, s0.y, s0.z);
 						ts.begin<true>(pnt, vsub(x, pnt));   // LineSeg(p, x) = Ray(p, x - p)
 					} else {
-						job.x = (uint32_t)pool.trav_list[my];
-						const float4 o4 = pool.ro[job.x], d4 = pool.rd[job.x];
+						job.x = (uint32_t)ld_stream(pool.trav_list + my);
+						const float4 o4 = ld_stream(pool.ro + job.x), d4 = ld_stream(pool.rd + job.x);
 						ts.begin<false>(mk(o4.x, o4.y, o4.z), mk(d4.x, d4.y, d4.z));
 					}
 				}
@@ -141,10 +147,10 @@ __global__ void __launch_bounds__(kBlock, 6) wf_traverse_kernel(SceneDev sc, WfP
 					int base = 0;
 					if (lane == 0) base = atomicAdd(pool.counts + 2, __popc(m_vis));
 					base = __shfl_sync(0xffffffffu, base, 0);
-					if (visible) pool.vis_list[base + __popc(m_vis & lt_mask)] = job;
+					if (visible) st_stream(pool.vis_list + base + __popc(m_vis & lt_mask), job);
 				}
 			} else if (has_job) {
-				pool.hit[job.x] = make_int2(__float_as_int(ts.best_t), ts.best_slot);
+				st_stream(pool.hit + job.x, make_int2(__float_as_int(ts.best_t), ts.best_slot));
 			}
 			break;
 		}
@@ -243,20 +249,20 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 	for (int i = tid; i < n_trav; i += 4 * stride) {
 		uint2 e[4]; int pos[4];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) e[k] = pool.trav_tmp[i + k * stride];
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) e[k] = ld_stream(pool.trav_tmp + i + k * stride);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pos[k] = atomicAdd(pool.bins + e[k].y, 1) + pool.bins[kRayBins + kSortBins + (e[k].y >> 10)];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pool.trav_list[pos[k]] = (int)e[k].x;
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) st_stream(pool.trav_list + pos[k], (int)e[k].x);
 	}
 	for (int i = tid; i < n_q; i += 4 * stride) {
 		uint2 e[4]; int pos[4];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = pool.q_tmp[i + k * stride];
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = ld_stream(pool.q_tmp + i + k * stride);
 #pragma unroll
 		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kRayBins + ((e[k].y >> 16) & 0x7fffu), 1) + pool.bins[kRayBins + kSortBins + kRayScanBlocks + ((e[k].y >> 26) & 0x1fu)];
 #pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pool.q_list[pos[k]] = e[k];
+		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) st_stream(pool.q_list + pos[k], e[k]);
 	}
 }
 
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
-	uint4 m = pool.rm[slot];
+	uint4 m = ld_stream(pool.rm + slot);
 	int bounce = (int)(m.z >> 16);
 	int c = (int)(m.z & 0xffffu);
 	bool alive = bounce != 0;
@@ -317,8 +323,8 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 
 	// ---- K3 (first half): consume the hit of the previous launch (Scene::Bounce, src/Scene.cpp:49-63) ----
 	if (alive) {
-		ro = pool.ro[slot]; rd = pool.rd[slot];
-		const int2 h = pool.hit[slot];
+		ro = ld_stream(pool.ro + slot); rd = ld_stream(pool.rd + slot);
+		const int2 h = ld_stream(pool.hit + slot);
 		++lc.segments;                                                            // one Scene::Bounce call
 		o = mk(ro.x, ro.y, ro.z);
 		const V3 d = mk(rd.x, rd.y, rd.z);
@@ -327,8 +333,8 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		if (h.y < 0) alive = false;                                               // escaped (src/Scene.cpp:166)
 		else {
 			t = __int_as_float(h.x);
-			const float4 r1 = __ldg(sc.tris + 4 * (size_t)h.y + 1);
-			const float4 r3 = __ldg(sc.tris + 4 * (size_t)h.y + 3);
+			const float4 r1 = ldg_keep(sc.tris + 4 * (size_t)h.y + 1);
+			const float4 r3 = ldg_keep(sc.tris + 4 * (size_t)h.y + 3);
 			prev_dir = vnormalized(d);                                            // prev_ray_dir (:277) of this bounce
 			const V3 tri_n = mk(r3.x, r3.y, r3.z);
 			pnt = vadd(o, vscale(d, t));                                          // src/Mesh.cpp:48
@@ -412,10 +418,10 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		else {
 			shaded = p.n_rec > 0;
 			if (shaded) {
-				pool.sh0[slot] = ro;
-				pool.sh1[slot] = make_float4(n.x, n.y, n.z, path);
-				pool.sh2[slot] = make_float4(prev_dir.x, prev_dir.y, prev_dir.z,
-				                             refract ? __int_as_float(__float_as_int(spec) | (int)0x80000000) : spec);
+				st_stream(pool.sh0 + slot, ro);
+				st_stream(pool.sh1 + slot, make_float4(n.x, n.y, n.z, path));
+				st_stream(pool.sh2 + slot, make_float4(prev_dir.x, prev_dir.y, prev_dir.z,
+				                             refract ? __int_as_float(__float_as_int(spec) | (int)0x80000000) : spec));
 			}
 			if ((double)intensity < 0.00000001) alive = false;                    // :275
 			else if (bounce + 1 >= p.max_bounces) alive = false;                  // loop bound (:143)
@@ -454,19 +460,19 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 				if (pool.sort_queries) {
 					const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
 					atomicAdd(pool.bins + kRayBins + bin, 1);
-					pool.q_tmp[base + __popc(mq & lt_mask)] =
-					    make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31));
+					st_stream(pool.q_tmp + base + __popc(mq & lt_mask),
+					          make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31)));
 				} else {
-					pool.q_list[base + __popc(mq & lt_mask)] =
-					    make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31));
+					st_stream(pool.q_list + base + __popc(mq & lt_mask),
+					          make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31)));
 				}
 			}
 		}
 	}
 	bounce = alive ? bounce + 1 : 0;
 	m.z = (uint32_t)c | ((uint32_t)bounce << 16);
-	pool.rm[slot] = m;
-	if (alive) { pool.ro[slot] = ro; pool.rd[slot] = rd; }
+	st_stream(pool.rm + slot, m);
+	if (alive) { st_stream(pool.ro + slot, ro); st_stream(pool.rd + slot, rd); }
 	// ---- K6 compaction: slots that need a closest-hit query next, binned by (direction octant, origin cell) ----
 	const unsigned live = __ballot_sync(0xffffffffu, alive);
 	if (live) {
@@ -476,7 +482,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		if (alive) {
 			const uint32_t bin = ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
 			atomicAdd(pool.bins + bin, 1);
-			pool.trav_tmp[base + __popc(live & lt_mask)] = make_uint2((uint32_t)slot, bin);
+			st_stream(pool.trav_tmp + base + __popc(live & lt_mask), make_uint2((uint32_t)slot, bin));
 		}
 	}
 	// the launch loop stops when no slot holds a ray and the shard's queue is dry
@@ -491,43 +497,208 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 // ---------------------------------------------------------------------------------------------------
 // K5: contribution weight (src/Scene.cpp:197-263) + Recorder::Record for every visible query
 // ---------------------------------------------------------------------------------------------------
+// weight of one visible query; false when the reference rejects it (INVALID_FLOAT, src/Scene.cpp:254)
+__device__ __forceinline__ bool splat_weight(const WfPool& pool, const RenderParams& p, uint2 q, const ear_b200_recorder& rec, uint32_t slot,
+                                             uint32_t c, V3& lsdir, float& contrib, float& dist) {
+	const float4 s0 = ld_stream(pool.sh0 + slot), s1 = ld_stream(pool.sh1 + slot), s2 = ld_stream(pool.sh2 + slot);
+	const V3 pnt = mk(s0.x, s0.y, s0.z), n = mk(s1.x, s1.y, s1.z), prev_dir = mk(s2.x, s2.y, s2.z);
+	const bool refract = (__float_as_uint(s2.w) >> 31) != 0u;   // sign bit carries the bounce type
+	const float spec = fabsf(s2.w);
+	const float intensity = s0.w, path = s1.w;
+	const float af = p.ctx[c].absorption_factor;
+	const V3 segv = vsub(mk(rec.position[0], rec.position[1], rec.position[2]), pnt);
+	lsdir = vnormalized(segv);
+	float factor;
+	if (spec > 1.5f) factor = 1.0f;                                              // bounce 0 of a mesh source: no surface term (:216)
+	else if (!refract) {                                                         // :219-235
+		const V3 rv = vreflect(prev_dir, n);
+		const float diff = -vdot(n, prev_dir);
+		const float dsp = vdot(rv, lsdir);
+		const float specf = (0.0f < dsp) ? dsp : 0.0f;
+		factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+	} else {                                                                     // :236-247
+		const float diff = vdot(n, prev_dir);
+		const float dsp = vdot(prev_dir, lsdir);
+		const float specf = (0.0f < dsp) ? dsp : 0.0f;
+		factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+	}
+	contrib = spec > 1.5f ? intensity : fmul(intensity, factor);
+	const float l = vlength(segv);                                               // :250
+	contrib = fmul(contrib, pow_ref_hoisted(af, pool.ctx_log2af[c], l));
+	contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
+	if (invalid_float(contrib)) return false;
+	if (q.y >> 31) contrib = fmul(contrib, -1.0f);                               // odd bounce (:257)
+	dist = fadd(path, l);
+	return true;
+}
+
 __global__ void __launch_bounds__(256) wf_splat_kernel(WfPool pool, RenderParams p) {
 	const int total = pool.counts[2];
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-		const uint2 q = pool.vis_list[i];
+		const uint2 q = ld_stream(pool.vis_list + i);
 		const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u), r = q.x >> pool.slot_bits, c = q.y & 0xffffu;
-		const float4 s0 = pool.sh0[slot], s1 = pool.sh1[slot], s2 = pool.sh2[slot];
 		const ear_b200_recorder& rec = p.rec[(size_t)c * p.n_rec + r];
-		const V3 pnt = mk(s0.x, s0.y, s0.z), n = mk(s1.x, s1.y, s1.z), prev_dir = mk(s2.x, s2.y, s2.z);
-		const bool refract = (__float_as_uint(s2.w) >> 31) != 0u;   // sign bit carries the bounce type
-		const float spec = fabsf(s2.w);
-		const float intensity = s0.w, path = s1.w;
-		const float af = p.ctx[c].absorption_factor;
-		const V3 segv = vsub(mk(rec.position[0], rec.position[1], rec.position[2]), pnt);
-		const V3 lsdir = vnormalized(segv);
-		float factor;
-		if (!refract) {                                                              // :219-235
-			const V3 rv = vreflect(prev_dir, n);
-			const float diff = -vdot(n, prev_dir);
-			const float dsp = vdot(rv, lsdir);
-			const float specf = (0.0f < dsp) ? dsp : 0.0f;
-			factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
-		} else {                                                                     // :236-247
-			const float diff = vdot(n, prev_dir);
-			const float dsp = vdot(prev_dir, lsdir);
-			const float specf = (0.0f < dsp) ? dsp : 0.0f;
-			factor = fadd(fmul(fmul(spec, 1001.0f), pow_ref(specf, 1000.0f)), fmul(fsub(1.0f, spec), diff));
+		V3 lsdir; float contrib, dist;
+		if (!splat_weight(pool, p, q, rec, slot, c, lsdir, contrib, dist)) continue;
+		const size_t track = ((size_t)c * p.n_rec + r) * p.tpr;
+		GlobalSink sink = {p.hist + track * p.n_bins, p.range + track * 2, p.n_bins};
+		record(rec, sink, p.n_bins, lsdir, contrib, fdiv(dist, 343.0f), dist, p.ctx[c].band, lc);
+	}
+	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
+	if ((threadIdx.x & 31) == 0 && (v3 | v4 | v5)) {
+		atomicAdd(p.counters + 3, v3); atomicAdd(p.counters + 4, v4);
+		if (v5) atomicAdd(p.counters + 5, v5);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5, privatised form (EAR_B200_SPLAT=window): the visible queries of an iteration are counting-sorted by
+// (context, recorder); a block then owns a run of one recorder's contributions, accumulates them into a
+// shared-memory copy of a TIME WINDOW of that recorder's track(s) and flushes the window once, lane i of a warp
+// adding bin i -- one coalesced RED per 32 touched bins instead of one RED per ramp sample.  It works because a pool
+// that runs in lockstep (bounce cap << pool generations) delivers, in one iteration, rays of nearly the same bounce
+// number: their arrival times cluster in a window a few thousand bins wide.  Samples outside the window go
+// straight to the global histogram, so the result is the same sum in a different order.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kPrivWindow = 16384;    // floats of shared memory per block (one mono track, or 2 x 8192 for stereo)
+constexpr int kPrivChunk = 32768;     // visible queries per block pass
+constexpr int kPrivMaxPairs = 65536;  // (context, recorder) pairs the sort supports; beyond that the direct form runs
+
+__global__ void __launch_bounds__(256) wf_vis_count_kernel(WfPool pool, RenderParams p) {
+	const int total = pool.counts[2];
+	const int stride = gridDim.x * blockDim.x;
+	for (int base = blockIdx.x * blockDim.x; base < total; base += stride) {   // warp-uniform trip count
+		const int i = base + threadIdx.x;
+		const bool on = i < total;
+		int pair = -1;
+		if (on) {
+			const uint2 q = ld_stream(pool.vis_list + i);
+			pair = (int)(q.y & 0xffffu) * p.n_rec + (int)(q.x >> pool.slot_bits);
 		}
-		float contrib = fmul(intensity, factor);
-		const float l = vlength(segv);                                               // :250
-		contrib = fmul(contrib, pow_ref_hoisted(af, pool.ctx_log2af[c], l));
-		contrib = fmul(contrib, fdiv(2.0f, fmul(fmul(fmul(4.0f, PI_F), l), l)));     // INV_HEMI_2, :252
-		if (invalid_float(contrib)) continue;
-		if (q.y >> 31) contrib = fmul(contrib, -1.0f);                               // odd bounce (:257)
-		const size_t track = ((size_t)c * p.n_rec + r) * 2;
-		record(rec, p.hist + track * p.n_bins, p.range + track * 2, p.n_bins, lsdir, contrib, fdiv(fadd(path, l), 343.0f),
-		       fadd(path, l), p.ctx[c].band, lc);
+		// one atomic per distinct pair in the warp
+		const unsigned peers = __match_any_sync(0xffffffffu, pair);
+		if (on && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(pool.pair_count + pair, __popc(peers));
+	}
+}
+// exclusive scan of the pair counts (one block; n_pairs <= kPrivMaxPairs), cursors reset
+__global__ void __launch_bounds__(1024) wf_vis_scan_kernel(WfPool pool, int n_pairs) {
+	__shared__ int warp_tot[32];
+	__shared__ int carry;
+	if (threadIdx.x == 0) carry = 0;
+	__syncthreads();
+	for (int base = 0; base < n_pairs; base += 1024) {
+		const int i = base + threadIdx.x;
+		const int v = i < n_pairs ? pool.pair_count[i] : 0;
+		int total;
+		const int ex = block_exclusive_scan(v, warp_tot, total);
+		if (i < n_pairs) { pool.pair_base[i] = carry + ex; pool.pair_count[i] = 0; }
+		__syncthreads();
+		if (threadIdx.x == 0) carry += total;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) pool.pair_base[n_pairs] = carry;
+}
+__global__ void __launch_bounds__(256) wf_vis_scatter_kernel(WfPool pool, RenderParams p) {
+	const int total = pool.counts[2];
+	const int stride = gridDim.x * blockDim.x;
+	const int lane = threadIdx.x & 31;
+	for (int base = blockIdx.x * blockDim.x; base < total; base += stride) {
+		const int i = base + threadIdx.x;
+		const bool on = i < total;
+		int pair = -1;
+		uint2 q = make_uint2(0u, 0u);
+		if (on) {
+			q = ld_stream(pool.vis_list + i);
+			pair = (int)(q.y & 0xffffu) * p.n_rec + (int)(q.x >> pool.slot_bits);
+		}
+		const unsigned peers = __match_any_sync(0xffffffffu, pair);
+		const int leader = __ffs(peers) - 1;
+		int at = 0;
+		if (on && lane == leader) at = atomicAdd(pool.pair_count + pair, __popc(peers));   // pair_count doubles as the cursor
+		at = __shfl_sync(0xffffffffu, at, leader);
+		if (on) st_stream(pool.vis_sorted + pool.pair_base[pair] + at + __popc(peers & ((1u << lane) - 1u)), q);
+	}
+}
+
+__device__ __forceinline__ int block_sum_i(int v, int* scratch) {
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	v = (threadIdx.x & 31) < (blockDim.x >> 5) ? scratch[threadIdx.x & 31] : 0;
+	for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	__syncthreads();
+	return v;
+}
+__device__ __forceinline__ int block_min_i32(int v, int* scratch) {
+	for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+	__syncthreads();
+	v = (threadIdx.x & 31) < (blockDim.x >> 5) ? scratch[threadIdx.x & 31] : 0x7fffffff;
+	for (int o = 16; o; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+	__syncthreads();
+	return v;
+}
+
+__global__ void __launch_bounds__(256) wf_splat_window_kernel(WfPool pool, RenderParams p) {
+	extern __shared__ float win[];            // kPrivWindow floats
+	__shared__ int scratch[32];
+	const int total = pool.counts[2];
+	const int n_chunks = (total + kPrivChunk - 1) / kPrivChunk;
+	LocalCounters lc = {0, 0, 0, 0, 0, 0};
+	for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+		const int end = min(total, (chunk + 1) * kPrivChunk);
+		int pos = chunk * kPrivChunk;
+		while (pos < end) {   // block-uniform: one run of a single (context, recorder) pair per round
+			const uint2 q0 = pool.vis_sorted[pos];
+			const uint32_t r0 = q0.x >> pool.slot_bits, c0 = q0.y & 0xffffu;
+			const int pair = (int)c0 * p.n_rec + (int)r0;
+			const int run_end = min(end, pool.pair_base[pair + 1]);
+			const ear_b200_recorder& rec = p.rec[pair];
+			const int n_tr = rec.kind == EAR_B200_STEREO ? 2 : 1;
+			const int width = kPrivWindow / n_tr;
+			// window placement: mean first bin of a sample of the run (one entry per thread)
+			const int len = run_end - pos;
+			int my_s = 0, my_n = 0;
+			if ((int)threadIdx.x < len) {
+				const uint2 q = pool.vis_sorted[pos + (int)(((long long)threadIdx.x * len) / blockDim.x)];
+				const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u);
+				const float4 s0 = pool.sh0[slot];
+				const float path = pool.sh1[slot].w;
+				const V3 segv = vsub(mk(rec.position[0], rec.position[1], rec.position[2]), mk(s0.x, s0.y, s0.z));
+				my_s = min(p.n_bins >> 8, __double2int_rz((double)fdiv(fadd(path, vlength(segv)), 343.0f) * 44100.0) >> 8);   // in units of 256 bins: the sum stays in range
+				my_n = 1;
+			}
+			const int sum = block_sum_i(my_s, scratch), cnt = block_sum_i(my_n, scratch);
+			int lo = (int)(((long long)sum << 8) / max(cnt, 1)) - width / 2;
+			lo = max(0, min(lo, p.n_bins - width)) & ~31;
+			for (int j = threadIdx.x; j < kPrivWindow; j += blockDim.x) win[j] = 0.0f;
+			__syncthreads();
+			const size_t track = (size_t)pair * p.tpr;
+			WindowSink sink = {p.hist + track * p.n_bins, p.n_bins, win, lo, width, {0x7fffffff, 0x7fffffff}, {-1, -1}};
+			for (int i = pos + threadIdx.x; i < run_end; i += blockDim.x) {
+				const uint2 q = ld_stream(pool.vis_sorted + i);
+				const uint32_t slot = q.x & ((1u << pool.slot_bits) - 1u);
+				V3 lsdir; float contrib, dist;
+				if (!splat_weight(pool, p, q, rec, slot, c0, lsdir, contrib, dist)) continue;
+				record(rec, sink, p.n_bins, lsdir, contrib, fdiv(dist, 343.0f), dist, p.ctx[c0].band, lc);
+			}
+			__syncthreads();
+			// flush: lane i of a warp adds bin i -> one coalesced RED per 32 touched bins
+			for (int k = 0; k < n_tr; ++k) {
+				float* tr = p.hist + (track + k) * p.n_bins + lo;
+				const int room = min(width, p.n_bins - lo);
+				for (int j = threadIdx.x; j < room; j += blockDim.x) {
+					const float v = win[k * width + j];
+					if (v != 0.0f) atomicAdd(tr + j, v);
+				}
+				const int t_lo = block_min_i32(sink.t_lo[k], scratch);
+				const int t_hi = -block_min_i32(-sink.t_hi[k], scratch);
+				if (threadIdx.x == 0 && t_hi >= 0) touch_range(p.range + (track + k) * 2, t_lo, t_hi);
+			}
+			__syncthreads();
+			pos = run_end;
+		}
 	}
 	const unsigned long long v3 = warp_sum(lc.contributions), v4 = warp_sum(lc.bin_updates), v5 = warp_sum(lc.dropped);
 	if ((threadIdx.x & 31) == 0 && (v3 | v4 | v5)) {

@@ -5,7 +5,8 @@
                      `[v0,v1,v2],[v0,v2,v3]`, blender/render_EAR/__init__.py:274).
 * `example1_scene`   BASELINE config 2: a 40 x 52 x 18 m hall with a 0.36 m thick, 3.47 m
                      high partition, 44 triangles, stereo recorder with exporter defaults.
-* `synthetic_hall`   BASELINE config 4/5 generator: 60 x 40 x 20 m shoebox whose six walls are
+* `synthetic_complex` BASELINE config 5: grid of coupled halls (C4 halls joined by door tunnels), 64 recorders.
+* `synthetic_hall`   BASELINE config 4 generator: 60 x 40 x 20 m shoebox whose six walls are
                      tessellated to an exact triangle count with seeded +-5 cm displacement,
                      plus seeded interior box obstacles; 4 materials x n_bands coefficients.
 """
@@ -181,6 +182,153 @@ def synthetic_hall(n_tris=1_000_000, n_obstacles=2000, n_bands=8, seed=0, dims=(
         else:
             pos = (rrng.uniform(x0 + 2, x1 - 2), rrng.uniform(y0 + 2, y1 - 2), rrng.uniform(1.2, dz - 2.0))
         sc.recorders.append(RecorderDef(f"/tmp/hall.{r}.wav", position=pos))
+    return sc, table
+
+
+def _wall_grid_holed(origin, eu, ev, normal, nu, nv, rng, amp, hole):
+    """_wall_grid with the quads [i0, i1) x [j0, j1) left out (a door).  Vertices on and inside the hole's border are
+    not displaced, so the border is a planar rectangle loop.  Returns (triangles, border loop [k][3])."""
+    i0, i1, j0, j1 = hole
+    s = np.linspace(0.0, 1.0, nu + 1)
+    t = np.linspace(0.0, 1.0, nv + 1)
+    S, T = np.meshgrid(s, t, indexing="ij")
+    P = (np.asarray(origin)[None, None, :] + S[..., None] * np.asarray(eu)[None, None, :]
+         + T[..., None] * np.asarray(ev)[None, None, :])
+    d = rng.uniform(-amp, amp, size=S.shape)
+    d[0, :] = d[-1, :] = 0.0
+    d[:, 0] = d[:, -1] = 0.0
+    d[i0:i1 + 1, j0:j1 + 1] = 0.0
+    P = P + d[..., None] * np.asarray(normal)[None, None, :]
+    a, b, c, e = P[:-1, :-1], P[1:, :-1], P[1:, 1:], P[:-1, 1:]
+    keep = np.ones((nu, nv), bool)
+    keep[i0:i1, j0:j1] = False
+    t1 = np.stack([a, b, c], axis=2)[keep]
+    t2 = np.stack([a, c, e], axis=2)[keep]
+    loop = ([P[i, j0] for i in range(i0, i1)] + [P[i1, j] for j in range(j0, j1)]
+            + [P[i, j1] for i in range(i1, i0, -1)] + [P[i0, j] for j in range(j1, j0, -1)])
+    return np.concatenate([t1, t2]).astype(np.float32), np.asarray(loop, np.float64)
+
+
+def synthetic_complex(n_tris=10_000_000, n_obstacles=20000, n_bands=3, seed=0, hall=(60.0, 40.0, 20.0), grid=(4, 2),
+                      n_recorders=64, samples=10_000_000, gap=0.6):
+    """BASELINE config 5 (SURVEY.md section 8d "C5"): a complex of grid[0] x grid[1] coupled halls -- the C4 hall
+    replicated on a grid, neighbours joined by a door-sized tunnel through their facing walls -- tessellated to an
+    exact triangle count with the same seeded +-5 cm wall displacement, seeded box obstacles in every hall, the same
+    four materials, ONE point source (hall 0) and `n_recorders` mono recorders spread over all halls.
+    Returns (SceneDef, material_table[M, n_bands, 4]) like synthetic_hall."""
+    rng = np.random.default_rng(seed)
+    gx, gy = grid
+    n_halls = gx * gy
+    dx, dy, dz = hall
+    per_hall_obst = n_obstacles // n_halls
+    n_box_tris = 12 * per_hall_obst * n_halls
+    per_mat = {0: [], 1: [], 2: [], 3: []}
+    # wall tessellation shared by all halls (same dims -> facing walls have matching grids)
+    spec = [((dx, 0, 0), (0, dy, 0)), ((dx, 0, 0), (0, dy, 0)), ((dx, 0, 0), (0, 0, dz)), ((dx, 0, 0), (0, 0, dz)),
+            ((0, dy, 0), (0, 0, dz)), ((0, dy, 0), (0, 0, dz))]
+    areas = np.array([np.linalg.norm(np.cross(e[0], e[1])) for e in spec])
+    budget = (n_tris - n_box_tris) // n_halls
+    budget -= 4096                                   # head-room for door tunnels and the exact-count top-up
+    dims_uv = []
+    for (eu, ev), area in zip(spec, areas):
+        quads = max(1, int(np.floor(budget * area / areas.sum() / 2.0)))
+        lu, lv = np.linalg.norm(eu), np.linalg.norm(ev)
+        nu = max(2, int(np.floor(np.sqrt(quads * lu / lv))))
+        nv = max(2, quads // nu)
+        dims_uv.append((nu, nv))
+
+    def door(nu, nv, lu, lv):
+        """quad-index rectangle of a 6 m wide, 3.2 m high door in the middle of a wall of lu x lv metres"""
+        w = max(1, int(round(6.0 / lu * nu)))
+        h = max(1, int(round(3.2 / lv * nv)))
+        i0 = (nu - w) // 2
+        return i0, i0 + w, 0, min(h, nv - 1)
+
+    loops = {}                                       # (hall index, wall index) -> border loop of its door
+    made = 0
+    origins = []
+    for cy in range(gy):
+        for cx in range(gx):
+            h = cy * gx + cx
+            x0, y0 = cx * (dx + gap), cy * (dy + gap)
+            origins.append((x0, y0))
+            x1, y1 = x0 + dx, y0 + dy
+            walls = [((x0, y0, 0.0), (0, 0, 1), 0, None), ((x0, y0, dz), (0, 0, -1), 1, None),
+                     ((x0, y0, 0.0), (0, 1, 0), 1, cy > 0), ((x0, y1, 0.0), (0, -1, 0), 1, cy + 1 < gy),
+                     ((x0, y0, 0.0), (1, 0, 0), 1, cx > 0), ((x1, y0, 0.0), (-1, 0, 0), 1, cx + 1 < gx)]
+            for wi, ((org, nrm, mat, has_door), (eu, ev), (nu, nv)) in enumerate(zip(walls, spec, dims_uv)):
+                if has_door:
+                    g, loop = _wall_grid_holed(org, eu, ev, nrm, nu, nv, rng, 0.05,
+                                               door(nu, nv, np.linalg.norm(eu), np.linalg.norm(ev)))
+                    loops[(h, wi)] = loop
+                else:
+                    g = _wall_grid(org, eu, ev, nrm, nu, nv, rng, 0.05)
+                per_mat[mat].append(g)
+                made += g.shape[0]
+    # tunnels: join the two border loops of every pair of facing doors (same grid -> vertex k faces vertex k)
+    def tunnel(la, lb):
+        n = la.shape[0]
+        a0, a1 = la, np.roll(la, -1, axis=0)
+        b0, b1 = lb, np.roll(lb, -1, axis=0)
+        return np.concatenate([np.stack([a0, a1, b1], axis=1), np.stack([a0, b1, b0], axis=1)]).astype(np.float32).reshape(2 * n, 3, 3)
+    for cy in range(gy):
+        for cx in range(gx):
+            h = cy * gx + cx
+            if cx + 1 < gx:
+                t = tunnel(loops[(h, 5)], loops[(h + 1, 4)])
+                per_mat[1].append(t); made += t.shape[0]
+            if cy + 1 < gy:
+                t = tunnel(loops[(h, 3)], loops[(h + gx, 2)])
+                per_mat[1].append(t); made += t.shape[0]
+    extra = n_tris - n_box_tris - made
+    assert extra >= 0, extra
+    while extra > 0:                                  # top up to the exact count by bisecting wall triangles
+        for m in (0, 1):
+            for k in range(len(per_mat[m])):
+                take = min(extra, per_mat[m][k].shape[0])
+                per_mat[m][k] = _split_triangles(per_mat[m][k], take)
+                extra -= take
+    # obstacles, per hall, as in synthetic_hall
+    for h, (ox, oy) in enumerate(origins):
+        for i in range(per_hall_obst):
+            cx_ = rng.uniform(ox + 3.0, ox + dx - 3.0)
+            cy_ = rng.uniform(oy + 3.0, oy + dy - 3.0)
+            if i % 4 == 0:
+                sx, sy, sz = (0.06, rng.uniform(0.8, 2.0), rng.uniform(1.0, 2.2))
+                if rng.uniform() < 0.5:
+                    sx, sy = sy, sx
+                mat = 3
+            else:
+                sx, sy, sz = rng.uniform(0.4, 1.2), rng.uniform(0.4, 1.2), rng.uniform(0.4, 1.1)
+                mat = 2
+            per_mat[mat].append(box_triangles((cx_ - sx / 2, cy_ - sy / 2, 0.06), (cx_ + sx / 2, cy_ + sy / 2, 0.06 + sz)))
+    table = np.zeros((4, n_bands, 4), np.float32)
+    refl = rng.uniform(0.6, 0.97, size=(4, n_bands)).astype(np.float32)
+    spc = rng.uniform(0.0, 0.9, size=(4, n_bands)).astype(np.float32)
+    refr = np.zeros((4, n_bands), np.float32)
+    refl[3, :] = 0.7
+    refr[3, :] = 0.24
+    sc = SceneDef(samples=samples, air_absorption=(0.001, 0.0015, 0.003))
+    names = ["floor", "shell", "seats", "glazing"]
+    eps = np.float32(1e-9)
+    for m in range(4):
+        sc.materials.append(MaterialDef(names[m], [float(x) for x in refl[m, :3]], [float(x) for x in refr[m, :3]],
+                                        [float(x) for x in spc[m, :3]]))
+        for b in range(n_bands):
+            a = np.float32(1.0)
+            a = np.float32(a - np.float32(refl[m, b] - eps))
+            a = np.float32(a - np.float32(refr[m, b] - eps))
+            table[m, b] = (refl[m, b], refr[m, b], np.float32(np.float32(1.0) - a), spc[m, b])
+    for m in range(4):
+        if per_mat[m]:
+            sc.meshes.append(MeshDef(names[m], np.concatenate(per_mat[m]).astype(np.float32)))
+    assert sc.triangles().shape[0] == n_tris, (sc.triangles().shape[0], n_tris)
+    sc.sources.append(SourceDef(["/tmp/click.wav"], position=(origins[0][0] + 8.0, origins[0][1] + 21.0, 1.7)))
+    rrng = np.random.default_rng(seed + 1)
+    for r in range(n_recorders):
+        ox, oy = origins[r % n_halls]
+        pos = (rrng.uniform(ox + 2, ox + dx - 2), rrng.uniform(oy + 2, oy + dy - 2), rrng.uniform(1.2, dz - 2.0))
+        sc.recorders.append(RecorderDef(f"/tmp/complex.{r}.wav", position=pos))
     return sc, table
 
 

@@ -89,7 +89,8 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
     opt = api.make_options(max_bounces, n_bins, seed, lo, hi - lo, False)
     if n_bins <= 0:
         n_bins = scene.default_bins(opt)
-    n_tracks = n_ctx * n_rec * 2
+    tpr = api.tracks_per_recorder(rec_c)          # device layout: [context][recorder][tpr][bins]
+    n_tracks = n_ctx * n_rec * tpr
     with torch.cuda.device(dev):
         hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
         rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
@@ -121,7 +122,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
             h_t60 = np.zeros((n_tracks,), np.float32)
             api._check(lib, lib.ear_b200_post_truncate_device(scene.handle, rec_c, n_ctx, n_rec, n_bins, hist.data_ptr(),
                                                               rng.data_ptr(), threshold, h_t60.ctypes.data, sp))
-            t60 = h_t60.reshape(n_ctx, n_rec, 2).tolist()
+            t60 = h_t60.reshape(n_ctx, n_rec, tpr).tolist()
         h_rng = rng.cpu().numpy()
         c = counters.cpu().numpy()
         # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
@@ -133,7 +134,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
         for k in range(n_rec):
             pair = []
             for tr in range(2 if rec_c[ci * n_rec + k].kind == api.STEREO else 1):
-                t = (ci * n_rec + k) * 2 + tr
+                t = (ci * n_rec + k) * tpr + tr
                 real_len = int(h_rng[t, 1])
                 data = np.zeros((n_bins,), np.float32)       # Track.data spans the whole buffer, like Scene.render()
                 data[:real_len + 1] = h_hist[t, :real_len + 1]

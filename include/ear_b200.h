@@ -37,11 +37,17 @@
 extern "C" {
 #endif
 
-#define EAR_B200_ABI_VERSION 2        /* 2: ear_b200_context.stream_id, scene images, device post chain */
+#define EAR_B200_ABI_VERSION 3        /* 2: ear_b200_context.stream_id, scene images, device post chain
+                                         3: mesh-emitter sources, one track per mono recorder in device buffers,
+                                            device BVH build, multi-GPU render inside the library */
 #define EAR_B200_MAX_BANDS 8          /* the .ear format carries 3; up to 8 through the ABI */
 #define EAR_B200_SAMPLE_RATE 44100    /* src/Recorder.h:35 */
 #define EAR_B200_MONO 1               /* OUT1, MonoRecorder  (src/MonoRecorder.cpp:83-97)   */
 #define EAR_B200_STEREO 2             /* OUT2, StereoRecorder (src/StereoRecorder.cpp:97-130) */
+#define EAR_B200_POINT_SOURCE 0       /* AbstractSoundFile without a mesh: Sample_Sphere at its location (src/SoundFile.cpp:222-226) */
+#define EAR_B200_MESH_SOURCE 1        /* AbstractSoundFile::mesh set: area-weighted emitter triangle, uniform point, hemisphere
+                                         about the triangle's own normal (src/SoundFile.cpp:216-221, src/Mesh.cpp:143-154,
+                                         src/Triangle.cpp:44-53); bounce 0 is recorded, no direct lobe (src/Scene.cpp:185,299) */
 
 typedef struct ear_b200_scene ear_b200_scene;    /* triangles + BVH + materials on one GPU */
 
@@ -67,6 +73,10 @@ typedef struct ear_b200_context {
 	float dry_level;              /* direct-sound gain (src/Scene.cpp:308-309) */
 	float gain;                   /* source gain; tracks are scaled by gain^2 (src/Scene.cpp:313-314) */
 	float source_position[3];     /* AbstractSoundFile::getLocation(kf) (src/SoundFile.cpp:142-148) */
+	int32_t source_kind;          /* EAR_B200_POINT_SOURCE | EAR_B200_MESH_SOURCE */
+	int32_t emitter_first;        /* mesh source: its triangles are [emitter_first, emitter_first + emitter_count) of the */
+	int32_t emitter_count;        /*              table given to ear_b200_scene_set_emitters                             */
+	int32_t reserved;
 } ear_b200_context;
 
 typedef struct ear_b200_options {
@@ -125,6 +135,11 @@ int32_t ear_b200_scene_create(const float* verts /*[n_tris][3][3]*/, const int32
                               int32_t n_tris, const float* materials, int32_t n_materials, int32_t n_bands,
                               int32_t device, ear_b200_scene** out);
 void ear_b200_scene_destroy(ear_b200_scene* scene);
+/* Emitter triangles of the scene's mesh sources (the `mesh` block inside a sound source, src/SoundFile.cpp:50-53):
+ * all of them concatenated, file order; contexts of mesh sources name a range of this table.  They emit only (they
+ * are not part of the geometry rays hit).  Normals and areas are formed as Triangle's constructor does
+ * (src/Triangle.cpp:26-34).  Replaces the table of an earlier call; n = 0 clears it. */
+int32_t ear_b200_scene_set_emitters(ear_b200_scene* scene, const float* verts /*[n][3][3]*/, int32_t n);
 
 /* Multi-GPU replication: the acceleration data of a scene is one contiguous device
  * image.  One rank builds the scene, writes its image into a device buffer it can broadcast (NCCL over
@@ -164,8 +179,10 @@ void ear_b200_result_free(ear_b200_result* result);
 
 /* Device-resident variant for one-process-per-GPU sharding: accumulates raw partial sums into
  * caller-owned device memory so the caller can reduce them across ranks (NCCL) before finalising.
- *   d_hist   float  [n_contexts][n_recorders][2][n_bins]   (zeroed by the caller)
- *   d_range  uint32 [n_contexts][n_recorders][2][2]        {first_sample (init 132299), real_length (init 0)}
+ *   d_hist   float  [n_contexts][n_recorders][tpr][n_bins]   (zeroed by the caller)
+ *   d_range  uint32 [n_contexts][n_recorders][tpr][2]        {first_sample (init 132299), real_length (init 0)}
+ *            tpr = ear_b200_tracks_per_recorder(rec, n_contexts * n_recorders): 2 when any recorder of the call is
+ *            stereo, else 1 (64 mono recorders do not carry 64 dead tracks through memset, atomics and the reduce)
  *   d_counters uint64 [8]: rays, segments, occlusion_queries, contributions, bin_updates, dropped, -, -
  * `stream` is a cudaStream_t (0 = legacy default stream).  All work is ordered on `stream`; the call returns once
  * the last ray has ended (the wavefront loop reads a 32-byte counter block every few iterations to know when to
@@ -177,6 +194,8 @@ int32_t ear_b200_trace_device(ear_b200_scene* scene, const ear_b200_context* ctx
 int32_t ear_b200_finalise_device(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
                                  const ear_b200_recorder* rec, int32_t n_recorders, int32_t n_bins,
                                  float* d_hist, uint32_t* d_range, void* stream);
+/* Tracks each recorder owns in the device buffers of a call with these recorders (see ear_b200_trace_device). */
+int32_t ear_b200_tracks_per_recorder(const ear_b200_recorder* rec, int32_t n);
 /* Bins per track the library would choose for these options (same rule as ear_b200_render). */
 int32_t ear_b200_default_bins(ear_b200_scene* scene, const ear_b200_options* opt);
 /* SURVEY.md 8(f) rank 1 -- impulse-response convolution, RecorderTrack::Process (src/Recorder.cpp:247-292,
@@ -198,11 +217,11 @@ int32_t ear_b200_convolve(int32_t device, const float* response, uint32_t length
  * the two phases the reference runs it in (every track is compressed before the global maximum is known):
  *   post_power     Recorder::Power(exponent) in place on every track (FloatBuffer::Power, src/Recorder.cpp:101-106:
  *                  sign(x) * |x|^exponent over [first_sample, real_length)), then FloatBuffer::Maximum of each track
- *                  (:76-83).  maximum = the largest of them (host, may be NULL); track_maximum [n_contexts][n_recorders][2]
+ *                  (:76-83).  maximum = the largest of them (host, may be NULL); track_maximum [n_contexts][n_recorders][tpr]
  *                  (host, may be NULL).  Multi-GPU callers reduce `maximum` by MAX before phase 2.
  *   post_truncate  Recorder::Truncate(Recorder::getLength(threshold)) for every recorder (src/Recorder.cpp:399-430,
  *                  108-118; the reference passes threshold = maximum / 256) -- updates real_length in d_range -- and
- *                  RecorderTrack::T60 (src/Recorder.cpp:303-340) of every truncated track into t60 [n_contexts][n_recorders][2]
+ *                  RecorderTrack::T60 (src/Recorder.cpp:303-340) of every truncated track into t60 [n_contexts][n_recorders][tpr]
  *                  (host; `EAR calc T60` prints t60[0]).
  * d_hist / d_range as in ear_b200_trace_device, after ear_b200_finalise_device.  Both calls synchronise `stream`. */
 int32_t ear_b200_post_power_device(ear_b200_scene* scene, const ear_b200_recorder* rec, int32_t n_contexts, int32_t n_recorders,

@@ -5,12 +5,14 @@
 #include "../../ear_b200/csrc/traverse.cuh"
 #include "../../ear_b200/csrc/vismap_geom.cuh"
 #include <vector>
+#include <cstdlib>
 #include <chrono>
 using namespace earb;
 struct Emul { Bvh bvh; SceneDev dev; double build_ms; };
 extern "C" {
 void* emul_create(const float* verts, const int32_t* mats, int32_t n) {
 	Emul* e = new Emul();
+	if (const char* k = getenv("EAR_B200_BVH_MARGIN_SCALE")) g_emul_decode_bias = 0.00390625f * (float)atof(k);   // the margins' test knob covers the decode bias too
 	auto t0 = std::chrono::steady_clock::now();
 	build_bvh(verts, mats, n, e->bvh);
 	e->build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -18,6 +20,7 @@ void* emul_create(const float* verts, const int32_t* mats, int32_t n) {
 	e->dev.tris = (const float4*)e->bvh.tris.data();
 	e->dev.materials = nullptr; e->dev.n_tris = n; e->dev.n_materials = 0; e->dev.n_bands = 0;
 	e->dev.s0 = e->bvh.s0; e->dev.exact = 0; e->dev.leaf_vote = kLeafVote; e->dev.fetch_vote = 8; e->dev.vis_cap = 64;
+	e->dev.emitters = nullptr; e->dev.spill = nullptr; e->dev.spill_threads = 1; e->dev.spill_rows = kStackSpill;
 	return e;
 }
 void emul_destroy(void* h) { delete (Emul*)h; }

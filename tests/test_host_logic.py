@@ -57,8 +57,8 @@ def test_library_exports_every_declared_symbol():
     assert declared == sorted(api.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.ear_b200_abi_version() == 2
-    assert ctypes.sizeof(api.ContextC) == 40 and ctypes.sizeof(api.RecorderC) == 64 and ctypes.sizeof(api.OptionsC) == 40
+    assert lib.ear_b200_abi_version() == 3
+    assert ctypes.sizeof(api.ContextC) == 56 and ctypes.sizeof(api.RecorderC) == 64 and ctypes.sizeof(api.OptionsC) == 40
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

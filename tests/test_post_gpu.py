@@ -23,12 +23,14 @@ def _device_post(scene, res, recs, n_ctx, exponent=0.335, divisor=256.0):
     import torch
     lib = scene.lib
     rec_c, n_rec = api.pack_recorders(recs, n_ctx)
+    tpr = api.tracks_per_recorder(rec_c)   # device layout [context][recorder][tpr][bins]: 1 when every recorder is mono
     flat = []
     for c in range(n_ctx):
         for r in range(n_rec):
             pair = res.tracks[c][r]
             flat.append(pair[0])
-            flat.append(pair[1] if len(pair) > 1 else None)
+            if tpr == 2:
+                flat.append(pair[1] if len(pair) > 1 else None)
     n_bins = max(t.data.shape[0] for t in flat if t is not None)
     hist = np.zeros((len(flat), n_bins), np.float32)
     rng = np.zeros((len(flat), 2), np.uint32)
@@ -47,7 +49,7 @@ def _device_post(scene, res, recs, n_ctx, exponent=0.335, divisor=256.0):
     t60 = np.zeros(len(flat), np.float32)
     api._check(lib, lib.ear_b200_post_truncate_device(scene.handle, rec_c, n_ctx, n_rec, n_bins, d_hist.data_ptr(), d_rng.data_ptr(),
                                                       thr, t60.ctypes.data, None))
-    return float(mx.value), d_hist.cpu().numpy(), d_rng.cpu().numpy().view(np.uint32), t60, tmax
+    return float(mx.value), d_hist.cpu().numpy(), d_rng.cpu().numpy().view(np.uint32), t60, tmax, tpr
 
 
 @pytest.mark.parametrize("name,stereo,samples", [("rt60", False, 40000), ("example1", True, 30000), ("rt60", True, 600)])
@@ -60,12 +62,12 @@ def test_post_chain_matches_oracle(ob, name, stereo, samples):
     ctxs, recs = api.contexts_from_def(sc)
     res = scene.render(ctxs, recs, max_bounces=300, seed=3)
     want_max, want = ob.post_all(res.tracks)
-    got_max, hist, rng, t60, tmax = _device_post(scene, res, recs, len(ctxs))
+    got_max, hist, rng, t60, tmax, tpr = _device_post(scene, res, recs, len(ctxs))
     assert got_max == pytest.approx(want_max, rel=2e-7)
     i = 0
     for c in range(len(ctxs)):
         for r in range(len(recs[c])):
-            for k in range(2):
+            for k in range(tpr):
                 if k >= len(want[c][r]):
                     assert t60[i] == 0.0 and tmax[i] == 0.0
                     i += 1
@@ -93,7 +95,8 @@ def test_post_chain_on_empty_and_single_sample_tracks(ob):
     two.data[40:44] = (0.25, -0.125, 0.01, 0.02)
     res = api.RenderResult([[[empty]], [[one, two]]], 0, 0, 0, 0, 0, 0, 0.0)
     want_max, want = ob.post_all(res.tracks)
-    got_max, hist, rng, t60, tmax = _device_post(scene, res, recs, 2)
+    got_max, hist, rng, t60, tmax, tpr = _device_post(scene, res, recs, 2)
+    assert tpr == 2
     assert got_max == pytest.approx(want_max, rel=2e-7)
     rows = {0: want[0][0][0], 2: want[1][0][0], 3: want[1][0][1]}
     for i, (data, first, real, w_t60) in rows.items():
