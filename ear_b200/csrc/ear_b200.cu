@@ -797,6 +797,10 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	}
 	int* d_counts = s->d_vis_counts;
 	CUDA_TRY(cudaMalloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
+	struct MapGuard {   // the two allocations of a map are released on every error return until the map is adopted
+		ear_b200_scene::VisMapHost* m;
+		~MapGuard() { if (m) { cudaFree(m->d_offsets); cudaFree(m->d_items); } }
+	} guard{&m};
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
 	lap("alloc + clear");
 	const double reach = 2.0 * (double)s->diagonal + 1.0;
@@ -829,12 +833,12 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 		size_t free_b = 0, total_b = 0;
 		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
 		s->vis_budget = std::max<size_t>(free_b / 4, 1);
+		if (const char* vb = std::getenv("EAR_B200_VISMAP_BUDGET")) s->vis_budget = std::max<size_t>((size_t)std::atof(vb), 1);   // bytes (tests: force the BVH route)
 	}
 	const size_t map_bytes = ((size_t)n_tex + 1) * sizeof(int) + (total < 0 ? 0 : (size_t)total * sizeof(int));
 	if (total < 0 || s->vis_bytes + map_bytes > s->vis_budget) {
-		cudaFree(m.d_offsets);
 		s->vis_budget_spent = true;
-		return 0;
+		return 0;   // the guard frees the offsets
 	}
 	s->vis_bytes += map_bytes;
 	m.n_items = (size_t)total;
@@ -845,6 +849,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	CUDA_TRY(cudaStreamSynchronize(stream));
 	lap("fill pass");
 	s->vismaps.push_back(m);
+	guard.m = nullptr;
 	*index = (int)s->vismaps.size() - 1;
 	return 0;
 }

@@ -164,3 +164,63 @@ def edge_case_queries(sc: SceneDef, n: int = 20000):
     p, x = make_segments(sc, n, seed=10)
     x[: n // 40] = p[: n // 40]
     return o, d, p, x
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the brute-force oracle over many host threads (ctypes releases the GIL during the call): full-size scenes
+# ---------------------------------------------------------------------------------------------------------
+def oracle_first_hit_parallel(cpu, o, d, workers=None):
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    workers = workers or max(1, min(32, os.cpu_count() or 1))
+    n = o.shape[0]
+    cuts = [n * k // workers for k in range(workers + 1)]
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(lambda k: cpu.first_hit(o[cuts[k]:cuts[k + 1]], d[cuts[k]:cuts[k + 1]]), range(workers)))
+    return np.concatenate([p[0] for p in parts]), np.concatenate([p[1] for p in parts])
+
+
+def oracle_occluded_parallel(cpu, p, x, workers=None):
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    workers = workers or max(1, min(32, os.cpu_count() or 1))
+    n = p.shape[0]
+    cuts = [n * k // workers for k in range(workers + 1)]
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(lambda k: cpu.occluded(p[cuts[k]:cuts[k + 1]], x[cuts[k]:cuts[k + 1]]), range(workers)))
+    return np.concatenate(parts)
+
+
+def oracle_render_parallel(cpu, ctxs, recs, max_bounces, seed, workers=None):
+    """Raw (not finalised) oracle render with the ray-id range of every context dealt to host threads; the partial
+    tracks are summed in float64.  Returns (tracks[ctx][rec][k] = (data float64, first_sample, real_length), counters)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    workers = workers or max(1, min(32, os.cpu_count() or 1))
+    rays = max(int(c.num_samples) for c in ctxs)
+    workers = max(1, min(workers, rays))
+    cuts = [rays * k // workers for k in range(workers + 1)]
+    from oracle import binding as ob
+
+    def part(k):
+        return cpu.render(ctxs, recs, max_bounces=max_bounces, rng_mode=ob.RNG_PHILOX, seed=seed, first_ray=cuts[k],
+                          ray_count=cuts[k + 1] - cuts[k], finalise=False)
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(part, range(workers)))
+    total, counters = None, {}
+    for tracks, cnt in parts:
+        for key, v in cnt.items():
+            counters[key] = counters.get(key, 0) + v
+        if total is None:
+            total = [[[[t.data.astype(np.float64), t.first_sample, t.real_length] for t in pair] for pair in per_rec] for per_rec in tracks]
+            continue
+        for c, per_rec in enumerate(tracks):
+            for r, pair in enumerate(per_rec):
+                for k, t in enumerate(pair):
+                    acc = total[c][r][k]
+                    if t.data.shape[0] > acc[0].shape[0]:
+                        acc[0] = np.concatenate([acc[0], np.zeros(t.data.shape[0] - acc[0].shape[0])])
+                    acc[0][: t.data.shape[0]] += t.data
+                    acc[1] = min(acc[1], t.first_sample)
+                    acc[2] = max(acc[2], t.real_length)
+    return total, counters
