@@ -263,10 +263,11 @@ def run_ours(args):
         depth = math.ceil(math.log2(max(2, math.ceil(N_TRIS / 4))))
         q_bytes = 32 * depth + 192
         if WORKLOAD_KEY == "c5":
-            dom, dom_name, units = "anyhit", "wf_vismap_kernel + wf_traverse_kernel<true> (occlusion queries)", occl / world
+            dom_name, units = "wf_vismap_kernel + wf_traverse_kernel<true> (occlusion queries)", occl / world
+            dom_ms = st["ms"]["vismap"] + st["ms"]["anyhit"]
         else:
-            dom, dom_name, units = "closest", "wf_traverse_kernel<false> (closest hit)", segments / world
-        dom_ms = st["ms"][dom]
+            dom_name, units = "wf_traverse_kernel<false> (closest hit)", segments / world
+            dom_ms = st["ms"]["closest"]
         dom_launches = st["launches"]["closest"]      # one launch of every class per iteration
         dom_bytes = q_bytes * units
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9

@@ -63,7 +63,7 @@ class StatsC(C.Structure):
     _fields_ = [("launches", C.c_uint64 * 8), ("ms", C.c_double * 8), ("iterations", C.c_uint64), ("reserved", C.c_uint64)]
 
 
-KERNEL_CLASSES = ["shade", "closest", "anyhit", "splat", "fused", "finalise"]
+KERNEL_CLASSES = ["shade", "closest", "anyhit", "splat", "sort", "finalise", "vismap", "mapbuild"]
 
 EXPORTS = [
     "ear_b200_last_error", "ear_b200_abi_version", "ear_b200_device_count", "ear_b200_scene_create",

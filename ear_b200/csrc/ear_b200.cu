@@ -169,6 +169,7 @@ constexpr int kBlock = 128;
 #include "wavefront.cuh"
 #include "vismap.cuh"
 #include "post.cuh"
+#include "bvh_device.cuh"
 
 // ---- K7: Scene::Render's tail, src/Scene.cpp:286-316 ----
 // FloatBuffer::Multiply over [first_sample, real_length) -- the last touched bin is NOT scaled
@@ -402,25 +403,55 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
 	s->device = device;
 	const auto t0 = std::chrono::steady_clock::now();
-	Bvh bvh;
-	build_bvh(verts, tri_material, n_tris, bvh);
-	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+	// K0: the BVH is built on the device (bvh_device.cuh) unless the scene is tiny or EAR_B200_BUILD=host asks for
+	// the host builder (bvh_build.cpp, kept for A/B and for the CPU-side tests of the traversal logic)
+	const char* bk = std::getenv("EAR_B200_BUILD");
+	const bool on_device = bk ? std::string(bk) == "device" : n_tris >= 2048;
 	ImageHeader h{};
 	h.magic = kImageMagic; h.version = EAR_B200_ABI_VERSION;
 	h.n_tris = n_tris; h.n_materials = n_materials; h.n_bands = n_bands;
-	h.n_nodes = (int32_t)bvh.nodes.size(); h.depth = bvh.depth; h.diagonal = bvh.diagonal; h.s0 = bvh.s0;
-	for (int k = 0; k < 3; ++k) {
-		h.lo[k] = bvh.lo[k]; h.hi[k] = bvh.hi[k];
-		h.maxabs = std::max(h.maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
-	}
-	image_layout(h);
 	s->materials.assign(materials, materials + (size_t)n_materials * n_bands * 4);
-	CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
-	CUDA_TRY(cudaMemcpy(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMemcpy(s->d_image + h.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
-	if (!bvh.tris.empty())
-		CUDA_TRY(cudaMemcpy(s->d_image + h.off_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
-	CUDA_TRY(cudaMemcpy(s->d_image + h.off_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice));
+	if (on_device) {
+		DevBuf<float> d_verts;
+		DevBuf<int32_t> d_mat;
+		CUDA_TRY(d_verts.alloc((size_t)n_tris * 9));
+		if (n_tris) CUDA_TRY(cudaMemcpyAsync(d_verts, verts, (size_t)n_tris * 36, cudaMemcpyHostToDevice, 0));
+		if (tri_material) { CUDA_TRY(d_mat.alloc((size_t)n_tris)); if (n_tris) CUDA_TRY(cudaMemcpyAsync(d_mat, tri_material, (size_t)n_tris * 4, cudaMemcpyHostToDevice, 0)); }
+		dbvh::Result r;
+		std::string err;
+		const bool ok = dbvh::build(d_verts, tri_material ? d_mat.p : nullptr, n_tris, 0, r, err);
+		DevBuf<Node> own_nodes; own_nodes.p = r.d_nodes;          // released on every path below
+		DevBuf<TriRecord> own_tris; own_tris.p = r.d_tris;
+		if (!ok) return fail(err);
+		h.n_nodes = r.n_nodes; h.depth = r.depth; h.diagonal = r.diagonal; h.s0 = r.s0;
+		for (int k = 0; k < 3; ++k) {
+			h.lo[k] = r.lo[k]; h.hi[k] = r.hi[k];
+			h.maxabs = std::max(h.maxabs, std::max(std::fabs(r.lo[k]), std::fabs(r.hi[k])));
+		}
+		image_layout(h);
+		CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+		CUDA_TRY(cudaMemcpyAsync(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice, 0));
+		CUDA_TRY(cudaMemcpyAsync(s->d_image + h.off_nodes, r.d_nodes, (size_t)r.n_nodes * sizeof(Node), cudaMemcpyDeviceToDevice, 0));
+		if (n_tris) CUDA_TRY(cudaMemcpyAsync(s->d_image + h.off_tris, r.d_tris, (size_t)n_tris * sizeof(TriRecord), cudaMemcpyDeviceToDevice, 0));
+		CUDA_TRY(cudaMemcpyAsync(s->d_image + h.off_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice, 0));
+		CUDA_TRY(cudaStreamSynchronize(0));
+	} else {
+		Bvh bvh;
+		build_bvh(verts, tri_material, n_tris, bvh);
+		h.n_nodes = (int32_t)bvh.nodes.size(); h.depth = bvh.depth; h.diagonal = bvh.diagonal; h.s0 = bvh.s0;
+		for (int k = 0; k < 3; ++k) {
+			h.lo[k] = bvh.lo[k]; h.hi[k] = bvh.hi[k];
+			h.maxabs = std::max(h.maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
+		}
+		image_layout(h);
+		CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+		CUDA_TRY(cudaMemcpy(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(s->d_image + h.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
+		if (!bvh.tris.empty())
+			CUDA_TRY(cudaMemcpy(s->d_image + h.off_tris, bvh.tris.data(), bvh.tris.size() * sizeof(TriRecord), cudaMemcpyHostToDevice));
+		CUDA_TRY(cudaMemcpy(s->d_image + h.off_materials, s->materials.data(), s->materials.size() * sizeof(float), cudaMemcpyHostToDevice));
+	}
+	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	if (int32_t rc = scene_finish(s.get(), h)) return rc;
 	*out = s.release();
 	return 0;
@@ -524,7 +555,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
 	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
 	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins); cudaFree(s->pool.ctx_log2af);
-	cudaFree(s->pool.pair_count); cudaFree(s->pool.pair_base);
+	cudaFree(s->pool.pair_count); cudaFree(s->pool.pair_base); cudaFree(s->pool.trav_rank); cudaFree(s->pool.q_rank);
 	cudaFree(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -730,18 +761,20 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	WfPool& pl = s->pool;
 	if (slots > s->pool_slots) {
 		cudaFree(pl.ro); cudaFree(pl.rd); cudaFree(pl.rm); cudaFree(pl.hit); cudaFree(pl.sh0); cudaFree(pl.sh1); cudaFree(pl.sh2);
-		cudaFree(pl.trav_list); cudaFree(pl.trav_tmp);
+		cudaFree(pl.trav_list); cudaFree(pl.trav_tmp); cudaFree(pl.trav_rank);
 		CUDA_TRY(cudaMalloc(&pl.ro, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.rd, slots * sizeof(float4)));
 		CUDA_TRY(cudaMalloc(&pl.rm, slots * sizeof(uint4))); CUDA_TRY(cudaMalloc(&pl.hit, slots * sizeof(int2)));
 		CUDA_TRY(cudaMalloc(&pl.sh0, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.sh1, slots * sizeof(float4)));
 		CUDA_TRY(cudaMalloc(&pl.sh2, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.trav_list, slots * sizeof(int)));
 		CUDA_TRY(cudaMalloc(&pl.trav_tmp, slots * sizeof(uint2)));
+		CUDA_TRY(cudaMalloc(&pl.trav_rank, slots * sizeof(int)));
 		s->pool_slots = slots;
 	}
 	if (queries > s->pool_queries) {
-		cudaFree(pl.q_list); cudaFree(pl.vis_list); cudaFree(pl.q_tmp);
+		cudaFree(pl.q_list); cudaFree(pl.vis_list); cudaFree(pl.q_tmp); cudaFree(pl.q_rank);
 		CUDA_TRY(cudaMalloc(&pl.q_list, queries * sizeof(uint2))); CUDA_TRY(cudaMalloc(&pl.vis_list, queries * sizeof(uint2)));
 		CUDA_TRY(cudaMalloc(&pl.q_tmp, queries * sizeof(uint2)));
+		CUDA_TRY(cudaMalloc(&pl.q_rank, queries * sizeof(int)));
 		s->pool_queries = queries;
 	}
 	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
@@ -946,10 +979,10 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
 			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
 			CUDA_TRY(cudaMemsetAsync(pl.bins, 0, kBinsTotal * sizeof(int), stream));
+			{ LaunchTimer t(s, stream, 0); wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p); }
 			{
-				LaunchTimer t(s, stream, 0);
-				s->stats.launches[0] += 3;
-				wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p);
+				LaunchTimer t(s, stream, 4);
+				s->stats.launches[4] += 2;
 				wf_scan_kernel<<<kScanBlocks, 1024, 0, stream>>>(pl);
 				wf_scan_top_kernel<<<1, kScanBlocks, 0, stream>>>(pl);
 				wf_scatter_kernel<<<s->sm_count * 8, 256, 0, stream>>>(pl);
@@ -957,10 +990,8 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 			if (p.n_rec > 0) {
 				if (n_mapped) {
-					LaunchTimer t(s, stream, 2);
-					++s->stats.launches[2];
-					wf_vismap_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh);
-					anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl_fb, p);
+					{ LaunchTimer t(s, stream, 6); wf_vismap_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh); }
+					{ LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl_fb, p); }
 				} else { LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 				if (windowed) {
 					LaunchTimer t(s, stream, 3);

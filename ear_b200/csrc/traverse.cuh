@@ -247,7 +247,8 @@ __device__ __forceinline__ int32_t pick4(int32_t c0, int32_t c1, int32_t c2, int
 }
 
 #ifndef EARB_DECODE_PRMT
-#define EARB_DECODE_PRMT 1
+#define EARB_DECODE_PRMT 0   // measured on B200 (profiles/r2_ab_closest.txt): the PRMT form is 4 % SLOWER than I2F.U8 -- the kernel
+                             // is bound by issue slots and divergence, not by the XU pipe, and the form costs 6 more FMAs per node
 #endif
 #ifdef EARB_HOST_EMULATION
 static float g_emul_decode_bias = 0.00390625f;

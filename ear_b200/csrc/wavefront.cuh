@@ -34,6 +34,8 @@ struct WfPool {
 	int* trav_list;     // [N] slots that need a closest-hit query, binned by (direction octant, origin cell)
 	uint2* trav_tmp;    // [N] (slot, bin) as appended by the shade kernel, before binning
 	uint2* q_tmp;       // [N*R] queries as appended by the shade kernel (bin in bits 16..30 of y), before binning
+	int* trav_rank;     // [N] position of the appended ray inside its bin (the value the shade kernel's counting atomic returned)
+	int* q_rank;        // [N*R] same for the queries
 	int* bins;          // [kRayBins + kSortBins (+ block sums)] histogram -> offsets of the two counting sorts (closest rays, queries)
 	float cell_origin[3], cell_scale[3];   // world -> [0,16) cell coordinates of the scene bounds
 	int slot_bits;      // split of the query word between slot index and recorder index (see kMaxSlotBits)
@@ -240,29 +242,23 @@ __global__ void __launch_bounds__(kScanBlocks) wf_scan_top_kernel(WfPool pool) {
 	for (int w = first_warp; w < wid; ++w) before += warp_tot[w];
 	h[threadIdx.x] = before + inc - v;
 }
-// scatter the appended entries to their bins (order inside a bin is arbitrary)
+// scatter the appended entries to their bins.  The position inside the bin is the value the shade kernel's counting
+// atomic returned (kept in trav_rank / q_rank), so this pass is a plain gather / scatter: the first version counted
+// with fire-and-forget atomics and took a second, returning atomic per entry here -- whose round trip was its whole cost.
 __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 	const int n_trav = pool.counts[0], n_q = pool.sort_queries ? pool.counts[1] : 0;
 	const int stride = gridDim.x * blockDim.x;
 	const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-	// four independent atomics in flight per thread: the returning atomic's round trip is the whole cost here
-	for (int i = tid; i < n_trav; i += 4 * stride) {
-		uint2 e[4]; int pos[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) e[k] = ld_stream(pool.trav_tmp + i + k * stride);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) pos[k] = atomicAdd(pool.bins + e[k].y, 1) + pool.bins[kRayBins + kSortBins + (e[k].y >> 10)];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_trav) st_stream(pool.trav_list + pos[k], (int)e[k].x);
+	for (int i = tid; i < n_trav; i += stride) {
+		const uint2 e = ld_stream(pool.trav_tmp + i);
+		const int pos = pool.bins[e.y] + pool.bins[kRayBins + kSortBins + (e.y >> 10)] + ld_stream(pool.trav_rank + i);
+		st_stream(pool.trav_list + pos, (int)e.x);
 	}
-	for (int i = tid; i < n_q; i += 4 * stride) {
-		uint2 e[4]; int pos[4];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) e[k] = ld_stream(pool.q_tmp + i + k * stride);
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) pos[k] = atomicAdd(pool.bins + kRayBins + ((e[k].y >> 16) & 0x7fffu), 1) + pool.bins[kRayBins + kSortBins + kRayScanBlocks + ((e[k].y >> 26) & 0x1fu)];
-#pragma unroll
-		for (int k = 0; k < 4; ++k) if (i + k * stride < n_q) st_stream(pool.q_list + pos[k], e[k]);
+	for (int i = tid; i < n_q; i += stride) {
+		const uint2 e = ld_stream(pool.q_tmp + i);
+		const uint32_t bin = (e.y >> 16) & 0x7fffu;
+		const int pos = pool.bins[kRayBins + bin] + pool.bins[kRayBins + kSortBins + kRayScanBlocks + (bin >> 10)] + ld_stream(pool.q_rank + i);
+		st_stream(pool.q_list + pos, e);
 	}
 }
 
@@ -459,8 +455,9 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			if (facing) {
 				if (pool.sort_queries) {
 					const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
-					atomicAdd(pool.bins + kRayBins + bin, 1);
-					st_stream(pool.q_tmp + base + __popc(mq & lt_mask),
+					const int at = base + __popc(mq & lt_mask);
+					st_stream(pool.q_rank + at, atomicAdd(pool.bins + kRayBins + bin, 1));
+					st_stream(pool.q_tmp + at,
 					          make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31)));
 				} else {
 					st_stream(pool.q_list + base + __popc(mq & lt_mask),
@@ -481,8 +478,9 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		base = __shfl_sync(0xffffffffu, base, 0);
 		if (alive) {
 			const uint32_t bin = ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
-			atomicAdd(pool.bins + bin, 1);
-			st_stream(pool.trav_tmp + base + __popc(live & lt_mask), make_uint2((uint32_t)slot, bin));
+			const int at = base + __popc(live & lt_mask);
+			st_stream(pool.trav_rank + at, atomicAdd(pool.bins + bin, 1));
+			st_stream(pool.trav_tmp + at, make_uint2((uint32_t)slot, bin));
 		}
 	}
 	// the launch loop stops when no slot holds a ray and the shard's queue is dry

@@ -30,16 +30,20 @@ def reduce_partials(hist, first_sample, real_length, dst: int = 0) -> None:
     dist.reduce(real_length, dst=dst, op=dist.ReduceOp.MAX)
 
 
-def create_replicated_scene(verts, tri_material, materials, device: int, src: int = 0):
-    """One host BVH build per job: rank `src` builds the scene on its GPU, broadcasts the device image
-    (header + nodes + triangle records + materials, one contiguous buffer) over NCCL / NVLink, and the other
-    ranks adopt the received bytes (ear_b200_scene_create_from_image).  With a single process this is just
-    Scene(...).  Needs the NCCL backend for world > 1 (the image lives in device memory)."""
+def create_replicated_scene(verts, tri_material, materials, device: int, src: int = 0, how: str = "auto"):
+    """The scene on every rank's GPU.  The BVH is built on the device (a few ms for 1M triangles), so by default every
+    rank simply builds its own copy from the host triangles (the builder is deterministic: the copies are identical).
+    how="broadcast" is the form the host builder needs (EAR_B200_BUILD=host): rank `src` builds, broadcasts the device
+    image (header + nodes + triangle records + materials, one contiguous buffer) over NCCL / NVLink, and the other
+    ranks adopt the bytes (ear_b200_scene_create_from_image) -- one host build per job instead of one per rank."""
+    import os
     import torch
     import torch.distributed as dist
     from . import api
     world = dist.get_world_size() if dist.is_initialized() else 1
-    if world == 1:
+    if how == "auto":
+        how = "broadcast" if os.environ.get("EAR_B200_BUILD") == "host" else "each"
+    if world == 1 or how == "each":
         return api.Scene(verts, tri_material, materials, device=device)
     rank = dist.get_rank()
     dev = torch.device("cuda", device)

@@ -114,8 +114,9 @@ typedef struct ear_b200_result {
 } ear_b200_result;
 
 /* Cumulative per-scene launch statistics of the trace engine (reset by ear_b200_scene_stats_reset).
- * Kernel classes: 0 shade/refill/enqueue, 1 closest-hit traversal, 2 any-hit traversal, 3 splat,
- * 4 fused single-kernel engine, 5 finalise (scale, direct).  ms[] are CUDA-event times on the launch stream. */
+ * Kernel classes: 0 shade/refill/enqueue, 1 closest-hit traversal, 2 BVH any-hit traversal, 3 splat,
+ * 4 list binning (scan, scatter), 5 finalise (scale, direct), 6 visibility-map lookups, 7 visibility-map builds.
+ * ms[] are CUDA-event times on the launch stream. */
 typedef struct ear_b200_stats {
 	uint64_t launches[8];
 	double ms[8];
