@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 ( timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_device_bvh.py -q -x -k "tiny or edge" ) > gpurun_out/c2_memcheck.log 2>&1
 echo "memcheck rc=$?" | tee -a gpurun_out/c2_memcheck.log
 tail -15 gpurun_out/c2_memcheck.log
-( time timeout 900 python -m pytest tests/test_gpu_device_bvh.py tests/test_gpu_round2.py tests/test_gpu_fullsize.py tests/test_gpu_parity.py -q -x --deselect tests/test_gpu_round2.py::test_default_culling_equals_exact_on_1e8_adversarial_rays ) > gpurun_out/c2_pytest.log 2>&1
+( time timeout 900 python -m pytest tests/test_gpu_device_bvh.py tests/test_dropin_gpu.py tests/test_gpu_round2.py tests/test_gpu_fullsize.py tests/test_gpu_parity.py tests/test_cli_gpu.py -q --deselect tests/test_gpu_round2.py::test_default_culling_equals_exact_on_1e8_adversarial_rays ) > gpurun_out/c2_pytest.log 2>&1
 echo "pytest rc=$?" >> gpurun_out/c2_pytest.log
 tail -6 gpurun_out/c2_pytest.log
 B="python bench.py --steps 2 --warmup 1 --no-cpu-baseline --rays 4e7"

@@ -1,0 +1,98 @@
+"""The drop-in proof: oracle/_ref/EAR_ref_gpu is the REFERENCE's own CLI -- its parser, band
+split, post chain, convolution, merge and WAV writer, object code built from /root/reference -- with the Scene::Render
+thread fan-out replaced by INTEGRATION.md's binding to libear_b200.so (oracle/ref_gpu_stub.cpp).  For one seed it must
+print the T60 this repo's own `EAR` prints and write byte-identical WAV files: that pins, at once, the C-ABI binding
+and this repo's host surface (`.ear` parse src/Datatype.cpp:81-163 + src/Mesh.cpp:77-108, band split
+lib/equalizer/Equalizer.cpp:81-96, WAV load / save lib/wave/WaveFile.cpp:157-256, Power / Truncate / T60
+src/EAR.cpp:209-228, RecorderTrack::Process src/Recorder.cpp:247-292, merge / normalise src/EAR.cpp:357-386)
+against the reference's, because both binaries receive identical tracks from the library."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from ear_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EAR = os.path.join(ROOT, "ear_b200", "csrc", "EAR")
+REF_GPU = os.path.join(ROOT, "oracle", "_ref", "EAR_ref_gpu")
+
+
+def _run(exe, args, env, cwd):
+    e = dict(os.environ)
+    e.update(env)
+    return subprocess.run([exe, *args], capture_output=True, text=True, env=e, timeout=900, cwd=cwd, stdin=subprocess.DEVNULL)
+
+
+def _need_binaries():
+    if not (os.path.exists(EAR) and os.path.exists(REF_GPU)):
+        pytest.skip("EAR / oracle/_ref/EAR_ref_gpu not built (python -c 'import __graft_entry__ as g; g.build()')")
+
+
+@pytest.mark.parametrize("stereo,spec", [(False, (0.0, 0.5, 0.0)), (True, (0.0, 1.0, 0.0))])
+def test_calc_t60_is_identical_through_the_reference_binding(tmp_path, stereo, spec):
+    _need_binaries()
+    wav = scenes.write_click_wav(str(tmp_path / "click.wav"))
+    sc = scenes.rt60_scene(samples=60000, wav=wav, stereo=stereo, spec=spec)
+    path = str(tmp_path / "rt60.ear")
+    sc.write(path)
+    env = {"EAR_SEED": "4242", "EAR_GPUS": "1"}
+    ours = _run(EAR, ["calc", "T60", path], env, str(tmp_path))
+    ref = _run(REF_GPU, ["calc", "T60", path], env, str(tmp_path))
+    assert ours.returncode == 0 and ref.returncode == 0, (ours.stdout[-400:], ref.stdout[-400:])
+    a = re.findall(r"T60_\w+\s*: ([0-9.]+)s", ours.stdout)
+    b = re.findall(r"T60_\w+\s*: ([0-9.]+)s", ref.stdout)
+    assert len(a) == 3 and a == b, (a, b)
+
+
+def _render_both(tmp_path, sc, name, env):
+    out = {}
+    for tag, exe in (("ours", EAR), ("ref", REF_GPU)):
+        d = tmp_path / tag
+        d.mkdir()
+        for k, rec in enumerate(sc.recorders):
+            rec.filename = str(d / f"out{k}.wav")
+        dbg = d / "debug"
+        dbg.mkdir()
+        sc.debugdir = str(dbg) + "/"
+        path = str(d / f"{name}.ear")
+        sc.write(path)
+        r = _run(exe, ["render", path], env, str(d))
+        assert r.returncode == 0, (tag, r.stdout[-800:], r.stderr[-400:])
+        out[tag] = d
+    return out
+
+
+def _same_files(a_dir, b_dir, pattern):
+    names = sorted(n for n in os.listdir(a_dir) if re.search(pattern, n))
+    assert names and names == sorted(n for n in os.listdir(b_dir) if re.search(pattern, n)), (names, os.listdir(b_dir))
+    for n in names:
+        a, b = open(os.path.join(a_dir, n), "rb").read(), open(os.path.join(b_dir, n), "rb").read()
+        assert a == b, f"{n}: {len(a)} vs {len(b)} bytes, first difference at {next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), -1)}"
+    return names
+
+
+def test_render_writes_identical_wavs_through_the_reference_binding(tmp_path):
+    """example1 (BASELINE config 2): click.wav through a stereo recorder, three bands, full render."""
+    _need_binaries()
+    wav = scenes.write_click_wav(str(tmp_path / "click.wav"))
+    sc = scenes.example1_scene(samples=30000, wav=wav, stereo=True)
+    out = _render_both(tmp_path, sc, "ex1", {"EAR_SEED": "9", "EAR_MAX_BOUNCES": "300", "EAR_GPUS": "1"})
+    _same_files(out["ours"], out["ref"], r"^out\d+\.wav$")
+    # the per-context dumps: raw tracks (.bin), band responses and processed tracks (.wav)
+    names = _same_files(out["ours"] / "debug", out["ref"] / "debug", r"\.(bin|wav)$")
+    assert len(names) >= 9
+
+
+def test_render_mono_and_two_recorders(tmp_path):
+    _need_binaries()
+    from ear_b200.earfile import RecorderDef
+    wav = scenes.write_click_wav(str(tmp_path / "click.wav"))
+    sc = scenes.rt60_scene(samples=20000, wav=wav, air=(0.001, 0.002, 0.004))
+    sc.recorders.append(RecorderDef(str(tmp_path / "b.wav"), position=(1.0, 2.0, 1.2), stereo=True, right_ear=(0.0, 1.0, 0.0),
+                                    head_size=0.25, head_absorption=(0.2, 0.4, 0.8)))
+    out = _render_both(tmp_path, sc, "two", {"EAR_SEED": "31", "EAR_MAX_BOUNCES": "150", "EAR_GPUS": "1"})
+    _same_files(out["ours"], out["ref"], r"^out\d+\.wav$")
