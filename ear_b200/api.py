@@ -44,7 +44,7 @@ class ContextC(C.Structure):
 class OptionsC(C.Structure):
     _fields_ = [("max_bounces", C.c_int32), ("n_bins", C.c_int32), ("seed", C.c_uint64),
                 ("first_ray", C.c_int64), ("ray_count", C.c_int64), ("finalise", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("post_exponent", C.c_float), ("post_divisor", C.c_float)]
 
 
 class TrackC(C.Structure):
@@ -56,7 +56,8 @@ class ResultC(C.Structure):
     _fields_ = [("n_contexts", C.c_int32), ("n_recorders", C.c_int32), ("tracks", C.POINTER(TrackC)),
                 ("rays", C.c_uint64), ("segments", C.c_uint64), ("occlusion_queries", C.c_uint64),
                 ("contributions", C.c_uint64), ("bin_updates", C.c_uint64), ("dropped_updates", C.c_uint64),
-                ("device_ms", C.c_double), ("bvh_build_ms", C.c_double)]
+                ("device_ms", C.c_double), ("bvh_build_ms", C.c_double), ("t60", C.POINTER(C.c_float)),
+                ("maximum", C.c_float), ("reserved", C.c_float)]
 
 
 class StatsC(C.Structure):
@@ -72,7 +73,8 @@ EXPORTS = [
     "ear_b200_default_bins", "ear_b200_scene_stats", "ear_b200_scene_stats_reset", "ear_b200_convolve",
     "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
     "ear_b200_post_power_device", "ear_b200_post_truncate_device", "ear_b200_tracks_per_recorder",
-    "ear_b200_scene_set_emitters",
+    "ear_b200_scene_set_emitters", "ear_b200_group_create", "ear_b200_group_destroy", "ear_b200_group_size",
+    "ear_b200_group_render",
 ]
 
 _lib = None
@@ -106,6 +108,12 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.ear_b200_trace_paths.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(OptionsC), i64, vp, vp]
     lib.ear_b200_render.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(RecorderC), i32, C.POINTER(OptionsC),
                                     C.POINTER(C.POINTER(ResultC))]
+    lib.ear_b200_group_create.argtypes = [vp, C.POINTER(i32), i32, C.POINTER(vp)]
+    lib.ear_b200_group_destroy.argtypes = [vp]
+    lib.ear_b200_group_destroy.restype = None
+    lib.ear_b200_group_size.argtypes = [vp]
+    lib.ear_b200_group_render.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(RecorderC), i32, C.POINTER(OptionsC),
+                                          C.POINTER(C.POINTER(ResultC))]
     lib.ear_b200_result_free.argtypes = [C.POINTER(ResultC)]
     lib.ear_b200_result_free.restype = None
     lib.ear_b200_trace_device.argtypes = [vp, C.POINTER(ContextC), i32, C.POINTER(RecorderC), i32,
@@ -191,10 +199,13 @@ def powf4(x: np.float32) -> np.float32:
     return np.float32(_libm.powf(float(x), 4.0))
 
 
-def make_options(max_bounces=1000, n_bins=0, seed=1, first_ray=0, ray_count=-1, finalise=True) -> OptionsC:
+def make_options(max_bounces=1000, n_bins=0, seed=1, first_ray=0, ray_count=-1, finalise=True, post=None) -> OptionsC:
+    """post=(exponent, divisor): run Render()'s post chain on the device before the download (the reference: 0.335, 256)."""
     o = OptionsC()
     o.max_bounces, o.n_bins, o.seed = int(max_bounces), int(n_bins), int(seed)
     o.first_ray, o.ray_count, o.finalise = int(first_ray), int(ray_count), 1 if finalise else 0
+    if post is not None:
+        o.post_exponent, o.post_divisor = float(post[0]), float(post[1])
     return o
 
 
@@ -371,43 +382,81 @@ class Scene:
         return int(self.lib.ear_b200_default_bins(self.handle, C.byref(opt)))
 
     def render(self, contexts: Sequence[Context], recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0,
-               first_ray: int = 0, ray_count: int = -1, finalise: bool = True) -> RenderResult:
-        import time
-        t0 = time.perf_counter()
-        ctx = pack_contexts(contexts)
-        rec, n_rec = pack_recorders(recorders, len(contexts))
-        opt = make_options(max_bounces, n_bins, seed, first_ray, ray_count, finalise)
-        res = C.POINTER(ResultC)()
-        t1 = time.perf_counter()
-        _check(self.lib, self.lib.ear_b200_render(self.handle, ctx, len(contexts), rec, n_rec, C.byref(opt),
-                                                   C.byref(res)))
-        t2 = time.perf_counter()
+               first_ray: int = 0, ray_count: int = -1, finalise: bool = True, post=None) -> RenderResult:
+        return _render_call(self.lib, self.lib.ear_b200_render, self.handle, contexts, recorders, max_bounces, seed, n_bins,
+                            first_ray, ray_count, finalise, post)
+
+
+def _render_call(lib, fn, handle, contexts, recorders, max_bounces, seed, n_bins, first_ray, ray_count, finalise, post):
+    import time
+    t0 = time.perf_counter()
+    ctx = pack_contexts(contexts)
+    rec, n_rec = pack_recorders(recorders, len(contexts))
+    opt = make_options(max_bounces, n_bins, seed, first_ray, ray_count, finalise, post)
+    res = C.POINTER(ResultC)()
+    t1 = time.perf_counter()
+    _check(lib, fn(handle, ctx, len(contexts), rec, n_rec, C.byref(opt), C.byref(res)))
+    t2 = time.perf_counter()
+    try:
+        r = res.contents
+        tracks, t60 = [], []
+        for c in range(r.n_contexts):
+            per_rec, per_t60 = [], []
+            for k in range(r.n_recorders):
+                pair, pair_t60 = [], []
+                n_tracks = 2 if rec[c * n_rec + k].kind == STEREO else 1
+                for tr in range(n_tracks):
+                    t = r.tracks[(c * r.n_recorders + k) * 2 + tr]
+                    # one memcpy out of the library-owned buffer (np.ctypeslib.as_array on a pointer builds a ctypes
+                    # array type per call and is an order of magnitude slower for 1e6-sample tracks)
+                    data = np.empty((t.length,), np.float32)
+                    C.memmove(data.ctypes.data, t.data, t.length * 4)
+                    pair.append(Track(data, int(t.first_sample), int(t.real_length)))
+                    if r.t60:
+                        pair_t60.append(float(r.t60[(c * r.n_recorders + k) * 2 + tr]))
+                per_rec.append(pair)
+                per_t60.append(pair_t60)
+            tracks.append(per_rec)
+            t60.append(per_t60)
+        out = RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
+                           int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
+        if r.t60:
+            out.maximum, out.t60 = float(r.maximum), t60
+    finally:
+        lib.ear_b200_result_free(res)
+    if os.environ.get("EAR_B200_DEBUG"):
+        t3 = time.perf_counter()
+        print(f"[ear_b200.api] render: pack {1e3 * (t1 - t0):.1f} ms, library call {1e3 * (t2 - t1):.1f} ms, "
+              f"track copies {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
+    return out
+
+
+class Group:
+    """`scene` replicated on several GPUs of this process (ear_b200_group): render() shards the ray ids of every context
+    over the GPUs and reduces the partial histograms onto the scene's own GPU through peer memory."""
+
+    def __init__(self, scene: Scene, devices: Sequence[int]):
+        self.scene, self.lib = scene, scene.lib
+        arr = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _check(self.lib, self.lib.ear_b200_group_create(scene.handle, arr, len(devices), C.byref(h)))
+        self.handle = h
+
+    def render(self, contexts, recorders, max_bounces: int = 1000, seed: int = 1, n_bins: int = 0, first_ray: int = 0,
+               ray_count: int = -1, finalise: bool = True, post=None) -> RenderResult:
+        return _render_call(self.lib, self.lib.ear_b200_group_render, self.handle, contexts, recorders, max_bounces, seed, n_bins,
+                            first_ray, ray_count, finalise, post)
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.ear_b200_group_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
         try:
-            r = res.contents
-            tracks = []
-            for c in range(r.n_contexts):
-                per_rec = []
-                for k in range(r.n_recorders):
-                    pair = []
-                    n_tracks = 2 if rec[c * n_rec + k].kind == STEREO else 1
-                    for tr in range(n_tracks):
-                        t = r.tracks[(c * r.n_recorders + k) * 2 + tr]
-                        # one memcpy out of the library-owned buffer (np.ctypeslib.as_array on a pointer builds a ctypes
-                        # array type per call and is an order of magnitude slower for 1e6-sample tracks)
-                        data = np.empty((t.length,), np.float32)
-                        C.memmove(data.ctypes.data, t.data, t.length * 4)
-                        pair.append(Track(data, int(t.first_sample), int(t.real_length)))
-                    per_rec.append(pair)
-                tracks.append(per_rec)
-            out = RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
-                               int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
-        finally:
-            self.lib.ear_b200_result_free(res)
-        if os.environ.get("EAR_B200_DEBUG"):
-            t3 = time.perf_counter()
-            print(f"[ear_b200.api] render: pack {1e3 * (t1 - t0):.1f} ms, library call {1e3 * (t2 - t1):.1f} ms, "
-                  f"track copies {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
-        return out
+            self.close()
+        except Exception:
+            pass
 
 
 def contexts_from_def(scene_def, t60_only: bool = False, n_bands: int = 3, air_factors=None):

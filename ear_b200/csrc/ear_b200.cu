@@ -244,6 +244,7 @@ struct ear_b200_scene {
 	float4* d_emitters = nullptr;       // emitter triangles of mesh sources, 4 float4 each (ear_b200_scene_set_emitters)
 	int32_t n_emitters = 0;
 	std::vector<float> emitter_area;    // host copy of the areas: Mesh::total_area per context is summed on the host
+	std::vector<float> emitter_verts;   // host copy of the table (replicas on other GPUs are given the same emitters)
 	float4* d_nodes = nullptr;          // views into d_image
 	float4* d_tris = nullptr;
 	float4* d_materials = nullptr;
@@ -300,6 +301,7 @@ extern "C" int32_t ear_b200_device_count(void) {
 }
 
 extern "C" void ear_b200_scene_destroy(ear_b200_scene* s);
+extern "C" void ear_b200_group_destroy(ear_b200_group* g);
 
 // Device image of a scene: [header | nodes | triangle records | materials] in ONE allocation, so a scene built
 // on one GPU can be replicated to the others with a single NVLink broadcast instead of N host BVH builds.
@@ -465,11 +467,12 @@ extern "C" int32_t ear_b200_scene_set_emitters(ear_b200_scene* s, const float* v
 	if (!s) return fail("scene_set_emitters: null scene");
 	if (n < 0 || (n > 0 && !verts)) return fail("scene_set_emitters: bad arguments");
 	CUDA_TRY(cudaSetDevice(s->device));
-	cudaFree(s->d_emitters); s->d_emitters = nullptr; s->n_emitters = 0; s->emitter_area.clear();
+	cudaFree(s->d_emitters); s->d_emitters = nullptr; s->n_emitters = 0; s->emitter_area.clear(); s->emitter_verts.clear();
 	s->dev.emitters = nullptr;
 	if (n == 0) return 0;
 	std::vector<float> rec((size_t)n * 16, 0.0f);
 	s->emitter_area.resize((size_t)n);
+	s->emitter_verts.assign(verts, verts + 9 * (size_t)n);
 	for (int32_t i = 0; i < n; ++i) {
 		const float* p = verts + 9 * (size_t)i;
 		float* r = rec.data() + 16 * (size_t)i;
@@ -1146,56 +1149,84 @@ extern "C" int32_t ear_b200_post_truncate_device(ear_b200_scene* s, const ear_b2
 	return 0;
 }
 
-extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,
-                                   const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt,
-                                   ear_b200_result** out) {
-	if (!s || !out) return fail("render: null scene/out");
-	*out = nullptr;
-	CUDA_TRY(cudaSetDevice(s->device));
-	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
-	auto tick = std::chrono::steady_clock::now();
-	auto lap = [&](const char* what) {
-		if (!dbg) return;
-		cudaDeviceSynchronize();
-		const auto now = std::chrono::steady_clock::now();
-		std::fprintf(stderr, "[ear_b200] render: %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tick).count());
-		tick = now;
-	};
-	RenderParams p{};
-	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, s->stream, p)) return rc;
-	const int32_t n_bins = ear_b200_default_bins(s, opt);
-	const int tpr = p.tpr;
-	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
-	DevBuf<float> d_hist;
-	DevBuf<uint32_t> d_range;
-	DevBuf<unsigned long long> d_counters;
-	CUDA_TRY(d_hist.alloc(n_tracks * (size_t)n_bins));
-	CUDA_TRY(d_range.alloc(n_tracks * 2));
-	CUDA_TRY(d_counters.alloc(8));
-	CUDA_TRY(cudaMemsetAsync(d_hist, 0, n_tracks * n_bins * sizeof(float), s->stream));
-	CUDA_TRY(cudaMemsetAsync(d_counters, 0, 8 * sizeof(unsigned long long), s->stream));
-	init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(d_range, (int)n_tracks);
-	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = d_counters;
-	lap("upload + histogram alloc");
-	struct Events {   // destroyed on every return path
-		cudaEvent_t a = nullptr, b = nullptr;
-		~Events() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
-	} ev;
-	CUDA_TRY(cudaEventCreate(&ev.a)); CUDA_TRY(cudaEventCreate(&ev.b));
-	cudaEvent_t e0 = ev.a, e1 = ev.b;
-	CUDA_TRY(cudaEventRecord(e0, s->stream));
-	if (int32_t rc = launch_trace(s, p, s->stream)) return rc;
-	CUDA_TRY(cudaEventRecord(e1, s->stream));
-	lap("trace (incl. pool + maps)");
-	if (!opt || opt->finalise) { if (int32_t rc = launch_finalise(s, p, s->stream)) return rc; }
-	std::vector<uint32_t> range(n_tracks * 2);
-	unsigned long long counters[8];
-	CUDA_TRY(cudaMemcpyAsync(range.data(), d_range, range.size() * 4, cudaMemcpyDeviceToHost, s->stream));
-	CUDA_TRY(cudaMemcpyAsync(counters, d_counters, sizeof(counters), cudaMemcpyDeviceToHost, s->stream));
-	CUDA_TRY(cudaStreamSynchronize(s->stream));
-	float ms = 0.0f;
-	CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+// ------------------------------------------------------------------------------------------
+// Scene::Render fan-out over the GPUs of one process (src/EAR.cpp:196-207 is the seam): ray sharding + peer reduce
+// ------------------------------------------------------------------------------------------
+struct ear_b200_group {
+	std::vector<ear_b200_scene*> scenes;   // [0] belongs to the caller, the others are clones owned by the group
+	bool peer = true;                      // every other GPU can address GPU 0's memory and vice versa
+};
 
+// hist0[i] = sum over k of part[k][i] for i in [begin, end): run by GPU g on its slice, reading its peers' partial
+// histograms over NVLink and writing the sum straight into GPU 0's buffer (part[0]).  Fixed order: deterministic.
+struct PeerParts { const float* part[16]; int n; };
+__global__ void __launch_bounds__(256) peer_reduce_kernel(PeerParts parts, float* dst, size_t begin, size_t end) {
+	const size_t stride = (size_t)gridDim.x * blockDim.x * 4;
+	for (size_t i = begin + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < end; i += stride) {
+		if (i + 4 <= end) {
+			float4 acc = *reinterpret_cast<const float4*>(parts.part[0] + i);
+			for (int k = 1; k < parts.n; ++k) {
+				const float4 v = *reinterpret_cast<const float4*>(parts.part[k] + i);
+				acc.x = fadd(acc.x, v.x); acc.y = fadd(acc.y, v.y); acc.z = fadd(acc.z, v.z); acc.w = fadd(acc.w, v.w);
+			}
+			*reinterpret_cast<float4*>(dst + i) = acc;
+		} else {
+			for (size_t j = i; j < end; ++j) {
+				float acc = parts.part[0][j];
+				for (int k = 1; k < parts.n; ++k) acc = fadd(acc, parts.part[k][j]);
+				dst[j] = acc;
+			}
+		}
+	}
+}
+__global__ void add_into_kernel(float* dst, const float* src, size_t n) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = fadd(dst[i], src[i]);
+}
+
+extern "C" int32_t ear_b200_group_create(ear_b200_scene* scene, const int32_t* devices, int32_t n_devices, ear_b200_group** out) {
+	if (!scene || !out || !devices || n_devices < 1) return fail("group_create: bad arguments");
+	*out = nullptr;
+	if (n_devices > 16) return fail("group_create: at most 16 GPUs");
+	if (devices[0] != scene->device) return fail("group_create: devices[0] must be the scene's own device");
+	std::unique_ptr<ear_b200_group, void (*)(ear_b200_group*)> g(new ear_b200_group(), ear_b200_group_destroy);
+	g->scenes.push_back(scene);
+	for (int32_t k = 1; k < n_devices; ++k) {
+		for (int32_t j = 0; j < k; ++j) if (devices[j] == devices[k]) return fail("group_create: a device is listed twice");
+		ear_b200_scene* c = nullptr;
+		if (int32_t rc = ear_b200_scene_clone(scene, devices[k], &c)) return rc;
+		g->scenes.push_back(c);
+		if (!scene->emitter_verts.empty())
+			if (int32_t rc = ear_b200_scene_set_emitters(c, scene->emitter_verts.data(), (int32_t)(scene->emitter_verts.size() / 9))) return rc;
+	}
+	// peer access between GPU 0 and every other GPU, both directions (the sliced reduce reads all partials)
+	for (int32_t a = 0; a < n_devices && g->peer; ++a)
+		for (int32_t b = 0; b < n_devices && g->peer; ++b) {
+			if (a == b) continue;
+			int can = 0;
+			if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) != cudaSuccess || !can) { g->peer = false; cudaGetLastError(); break; }
+			CUDA_TRY(cudaSetDevice(devices[a]));
+			const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+			if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { g->peer = false; }
+			cudaGetLastError();
+		}
+	*out = g.release();
+	return 0;
+}
+extern "C" void ear_b200_group_destroy(ear_b200_group* g) {
+	if (!g) return;
+	for (size_t k = 1; k < g->scenes.size(); ++k) ear_b200_scene_destroy(g->scenes[k]);
+	delete g;
+}
+extern "C" int32_t ear_b200_group_size(ear_b200_group* g) { return g ? (int32_t)g->scenes.size() : 0; }
+
+// host tracks out of GPU 0's buffers (shared by the single- and multi-GPU renders)
+static int32_t assemble_result(ear_b200_scene* s, const ear_b200_recorder* rec, int32_t n_ctx, int32_t n_rec, int tpr, int32_t n_bins,
+                               const float* d_hist, const uint32_t* d_range, const unsigned long long counters[8], double ms,
+                               float maximum, const float* t60, ear_b200_result** out) {
+	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
+	std::vector<uint32_t> range(n_tracks * 2);
+	CUDA_TRY(cudaMemcpyAsync(range.data(), d_range, range.size() * 4, cudaMemcpyDeviceToHost, s->stream));
+	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	// the result is the caller's once it is handed out; until then every error path frees it
 	std::unique_ptr<ear_b200_result, void (*)(ear_b200_result*)> holder((ear_b200_result*)calloc(1, sizeof(ear_b200_result)),
 	                                                                    ear_b200_result_free);
@@ -1205,6 +1236,10 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 	// the result keeps the [context][recorder][2] shape whatever the device layout was (mono: slot 0 only)
 	res->tracks = (ear_b200_track*)calloc((size_t)n_ctx * n_rec * 2, sizeof(ear_b200_track));
 	if (!res->tracks) return fail("render: out of host memory");
+	if (t60) {
+		res->t60 = (float*)calloc((size_t)n_ctx * n_rec * 2, sizeof(float));
+		if (!res->t60) return fail("render: out of host memory");
+	}
 	for (size_t j = 0; j < (size_t)n_ctx * n_rec; ++j)
 		for (int k = 0; k < 2; ++k) {
 			ear_b200_track& tr = res->tracks[2 * j + k];
@@ -1217,14 +1252,168 @@ extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ct
 			if (!tr.data) return fail("render: out of host memory");
 			const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
 			CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + t * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+			if (t60) res->t60[2 * j + k] = t60[t];
 		}
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
-	lap("finalise + track download");
 	res->rays = counters[0]; res->segments = counters[1]; res->occlusion_queries = counters[2];
 	res->contributions = counters[3]; res->bin_updates = counters[4]; res->dropped_updates = counters[5];
-	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms;
+	res->device_ms = ms; res->bvh_build_ms = s->bvh_build_ms; res->maximum = maximum;
 	*out = holder.release();
 	return 0;
+}
+
+// Render()'s post chain on GPU 0's finalised tracks (opt->post_exponent > 0), see ear_b200_post_*_device
+static int32_t run_post(ear_b200_scene* s, const ear_b200_recorder* rec, int32_t n_ctx, int32_t n_rec, int32_t n_bins, float* d_hist,
+                        uint32_t* d_range, const ear_b200_options* opt, float& maximum, std::vector<float>& t60) {
+	const size_t n_tracks = (size_t)n_ctx * n_rec * ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
+	if (int32_t rc = ear_b200_post_power_device(s, rec, n_ctx, n_rec, n_bins, d_hist, d_range, opt->post_exponent, &maximum, nullptr, s->stream)) return rc;
+	t60.assign(n_tracks, 0.0f);
+	const float threshold = opt->post_divisor > 0.0f ? maximum / opt->post_divisor : -1.0f;
+	return ear_b200_post_truncate_device(s, rec, n_ctx, n_rec, n_bins, d_hist, d_range, threshold, t60.data(), s->stream);
+}
+
+static int32_t render_on(std::vector<ear_b200_scene*>& scenes, bool peer, const ear_b200_context* ctx, int32_t n_ctx,
+                         const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt, ear_b200_result** out) {
+	const int G = (int)scenes.size();
+	ear_b200_scene* s0 = scenes[0];
+	if (n_ctx <= 0 || n_rec <= 0 || !ctx || !rec) return fail("render: need at least one context and one recorder");
+	const int32_t n_bins = ear_b200_default_bins(s0, opt);
+	const int tpr = ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
+	const size_t n_tracks = (size_t)n_ctx * n_rec * tpr;
+	const size_t hist_floats = n_tracks * (size_t)n_bins;
+	// ray-id range of this call, dealt to the GPUs in contiguous shares (src/EAR.cpp:196-207 deals whole contexts to
+	// threads; rays shard finer and the Philox streams make the union independent of the deal)
+	long long rays = 0;
+	for (int32_t c = 0; c < n_ctx; ++c) rays = std::max<long long>(rays, ctx[c].num_samples);
+	const long long first = opt ? opt->first_ray : 0;
+	long long count = (opt && opt->ray_count >= 0) ? opt->ray_count : rays - first;
+	count = std::max<long long>(0, std::min<long long>(count, rays - first));
+	struct PerGpu {
+		float* hist = nullptr; uint32_t* range = nullptr; unsigned long long* counters = nullptr;
+		int32_t rc = 0; std::string err; double ms = 0.0;
+		std::vector<uint32_t> h_range; unsigned long long h_counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	};
+	std::vector<PerGpu> per((size_t)G);
+	struct Cleanup {
+		std::vector<PerGpu>& per; std::vector<ear_b200_scene*>& scenes;
+		~Cleanup() {
+			for (size_t g = 0; g < per.size(); ++g) {
+				cudaSetDevice(scenes[g]->device);
+				cudaFree(per[g].hist); cudaFree(per[g].range); cudaFree(per[g].counters);
+			}
+		}
+	} cleanup{per, scenes};
+	auto work = [&](int g) {
+		PerGpu& me = per[(size_t)g];
+		ear_b200_scene* s = scenes[(size_t)g];
+		auto bad = [&](const std::string& what, cudaError_t e) { me.rc = 1; me.err = what + ": " + cudaGetErrorString(e); };
+		cudaError_t e;
+		if ((e = cudaSetDevice(s->device)) != cudaSuccess) return bad("cudaSetDevice", e);
+		if ((e = cudaMalloc(&me.hist, std::max<size_t>(hist_floats, 1) * sizeof(float))) != cudaSuccess) return bad("histogram allocation", e);
+		if ((e = cudaMalloc(&me.range, n_tracks * 2 * sizeof(uint32_t))) != cudaSuccess) return bad("range allocation", e);
+		if ((e = cudaMalloc(&me.counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bad("counter allocation", e);
+		cudaMemsetAsync(me.hist, 0, hist_floats * sizeof(float), s->stream);
+		cudaMemsetAsync(me.counters, 0, 8 * sizeof(unsigned long long), s->stream);
+		init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(me.range, (int)n_tracks);
+		ear_b200_options o{};
+		if (opt) o = *opt;
+		o.first_ray = first + count * g / G;
+		o.ray_count = first + count * (g + 1) / G - o.first_ray;
+		o.finalise = 0;
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaEventRecord(e0, s->stream);
+		me.rc = ear_b200_trace_device(s, ctx, n_ctx, rec, n_rec, &o, n_bins, me.hist, me.range, (uint64_t*)me.counters, s->stream);
+		if (me.rc) me.err = g_last_error;   // per-thread error text: carry it to the caller's thread
+		cudaEventRecord(e1, s->stream);
+		me.h_range.resize(n_tracks * 2);
+		cudaMemcpyAsync(me.h_range.data(), me.range, n_tracks * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream);
+		cudaMemcpyAsync(me.h_counters, me.counters, sizeof(me.h_counters), cudaMemcpyDeviceToHost, s->stream);
+		if ((e = cudaStreamSynchronize(s->stream)) != cudaSuccess && !me.rc) bad("trace", e);
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		me.ms = ms;
+		cudaEventDestroy(e0); cudaEventDestroy(e1);
+	};
+	if (G == 1) work(0);
+	else {
+		std::vector<std::thread> threads;
+		for (int g = 0; g < G; ++g) threads.emplace_back(work, g);
+		for (auto& t : threads) t.join();
+	}
+	for (int g = 0; g < G; ++g) if (per[(size_t)g].rc) return fail(per[(size_t)g].err);
+	double ms = 0.0;
+	unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+	for (int g = 0; g < G; ++g) {
+		ms = std::max(ms, per[(size_t)g].ms);
+		for (int k = 0; k < 8; ++k) counters[k] += per[(size_t)g].h_counters[k];
+	}
+	if (G > 1) {
+		// ---- ONE reduce of the partial histograms onto GPU 0 ----
+		if (peer) {
+			// sliced: GPU g sums slice g of all partials (peer reads over NVLink) and writes it into GPU 0's buffer
+			PeerParts parts{};
+			parts.n = G;
+			for (int g = 0; g < G; ++g) parts.part[g] = per[(size_t)g].hist;
+			const size_t quads = (hist_floats + 3) / 4;
+			for (int g = 0; g < G; ++g) {
+				const size_t begin = std::min(hist_floats, quads * g / G * 4), end = std::min(hist_floats, quads * (g + 1) / G * 4);
+				if (end <= begin) continue;
+				CUDA_TRY(cudaSetDevice(scenes[(size_t)g]->device));
+				peer_reduce_kernel<<<scenes[(size_t)g]->sm_count * 4, 256, 0, scenes[(size_t)g]->stream>>>(parts, per[0].hist, begin, end);
+				CUDA_TRY(cudaGetLastError());
+			}
+			for (int g = 0; g < G; ++g) {
+				CUDA_TRY(cudaSetDevice(scenes[(size_t)g]->device));
+				CUDA_TRY(cudaStreamSynchronize(scenes[(size_t)g]->stream));
+			}
+		} else {
+			// no peer addressing: copy every partial to GPU 0 and add it there
+			CUDA_TRY(cudaSetDevice(s0->device));
+			DevBuf<float> stage;
+			CUDA_TRY(stage.alloc(hist_floats));
+			for (int g = 1; g < G; ++g) {
+				CUDA_TRY(cudaMemcpyPeerAsync(stage, s0->device, per[(size_t)g].hist, scenes[(size_t)g]->device, hist_floats * sizeof(float), s0->stream));
+				add_into_kernel<<<s0->sm_count * 8, 256, 0, s0->stream>>>(per[0].hist, stage, hist_floats);
+			}
+			CUDA_TRY(cudaStreamSynchronize(s0->stream));
+		}
+		// track ranges: min / max over the GPUs (a few words per track: on the host)
+		std::vector<uint32_t>& r0 = per[0].h_range;
+		for (int g = 1; g < G; ++g)
+			for (size_t t = 0; t < n_tracks; ++t) {
+				r0[2 * t] = std::min(r0[2 * t], per[(size_t)g].h_range[2 * t]);
+				r0[2 * t + 1] = std::max(r0[2 * t + 1], per[(size_t)g].h_range[2 * t + 1]);
+			}
+		CUDA_TRY(cudaSetDevice(s0->device));
+		CUDA_TRY(cudaMemcpyAsync(per[0].range, r0.data(), n_tracks * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s0->stream));
+	}
+	CUDA_TRY(cudaSetDevice(s0->device));
+	float maximum = 0.0f;
+	std::vector<float> t60;
+	if (!opt || opt->finalise) {
+		if (int32_t rc = ear_b200_finalise_device(s0, ctx, n_ctx, rec, n_rec, n_bins, per[0].hist, per[0].range, s0->stream)) return rc;
+		if (opt && opt->post_exponent > 0.0f)
+			if (int32_t rc = run_post(s0, rec, n_ctx, n_rec, n_bins, per[0].hist, per[0].range, opt, maximum, t60)) return rc;
+	}
+	return assemble_result(s0, rec, n_ctx, n_rec, tpr, n_bins, per[0].hist, per[0].range, counters, ms, maximum, t60.empty() ? nullptr : t60.data(), out);
+}
+
+extern "C" int32_t ear_b200_render(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,
+                                   const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt,
+                                   ear_b200_result** out) {
+	if (!s || !out) return fail("render: null scene/out");
+	*out = nullptr;
+	std::vector<ear_b200_scene*> one(1, s);
+	return render_on(one, true, ctx, n_ctx, rec, n_rec, opt, out);
+}
+
+extern "C" int32_t ear_b200_group_render(ear_b200_group* g, const ear_b200_context* ctx, int32_t n_ctx,
+                                         const ear_b200_recorder* rec, int32_t n_rec, const ear_b200_options* opt,
+                                         ear_b200_result** out) {
+	if (!g || !out) return fail("group_render: null group/out");
+	*out = nullptr;
+	return render_on(g->scenes, g->peer, ctx, n_ctx, rec, n_rec, opt, out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1339,6 +1528,7 @@ extern "C" void ear_b200_result_free(ear_b200_result* r) {
 		for (size_t k = 0; k < n; ++k) free(r->tracks[k].data);
 		free(r->tracks);
 	}
+	free(r->t60);
 	free(r);
 }
 

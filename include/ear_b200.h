@@ -88,6 +88,9 @@ typedef struct ear_b200_options {
 	int32_t finalise;             /* 1: apply 1/N, direct sound, gain^2 (src/Scene.cpp:286-316);
 	                                 0: leave raw partial sums (multi-GPU: reduce first, then finalise) */
 	int32_t reserved;
+	float post_exponent;          /* > 0 (with finalise): also run Render()'s post chain on the device before the download --  */
+	float post_divisor;           /*   Power(post_exponent), global maximum, Truncate(getLength(maximum / post_divisor)), T60  */
+	                              /*   (src/EAR.cpp:209-228; the reference uses 0.335 and 256).  0: tracks come back raw.     */
 } ear_b200_options;
 
 /* FloatBuffer view (src/Recorder.h:55-65). `length` is the allocated bin count. */
@@ -109,8 +112,11 @@ typedef struct ear_b200_result {
 	uint64_t contributions;       /* Recorder::Record invocations (src/Scene.cpp:259) */
 	uint64_t bin_updates;         /* track[i] += v operations */
 	uint64_t dropped_updates;     /* bin updates beyond n_bins (must be 0 for parity) */
-	double device_ms;             /* CUDA-event time of the trace kernels on the library's stream */
+	double device_ms;             /* CUDA-event time of the trace kernels on the library's stream (slowest GPU) */
 	double bvh_build_ms;
+	float* t60;                   /* post chain only: RecorderTrack::T60 per track, [n_contexts][n_recorders][2]; else NULL */
+	float maximum;                /* post chain only: the global maximum after Power() */
+	float reserved;
 } ear_b200_result;
 
 /* Cumulative per-scene launch statistics of the trace engine (reset by ear_b200_scene_stats_reset).
@@ -177,6 +183,22 @@ int32_t ear_b200_render(ear_b200_scene* scene, const ear_b200_context* ctx, int3
                         const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
                         ear_b200_result** out);
 void ear_b200_result_free(ear_b200_result* result);
+
+/* Several GPUs in ONE process (the CLI's form).  A group is `scene` plus peer copies of its device
+ * image on the other listed GPUs (devices[0] must be the scene's own device; the scene stays the caller's, the copies
+ * are destroyed with the group).  ear_b200_group_render is ear_b200_render over all of them: every GPU traces a
+ * contiguous share of the ray ids of EVERY context into its own partial histogram (one host thread per GPU); the
+ * partials meet on GPU 0 in one sliced reduce -- GPU g sums slice g of all partials through peer loads over
+ * NVLink / NVSwitch and stores it into GPU 0's buffer -- then GPU 0 finalises (and runs the post chain if asked) and
+ * the tracks are downloaded.  Random streams are keyed by (seed, context, ray id): the result does not depend on the
+ * number of GPUs beyond the order of the float sums. */
+typedef struct ear_b200_group ear_b200_group;
+int32_t ear_b200_group_create(ear_b200_scene* scene, const int32_t* devices, int32_t n_devices, ear_b200_group** out);
+void ear_b200_group_destroy(ear_b200_group* group);
+int32_t ear_b200_group_size(ear_b200_group* group);
+int32_t ear_b200_group_render(ear_b200_group* group, const ear_b200_context* ctx, int32_t n_contexts,
+                              const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
+                              ear_b200_result** out);
 
 /* Device-resident variant for one-process-per-GPU sharding: accumulates raw partial sums into
  * caller-owned device memory so the caller can reduce them across ranks (NCCL) before finalising.

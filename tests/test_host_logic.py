@@ -58,7 +58,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert getattr(lib, name) is not None
     assert lib.ear_b200_abi_version() == 3
-    assert ctypes.sizeof(api.ContextC) == 56 and ctypes.sizeof(api.RecorderC) == 64 and ctypes.sizeof(api.OptionsC) == 40
+    assert ctypes.sizeof(api.ContextC) == 56 and ctypes.sizeof(api.RecorderC) == 64 and ctypes.sizeof(api.OptionsC) == 48
 
 
 def test_no_gpu_means_loud_failure_not_fallback():
