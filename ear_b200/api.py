@@ -300,7 +300,11 @@ class Scene:
     @classmethod
     def from_def(cls, scene_def, materials: Optional[np.ndarray] = None, device: int = 0) -> "Scene":
         tab = scene_def.material_table() if materials is None else materials
-        return cls(scene_def.triangles(), scene_def.triangle_materials(), tab, device)
+        scene = cls(scene_def.triangles(), scene_def.triangle_materials(), tab, device)
+        em = emitter_table(scene_def)
+        if em is not None:
+            scene.set_emitters(em)
+        return scene
 
     @classmethod
     def from_image(cls, image_ptr: int, image_bytes: int, n_bands: int, device: int = 0) -> "Scene":
@@ -459,6 +463,12 @@ class Group:
             pass
 
 
+def emitter_table(scene_def) -> Optional[np.ndarray]:
+    """Emitter triangles of all mesh sources, concatenated in file order ([E][3][3]) -- what Scene.set_emitters takes."""
+    parts = [np.asarray(s.mesh_verts, np.float32).reshape(-1, 3, 3) for s in scene_def.sources if getattr(s, "mesh_verts", None) is not None]
+    return np.concatenate(parts) if parts else None
+
+
 def contexts_from_def(scene_def, t60_only: bool = False, n_bands: int = 3, air_factors=None):
     """The SceneContext list `Render()` builds (src/EAR.cpp:170-191): sound x keyframe x band, with
     rays = samples // 10 (src/EAR.cpp:81) and absorption_factor = 1 - air[band] in float32.
@@ -466,7 +476,13 @@ def contexts_from_def(scene_def, t60_only: bool = False, n_bands: int = 3, air_f
     contexts, recs = [], []
     rays = int(scene_def.samples) // 10
     keys = scene_def.keys
+    emit_at = 0   # mesh sources: position of their triangles in the concatenated emitter table (emitter_table())
     for src in scene_def.sources:
+        emitter = None
+        if getattr(src, "mesh_verts", None) is not None:
+            n_e = int(np.asarray(src.mesh_verts).reshape(-1, 3, 3).shape[0])
+            emitter = (emit_at, n_e)
+            emit_at += n_e
         kfs = range(len(keys)) if keys is not None else [-1]
         for kf in kfs:
             for band in range(n_bands):
@@ -477,7 +493,9 @@ def contexts_from_def(scene_def, t60_only: bool = False, n_bands: int = 3, air_f
                 else:
                     af = np.float32(1.0) - np.float32(scene_def.air_absorption[band])
                 pos = src.animation[kf] if (kf >= 0 and src.animation is not None) else src.position
-                contexts.append(Context(band, rays, float(af), [float(x) for x in pos], scene_def.drylevel, src.gain))
+                if emitter is not None:
+                    pos = (0.0, 0.0, 0.0)   # a mesh source has no location (src/SoundFile.cpp:50-56)
+                contexts.append(Context(band, rays, float(af), [float(x) for x in pos], scene_def.drylevel, src.gain, 0, emitter))
                 rr = []
                 for rec in scene_def.recorders:
                     rpos = rec.animation[kf] if (kf >= 0 and rec.animation is not None) else rec.position

@@ -58,6 +58,7 @@ struct RenderParams {
 	const ear_b200_context* ctx;     // [n_ctx]
 	const ear_b200_recorder* rec;    // [n_ctx][n_rec]
 	const long long* work_prefix;    // [n_ctx + 1] rays of this shard, prefix-summed over contexts
+	const float* ctx_emit_area;      // [n_ctx] Mesh::total_area of a mesh source's emitter (float sum in file order), else 0
 	int32_t n_ctx, n_rec, max_bounces, n_bins;
 	int32_t tpr;                     // tracks per recorder in hist / range: 2 when the call has a stereo recorder, else 1
 	unsigned long long seed;
@@ -287,7 +288,7 @@ struct ear_b200_scene {
 	size_t ev_used = 0;
 	cudaStream_t last_stream = nullptr;
 	// scratch reused across calls
-	ear_b200_context* d_ctx = nullptr; ear_b200_recorder* d_rec = nullptr; long long* d_prefix = nullptr;
+	ear_b200_context* d_ctx = nullptr; ear_b200_recorder* d_rec = nullptr; long long* d_prefix = nullptr; float* d_ctx_area = nullptr;
 	unsigned long long* d_queue = nullptr;
 	size_t ctx_cap = 0, rec_cap = 0;
 };
@@ -553,7 +554,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
 	cudaFree(s->d_image); cudaFree(s->d_spill); cudaFree(s->d_emitters);
-	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue);
+	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue); cudaFree(s->d_ctx_area);
 	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
 	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
 	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
@@ -698,15 +699,29 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 		if (ctx[c].band < 0 || ctx[c].band >= s->n_bands) return fail("render: context band outside the material table");
 		if (ctx[c].num_samples < 0) return fail("render: negative num_samples");
 		if (ctx[c].stream_id < 0) return fail("render: negative stream_id");
+		if (ctx[c].source_kind != EAR_B200_POINT_SOURCE && ctx[c].source_kind != EAR_B200_MESH_SOURCE) return fail("render: unknown source kind");
+		if (ctx[c].source_kind == EAR_B200_MESH_SOURCE &&
+		    (ctx[c].emitter_first < 0 || ctx[c].emitter_count < 0 || (long long)ctx[c].emitter_first + ctx[c].emitter_count > s->n_emitters))
+			return fail("render: a mesh source names triangles outside the emitter table (ear_b200_scene_set_emitters)");
 	}
 	for (int32_t i = 0; i < n_ctx * n_rec; ++i)
 		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("render: unknown recorder kind");
 	if ((size_t)n_ctx > s->ctx_cap) {
-		cudaFree(s->d_ctx); cudaFree(s->d_prefix);
+		cudaFree(s->d_ctx); cudaFree(s->d_prefix); cudaFree(s->d_ctx_area);
+		s->d_ctx = nullptr; s->d_prefix = nullptr; s->d_ctx_area = nullptr; s->ctx_cap = 0;
 		CUDA_TRY(cudaMalloc(&s->d_ctx, sizeof(ear_b200_context) * n_ctx));
 		CUDA_TRY(cudaMalloc(&s->d_prefix, sizeof(long long) * (n_ctx + 1)));
+		CUDA_TRY(cudaMalloc(&s->d_ctx_area, sizeof(float) * n_ctx));
 		s->ctx_cap = n_ctx;
 	}
+	// Mesh::total_area of every mesh source: areas added one by one in file order, in float (src/Mesh.cpp:90)
+	std::vector<float> emit_area((size_t)n_ctx, 0.0f);
+	for (int32_t c = 0; c < n_ctx; ++c)
+		if (ctx[c].source_kind == EAR_B200_MESH_SOURCE) {
+			float total = 0.0f;
+			for (int32_t i = 0; i < ctx[c].emitter_count; ++i) total += s->emitter_area[(size_t)ctx[c].emitter_first + i];
+			emit_area[(size_t)c] = total;
+		}
 	if ((size_t)n_ctx * n_rec > s->rec_cap) {
 		cudaFree(s->d_rec);
 		CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec));
@@ -724,8 +739,9 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	CUDA_TRY(cudaMemcpyAsync(s->d_ctx, ctx, sizeof(ear_b200_context) * n_ctx, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaMemcpyAsync(s->d_prefix, prefix.data(), sizeof(long long) * (n_ctx + 1), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(s->d_ctx_area, emit_area.data(), sizeof(float) * n_ctx, cudaMemcpyHostToDevice, stream));
 	CUDA_TRY(cudaStreamSynchronize(stream));  // `prefix` is a stack temporary
-	p.ctx = s->d_ctx; p.rec = s->d_rec; p.work_prefix = s->d_prefix;
+	p.ctx = s->d_ctx; p.rec = s->d_rec; p.work_prefix = s->d_prefix; p.ctx_emit_area = s->d_ctx_area;
 	p.n_ctx = n_ctx; p.n_rec = n_rec;
 	p.tpr = ear_b200_tracks_per_recorder(rec, n_ctx * n_rec);
 	p.max_bounces = (opt && opt->max_bounces > 0) ? opt->max_bounces : 1000;
@@ -1392,7 +1408,15 @@ static int32_t render_on(std::vector<ear_b200_scene*>& scenes, bool peer, const 
 	float maximum = 0.0f;
 	std::vector<float> t60;
 	if (!opt || opt->finalise) {
-		if (int32_t rc = ear_b200_finalise_device(s0, ctx, n_ctx, rec, n_rec, n_bins, per[0].hist, per[0].range, s0->stream)) return rc;
+		// the direct lobe is a Record() call like any other (src/Scene.cpp:308): GPU 0's counters take it
+		RenderParams fp{};
+		if (int32_t rc = upload_params(s0, ctx, n_ctx, rec, n_rec, nullptr, s0->stream, fp)) return rc;
+		fp.n_bins = n_bins; fp.hist = per[0].hist; fp.range = per[0].range; fp.counters = per[0].counters;
+		if (int32_t rc = launch_finalise(s0, fp, s0->stream)) return rc;
+		unsigned long long after[8];
+		CUDA_TRY(cudaMemcpyAsync(after, per[0].counters, sizeof(after), cudaMemcpyDeviceToHost, s0->stream));
+		CUDA_TRY(cudaStreamSynchronize(s0->stream));
+		for (int k = 0; k < 8; ++k) counters[k] += after[k] - per[0].h_counters[k];
 		if (opt && opt->post_exponent > 0.0f)
 			if (int32_t rc = run_post(s0, rec, n_ctx, n_rec, n_bins, per[0].hist, per[0].range, opt, maximum, t60)) return rc;
 	}

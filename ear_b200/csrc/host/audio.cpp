@@ -112,7 +112,7 @@ struct Lr4 {
 	Lr4(float fc, bool highpass) {
 		const float srate = 44100.0f, pi = 3.14285714285714f;
 		const float wc = 2.0f * pi * srate, wc2 = wc * wc, wc3 = wc2 * wc, wc4 = wc2 * wc2;
-		const float k = wc / tan(pi * fc / srate), k2 = k * k, k3 = k2 * k, k4 = k2 * k2;
+		const float k = wc / std::tan(pi * fc / srate) /* the float overload, as the reference gets through <math.h> */, k2 = k * k, k3 = k2 * k, k4 = k2 * k2;
 		const float sqrt2 = sqrtf(2.0f), t1 = sqrt2 * wc3 * k, t2 = sqrt2 * wc * k3;
 		const float at = 4.0f * wc2 * k2 + 2.0f * t1 + k4 + 2.0f * t2 + wc4;
 		b[0] = 0.0f;

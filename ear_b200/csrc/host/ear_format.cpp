@@ -153,9 +153,25 @@ void read_mesh(Cursor c, SceneFile& sf, std::ostream* log) {
 void read_source(Cursor c, SceneFile& sf, int n_files, std::ostream* log) {
 	Source s;
 	for (int i = 0; i < n_files; ++i) s.wavs.push_back(c.read_string());
-	if (c.next_is("mesh"))
-		throw FormatError("Mesh emitters are not supported (the reference's own reader cannot load the exporter's 'mesh' block)");
-	s.location = read_placement(c, sf);
+	if (c.next_is("mesh")) {
+		// Mesh's constructor inside a source (src/SoundFile.cpp:50-53, src/Mesh.cpp:76-91): [str material][tri ...].  The
+		// material must exist (the reference dereferences it); the triangles emit, they are not part of the geometry.
+		Cursor m = c.open("mesh");
+		const std::string name = m.read_string();
+		bool known = false;
+		for (size_t i = 0; i < sf.materials.size(); ++i) if (sf.materials[i].name == name) known = true;
+		if (!known) throw FormatError("Mesh refers to undefined material '" + name + "'");
+		s.is_mesh = true;
+		s.emitter_first = (int)(sf.emitter_vertices.size() / 9);
+		while (m.next_is("tri ")) {
+			m.expect("tri ");
+			for (int v = 0; v < 3; ++v) {
+				const std::array<float, 3> p = m.read_vec();
+				for (int k = 0; k < 3; ++k) sf.emitter_vertices.push_back(p[k]);
+			}
+			++s.emitter_count;
+		}
+	} else s.location = read_placement(c, sf);
 	if (c.more() && c.next_is("flt4")) s.gain = c.read_float();
 	if (c.more() && c.next_is("flt4")) s.offset = (unsigned int)(c.read_float() * 44100.0f);
 	if (log) {

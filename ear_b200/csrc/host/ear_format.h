@@ -48,6 +48,10 @@ struct Source {
 	Placement location;
 	float gain = 1.0f;
 	unsigned offset = 0;             // start offset in samples
+	// mesh source (`mesh` sub-block instead of a location, src/SoundFile.cpp:50-53): its triangles are
+	// [emitter_first, emitter_first + emitter_count) of SceneFile::emitter_vertices
+	bool is_mesh = false;
+	int emitter_first = 0, emitter_count = 0;
 };
 
 struct Listener {
@@ -73,6 +77,7 @@ struct SceneFile {
 	std::vector<MeshBlock> meshes;
 	std::vector<float> vertices;         // [T][3][3] in file order == triangle index
 	std::vector<int32_t> tri_material;   // [T]
+	std::vector<float> emitter_vertices; // [E][3][3]: the triangles of all mesh sources, file order
 	std::vector<Source> sources;
 	std::vector<Listener> listeners;
 	std::vector<float> keys;

@@ -19,6 +19,7 @@
 #include <iomanip>
 #include <iostream>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <thread>
 
@@ -115,6 +116,23 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 		}
 	}
 
+	// equalizer output saved for debugging (src/EAR.cpp:123-148); the reference splits every source here, also for calc T60
+	if (has_debugdir) {
+		for (size_t sid = 0; sid < sf.sources.size(); ++sid) {
+			if (calc_t60 && sounds[sid].band[1].empty() && sf.sources[sid].wavs.size() == 1) {
+				std::vector<float> dry = load_wav_mono(sf.sources[sid].wavs[0]);
+				split_bands(dry, sf.freq[0] * 1000.0f, sf.freq[1] * 1000.0f, sf.freq[2] * 1000.0f, sounds[sid].band[0], sounds[sid].band[1], sounds[sid].band[2]);
+			}
+			for (int band = 0; band < 3; ++band) {
+				if (calc_t60 && band != 1) continue;
+				std::stringstream ss;
+				ss << debugdir << "sound-" << sid << ".band-" << band << lomihi[band] << ".wav";
+				save_wav_mono(ss.str(), sounds[sid].band[band].data(), sounds[sid].band[band].size(), false, -1.0f);
+			}
+			if (calc_t60) break;
+		}
+	}
+
 	std::cout << "Rendering..." << std::endl;
 	// contexts: sound x keyframe x band (src/EAR.cpp:170-191)
 	std::vector<Context> ctxs;
@@ -143,8 +161,14 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 		cc[c].absorption_factor = 1.0f - air[ctxs[c].band];
 		cc[c].dry_level = dry_level;
 		cc[c].gain = src.gain;
-		const std::array<float, 3>& sp = src.location.at(ctxs[c].keyframe);
-		for (int k = 0; k < 3; ++k) cc[c].source_position[k] = sp[k];
+		if (src.is_mesh) {   // AbstractSoundFile::mesh: rays start on its triangles (src/SoundFile.cpp:216-221)
+			cc[c].source_kind = EAR_B200_MESH_SOURCE;
+			cc[c].emitter_first = src.emitter_first;
+			cc[c].emitter_count = src.emitter_count;
+		} else {
+			const std::array<float, 3>& sp = src.location.at(ctxs[c].keyframe);
+			for (int k = 0; k < 3; ++k) cc[c].source_position[k] = sp[k];
+		}
 		for (int r = 0; r < n_rec; ++r) {
 			const Listener& l = sf.listeners[r];
 			ear_b200_recorder& rec = rr[(size_t)c * n_rec + r];
@@ -164,56 +188,43 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 			row[0] = sf.materials[m].refl[b]; row[1] = sf.materials[m].refr[b]; row[2] = sf.materials[m].kept[b]; row[3] = sf.materials[m].spec[b];
 		}
 
-	// one library call per GPU; contexts are independent, so they are dealt round-robin over devices
+	// One library call for the whole fan-out (src/EAR.cpp:196-207): the scene is built on GPU 0 and peer-copied to the
+	// other GPUs of the box; every GPU traces a contiguous share of the ray ids of EVERY context, the partial histograms
+	// meet on GPU 0 over NVLink (ear_b200_group_render).  `calc T60` (one context) uses all GPUs this way too.
 	int n_gpus = std::max(1, ear_b200_device_count());
 	if (const char* e = std::getenv("EAR_GPUS")) n_gpus = std::max(1, std::min(n_gpus, std::atoi(e)));
-	n_gpus = std::min(n_gpus, n_ctx);
+	n_gpus = std::min(n_gpus, 16);
 	ear_b200_options opt;
 	std::memset(&opt, 0, sizeof(opt));
 	opt.max_bounces = std::getenv("EAR_MAX_BOUNCES") ? std::atoi(std::getenv("EAR_MAX_BOUNCES")) : 1000;
 	opt.seed = std::getenv("EAR_SEED") ? std::strtoull(std::getenv("EAR_SEED"), 0, 10) : (uint64_t)std::time(0);
 	opt.first_ray = 0; opt.ray_count = -1; opt.finalise = 1;
-	std::vector<std::string> errors((size_t)n_gpus);
-	std::vector<std::thread> workers;
 	uint64_t segments = 0; double device_ms = 0.0;
-	std::vector<uint64_t> seg_per_gpu((size_t)n_gpus, 0);
-	std::vector<double> ms_per_gpu((size_t)n_gpus, 0.0);
-	// one BVH build: the scene is built on GPU 0 and its device image copied to the other GPUs
-	std::vector<ear_b200_scene*> scenes((size_t)n_gpus, nullptr);
-	if (ear_b200_scene_create(sf.vertices.data(), sf.tri_material.data(), sf.triangle_count(), table.data(),
-	                          (int32_t)std::max<size_t>(sf.materials.size(), 1), 3, 0, &scenes[0]))
-		throw std::runtime_error(ear_b200_last_error());
-	for (int g = 0; g < n_gpus; ++g) {
-		workers.emplace_back([&, g]() {
-			std::vector<int> mine;
-			for (int c = g; c < n_ctx; c += n_gpus) mine.push_back(c);
-			std::vector<ear_b200_context> lc; std::vector<ear_b200_recorder> lr;
-			for (int c : mine) { lc.push_back(cc[c]); for (int r = 0; r < n_rec; ++r) lr.push_back(rr[(size_t)c * n_rec + r]); }
-			if (g > 0 && ear_b200_scene_clone(scenes[0], g, &scenes[g])) { errors[g] = ear_b200_last_error(); return; }
-			ear_b200_scene* scene = scenes[g];
-			ear_b200_result* res = nullptr;
-			ear_b200_options o = opt;   // same seed everywhere: the contexts carry their global stream ids
-			if (ear_b200_render(scene, lc.data(), (int32_t)lc.size(), lr.data(), n_rec, &o, &res)) { errors[g] = ear_b200_last_error(); return; }
-			for (size_t i = 0; i < mine.size(); ++i) {
-				Context& c = ctxs[mine[i]];
-				for (int r = 0; r < n_rec; ++r)
-					for (int k = 0; k < 2; ++k) {
-						const ear_b200_track& t = res->tracks[(i * n_rec + r) * 2 + k];
-						std::unique_ptr<Track> tr;
-						if (t.data) { tr.reset(new Track()); tr->assign(t.data, t.length, t.first_sample, t.real_length); }
-						c.tracks.push_back(std::move(tr));
-					}
-			}
-			seg_per_gpu[g] = res->segments; ms_per_gpu[g] = res->device_ms;
-			if (res->dropped_updates) errors[g] = "histogram too short: bin updates were dropped";
-			ear_b200_result_free(res);
-		});
-	}
-	for (auto& w : workers) w.join();
-	for (ear_b200_scene* sc : scenes) ear_b200_scene_destroy(sc);
-	for (int g = 0; g < n_gpus; ++g) {
-		if (!errors[g].empty()) throw std::runtime_error(errors[g]);
-		segments += seg_per_gpu[g]; device_ms = std::max(device_ms, ms_per_gpu[g]);
+	{
+		struct Handles {   // released on every path, exceptions included
+			ear_b200_scene* scene = nullptr; ear_b200_group* group = nullptr; ear_b200_result* res = nullptr;
+			~Handles() { ear_b200_result_free(res); ear_b200_group_destroy(group); ear_b200_scene_destroy(scene); }
+		} h;
+		if (ear_b200_scene_create(sf.vertices.data(), sf.tri_material.data(), sf.triangle_count(), table.data(),
+		                          (int32_t)std::max<size_t>(sf.materials.size(), 1), 3, 0, &h.scene))
+			throw std::runtime_error(ear_b200_last_error());
+		if (!sf.emitter_vertices.empty() &&
+		    ear_b200_scene_set_emitters(h.scene, sf.emitter_vertices.data(), (int32_t)(sf.emitter_vertices.size() / 9)))
+			throw std::runtime_error(ear_b200_last_error());
+		std::vector<int32_t> devices((size_t)n_gpus);
+		for (int g = 0; g < n_gpus; ++g) devices[(size_t)g] = g;
+		if (ear_b200_group_create(h.scene, devices.data(), n_gpus, &h.group)) throw std::runtime_error(ear_b200_last_error());
+		if (ear_b200_group_render(h.group, cc.data(), n_ctx, rr.data(), n_rec, &opt, &h.res)) throw std::runtime_error(ear_b200_last_error());
+		if (h.res->dropped_updates) throw std::runtime_error("histogram too short: bin updates were dropped");
+		for (int c = 0; c < n_ctx; ++c)
+			for (int r = 0; r < n_rec; ++r)
+				for (int k = 0; k < 2; ++k) {
+					const ear_b200_track& t = h.res->tracks[((size_t)c * n_rec + r) * 2 + k];
+					std::unique_ptr<Track> tr;
+					if (t.data) { tr.reset(new Track()); tr->assign(t.data, t.length, t.first_sample, t.real_length); }
+					ctxs[(size_t)c].tracks.push_back(std::move(tr));
+				}
+		segments = h.res->segments; device_ms = h.res->device_ms;
 	}
 	std::cout << "[" << std::string(49, '=') << "]" << std::endl;
 	std::cout << "Traced " << segments << " ray-bounce segments on " << n_gpus << " GPU(s) in " << device_ms << " ms" << std::endl;
@@ -261,11 +272,13 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 		const unsigned hw = (unsigned)std::max(1, 2 * n_gpus);   // two host threads per GPU keep its copy engines busy
 		std::atomic<int> next(0);
 		std::string conv_error;
+		std::mutex conv_error_lock;
+		std::atomic<bool> conv_failed(false);
 		for (Context& c : ctxs) c.processed.resize((size_t)n_rec * 2);
 		auto work = [&]() {
 			for (;;) {
 				const int job = next.fetch_add(1);
-				if (job >= n_ctx * n_rec) break;
+				if (job >= n_ctx * n_rec || conv_failed.load()) break;
 				const int ci = job / n_rec, r = job % n_rec;
 				Context& c = ctxs[ci];
 				const Source& src = sf.sources[c.sound];
@@ -275,7 +288,10 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 					const unsigned start = (unsigned)(int)(start_s * 44100.0f);
 					const unsigned want = length_s < 0 ? total - start : (unsigned)(int)(length_s * 44100.0f);
 					if (start >= total) { ptr = nullptr; n = 0; offset = 0; return; }
-					ptr = dry.data() + start; n = std::min(want, total - start); offset = src.offset + start;
+					ptr = dry.data() + start; n = std::min(want, total - start);
+					// The per-band SoundFiles that Band() hands to the convolution are constructed with offset 0
+					// (src/SoundFile.cpp:83,150-152): the source's own `offset` setting never reaches Section() -- kept.
+					offset = start;
 				};
 				for (int k = 0; k < 2; ++k) {
 					const Track* tr = c.tracks[r * 2 + k].get();
@@ -293,12 +309,25 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 					} else section(0.0f, -1.0f, ptr, n, off);
 					// RecorderTrack::Process on the GPU (include/ear_b200.h: ear_b200_convolve)
 					const unsigned len = next ? std::max(tr->real_length, next->real_length) : tr->real_length;
-					std::vector<float> out((size_t)std::max<unsigned>(3 * kSampleRate, n + off + len), 0.0f);
+					const unsigned first = next ? std::min(tr->first_sample, next->first_sample) : tr->first_sample;
+					// The reference's result track is a FloatBuffer written through operator[] in increasing index order
+					// (src/Recorder.cpp:247-292): it starts at 3 s and grows to "index + 1 s" whenever an index falls outside
+					// (src/Recorder.cpp:52-59).  Its allocated length matters later: RecorderTrack::Add walks the WHOLE
+					// allocation (getLength(0.0f), src/Recorder.cpp:293-300), which sets the length of the saved file.
+					size_t alloc = 3 * kSampleRate;
+					if (n > 0 && len > first) {
+						const size_t i0 = (size_t)off + first, last = (size_t)(n - 1) + off + (len - 1);
+						if (i0 >= alloc) alloc = i0 + kSampleRate;
+						while (last >= alloc) alloc += kSampleRate;
+					}
+					std::vector<float> out(alloc, 0.0f);
 					uint32_t of = 0, orl = 0;
 					if (ear_b200_convolve(job % n_gpus, tr->data(), tr->allocated(), tr->first_sample, tr->real_length,
 					                      next ? next->data() : nullptr, next ? next->allocated() : 0, next ? next->first_sample : 0,
 					                      next ? next->real_length : 0, n ? ptr : nullptr, n, off, out.data(), (uint32_t)out.size(), &of, &orl)) {
-						conv_error = ear_b200_last_error();
+						std::lock_guard<std::mutex> lock(conv_error_lock);
+						if (conv_error.empty()) conv_error = ear_b200_last_error();
+						conv_failed.store(true);
 						return;
 					}
 					c.processed[r * 2 + k].reset(new Track());
@@ -324,17 +353,21 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 				if (c.keyframe != -1) ss << ".frame-" << std::setw(2) << std::setfill('0') << c.keyframe;
 				ss << ".band-" << c.band << ".wav";
 				const Track& p0 = *c.processed[r * 2];
-				if (l.stereo) save_wav_stereo(ss.str(), p0.data(), p0.length(), c.processed[r * 2 + 1]->data(), c.processed[r * 2 + 1]->length(), false);
-				else save_wav_mono(ss.str(), p0.data(), p0.length(), false, -1.0f);
+				// other->Save(fn) through a Recorder*: the defaults of the BASE declaration apply, norm = true, norm_max = -1
+				// (src/Recorder.h:181) -- the peak of the track lands at 0.8 (lib/wave/WaveFile.cpp:194-201)
+				if (l.stereo) save_wav_stereo(ss.str(), p0.data(), p0.length(), c.processed[r * 2 + 1]->data(), c.processed[r * 2 + 1]->length(), true);
+				else save_wav_mono(ss.str(), p0.data(), p0.length(), true, -1.0f);
 			}
 			for (int k = 0; k < n_tracks; ++k) total[k].add(*c.processed[r * 2 + k]);
 		}
 		float mx = -1e9f;
 		for (int k = 0; k < n_tracks; ++k) mx = std::max(mx, total[k].maximum());
 		for (int k = 0; k < n_tracks; ++k) total[k].normalize(0.8f, mx);
+		// total->Truncate(total->getLength(1e-6f)) (src/EAR.cpp:382): getLength of a processed recorder is the longest
+		// real_length (src/Recorder.cpp:412-418) and Truncate acts on the recorder's RESPONSE tracks (:399-404), which
+		// are blank here -- the summed tracks are saved with their own real_length
 		unsigned len = 0;
-		for (int k = 0; k < n_tracks; ++k) len = std::max(len, total[k].length());   // processed tracks: plain real_length
-		for (int k = 0; k < n_tracks; ++k) total[k].truncate(len);
+		for (int k = 0; k < n_tracks; ++k) len = std::max(len, total[k].length());
 		if (l.stereo) save_wav_stereo(l.filename, total[0].data(), total[0].length(), total[1].data(), total[1].length(), false);
 		else save_wav_mono(l.filename, total[0].data(), total[0].length(), false, -1.0f);
 		std::cout << "Saved " << l.filename << " (" << len << " samples)" << std::endl;

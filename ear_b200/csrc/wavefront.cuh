@@ -285,6 +285,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	// what this lane needs from the shared sampling loop below
 	enum { kNone = 0, kBounce = 1, kEmit = 2 };
 	int mode = kNone;
+	bool mesh_emit = false;   // this slot starts a ray of a mesh source: hemisphere about the emitter's normal, bounce 0 is recorded
 	V3 n = mk(0, 0, 0), pnt = mk(0, 0, 0), blend = mk(0, 0, 0), prev_dir = mk(0, 0, 0), o = mk(0, 0, 0);
 	float intensity = 0.0f, path = 0.0f, spec = 0.0f, kept = 0.0f, t = 0.0f;
 	bool refract = false;
@@ -313,6 +314,32 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			m.x = (uint32_t)ray; m.y = (uint32_t)(ray >> 32);
 			++lc.rays;
 			mode = kEmit;
+			if (p.ctx[c].source_kind == EAR_B200_MESH_SOURCE) {
+				// AbstractSoundFile::SoundRay of a mesh source (src/SoundFile.cpp:216-221): Mesh::SamplePoint picks a triangle
+				// by area (src/Mesh.cpp:143-154: x = rangeRandom(0, total_area) = r * total_area + 0; x -= area until x < 0),
+				// Triangle::SamplePoint (src/Triangle.cpp:44-53) a point in it; the direction is Sample_Hemi about the
+				// triangle's own normal (the shared loop below).  If x never drops below 0 the reference keeps its
+				// default-constructed zeros for point and normal.
+				mesh_emit = true;
+				const float total = p.ctx_emit_area[c];
+				float x = fadd(fmul(rng.unit1(), total), 0.0f);
+				const float4* et = sc.emitters + 4 * (size_t)p.ctx[c].emitter_first;
+				const int n_e = p.ctx[c].emitter_count;
+				for (int i = 0; i < n_e; ++i) {
+					const float4 e0 = __ldg(et + 4 * i);
+					x = fsub(x, e0.w);
+					if (x < 0.0f) {
+						const float4 e1 = __ldg(et + 4 * i + 1), e2 = __ldg(et + 4 * i + 2), e3 = __ldg(et + 4 * i + 3);
+						float r1, r2, unused;
+						rng.unit3(r1, r2, unused);
+						const float sr1 = fsqrt(r1);
+						pnt = vadd(vadd(vscale(mk(e0.x, e0.y, e0.z), fsub(1.0f, sr1)), vscale(mk(e1.x, e1.y, e1.z), fmul(sr1, fsub(1.0f, r2)))),
+						           vscale(mk(e2.x, e2.y, e2.z), fmul(sr1, r2)));
+						n = mk(e3.x, e3.y, e3.z);
+						break;
+					}
+				}
+			}
 		}
 	}
 	const long long out_row = (long long)(ray - (unsigned long long)p.first_ray);   // parity harness: output row
@@ -368,8 +395,9 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			l = vdot(cand, cand);
 			const bool in_sphere = !(l < 0.001f || l > 1.0f);
 			const float dc = fmaf(n.x, cand.x, fmaf(n.y, cand.y, n.z * cand.z));
-			bool accept = in_sphere && (mode != kBounce || dc > 1e-5f);
-			if (in_sphere && mode == kBounce && fabsf(dc) <= 1e-5f) {   // too close to call on the unnormalised candidate
+			const bool hemi = mode == kBounce || mesh_emit;   // Sample_Hemi; point sources emit over the sphere
+			bool accept = in_sphere && (!hemi || dc > 1e-5f);
+			if (in_sphere && hemi && fabsf(dc) <= 1e-5f) {   // too close to call on the unnormalised candidate
 				const float s = fsqrt(l);
 				accept = !(vdot(n, mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s))) < 0.0f);
 			}
@@ -393,7 +421,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			if (!(l < 0.001f || l > 1.0f)) {
 				const float s = fsqrt(l);
 				v = mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s));
-				pending = (mode == kBounce) && (vdot(n, v) < 0.0f);
+				pending = (mode == kBounce || mesh_emit) && (vdot(n, v) < 0.0f);
 			}
 		}
 	}
@@ -426,10 +454,19 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		// AbstractSoundFile::SoundRay, point source (src/SoundFile.cpp:223-226).  Bounce 0 of the reference loop
 		// records nothing for point sources (src/Scene.cpp:185) and leaves intensity 1, path 0.
 		const float* sp = p.ctx[c].source_position;
-		ro = make_float4(sp[0], sp[1], sp[2], 1.0f);
+		ro = mesh_emit ? make_float4(pnt.x, pnt.y, pnt.z, 1.0f) : make_float4(sp[0], sp[1], sp[2], 1.0f);
 		rd = make_float4(v.x, v.y, v.z, 0.0f);
 		bounce = 0;
 		alive = 1 < p.max_bounces;
+		if (mesh_emit && p.n_rec > 0) {
+			// "In case the sound source emits from a mesh, the direct sound is sampled regardless" (src/Scene.cpp:185):
+			// bounce 0 connects the emission point to every recorder with dot := 1 and no surface term (:205-216);
+			// specularity 2 marks the record for the splat kernel
+			shaded = true;
+			st_stream(pool.sh0 + slot, ro);
+			st_stream(pool.sh1 + slot, make_float4(n.x, n.y, n.z, 0.0f));
+			st_stream(pool.sh2 + slot, make_float4(0.0f, 0.0f, 0.0f, 2.0f));
+		}
 	}
 	m.w = rng.block;
 	if (!alive && (had_ray || mode == kEmit) && p.final_state) {   // parity harness: state the ray ended with
@@ -445,7 +482,7 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			++lc.occlusion;
 			const float* x = p.rec[(size_t)c * p.n_rec + r].position;
 			const V3 lsdir = vnormalized(vsub(mk(x[0], x[1], x[2]), pnt));
-			facing = vdot(lsdir, n) > 0.0f;
+			facing = mesh_emit || vdot(lsdir, n) > 0.0f;
 		}
 		const unsigned mq = __ballot_sync(0xffffffffu, facing);
 		if (mq) {

@@ -87,6 +87,10 @@ class SourceDef:
     animation: Optional[np.ndarray] = None  # [K,3]
     gain: float = 1.0
     offset: float = 0.0
+    # mesh source (src/SoundFile.cpp:50-53): instead of a location the block carries a `mesh` sub-block,
+    # [str material name][tri ...] -- the name must be a defined material (Mesh's constructor looks it up)
+    mesh_material: Optional[str] = None
+    mesh_verts: Optional[np.ndarray] = None  # [E,3,3] float32
 
 
 @dataclass
@@ -173,7 +177,11 @@ class SceneDef:
 
         for src in self.sources:
             p = b"".join(pack_str(w) for w in src.wavs)
-            p += loc(src.position, src.animation) + pack_float(src.gain) + pack_float(src.offset)
+            if src.mesh_verts is not None:
+                p += block("mesh", pack_str(src.mesh_material) + pack_tris(np.asarray(src.mesh_verts, np.float32)))
+            else:
+                p += loc(src.position, src.animation)
+            p += pack_float(src.gain) + pack_float(src.offset)
             out.append(block("SSRC" if len(src.wavs) == 1 else "3SRC", p))
         for rec in self.recorders:
             p = pack_str(rec.filename) + pack_float(35.0) + loc(rec.position, rec.animation)
@@ -305,10 +313,16 @@ def read_ear(path: str) -> SceneDef:
             scene.meshes.append(MeshDef(mat, sub.tris()))
         elif bid in (b"SSRC", b"3SRC"):
             wavs = [sub.string() for _ in range(1 if bid == b"SSRC" else 3)]
-            pos, anim = sub.location()
+            pos = anim = mesh_mat = mesh_verts = None
+            if sub.peek() == b"mesh":
+                _, inner = sub.container()
+                mesh_mat = inner.string()
+                mesh_verts = inner.tris()
+            else:
+                pos, anim = sub.location()
             gain = sub.f32() if sub.more() and sub.peek() == b"flt4" else 1.0
             off = sub.f32() if sub.more() and sub.peek() == b"flt4" else 0.0
-            scene.sources.append(SourceDef(wavs, pos, anim, gain, off))
+            scene.sources.append(SourceDef(wavs, pos, anim, gain, off, mesh_mat, mesh_verts))
         elif bid in (b"OUT1", b"OUT2"):
             fn = sub.string()
             sub.f32()

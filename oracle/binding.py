@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
         l.oracle_scene_create.restype = vp
         l.oracle_scene_create.argtypes = [vp, vp, i32, vp, i32, i32]
         l.oracle_scene_destroy.argtypes = [vp]
+        l.oracle_scene_set_emitters.argtypes = [vp, vp, i32]
         l.oracle_first_hit.argtypes = [vp, vp, vp, i64, vp, vp]
         l.oracle_occluded.argtypes = [vp, vp, vp, i64, vp]
         l.oracle_render.restype = vp
@@ -68,8 +69,17 @@ class OracleScene:
 
     @classmethod
     def from_def(cls, scene_def, materials=None):
+        from ear_b200.api import emitter_table
         tab = scene_def.material_table() if materials is None else materials
-        return cls(scene_def.triangles(), scene_def.triangle_materials(), tab)
+        scene = cls(scene_def.triangles(), scene_def.triangle_materials(), tab)
+        em = emitter_table(scene_def)
+        if em is not None:
+            scene.set_emitters(em)
+        return scene
+
+    def set_emitters(self, verts):
+        self.emitters = np.ascontiguousarray(verts, np.float32).reshape(-1, 3, 3)
+        lib().oracle_scene_set_emitters(self.h, self.emitters.ctypes.data, self.emitters.shape[0])
 
     def __del__(self):
         if getattr(self, "h", None):
