@@ -25,7 +25,10 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <string>
 #include <vector>
 
 #include "bvh_build.h"
@@ -741,6 +744,15 @@ static void exclusive_scan(const int* in, int n, int* out, int* sums, cudaStream
 // d_verts [n][3][3], d_mat [n] on the current device.  On success `out` owns two device allocations.
 static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_t st, Result& out, std::string& err) {
 	Scratch sc;
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!dbg) return;
+		cudaStreamSynchronize(st);
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[ear_b200] device bvh: %-22s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
 	const char* knob = std::getenv("EAR_B200_BVH_MARGIN_SCALE");
 	const float margin_scale = knob ? (float)std::atof(knob) : 1.0f;
 	int max_leaf = kMaxLeaf; float sah_ct = 1.0f;
@@ -772,7 +784,9 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 	DBVH_TRY(sc.get(&lv.cmin, 3 * (size_t)cap)); DBVH_TRY(sc.get(&lv.scale, 3 * (size_t)cap)); DBVH_TRY(sc.get(&lv.child_seg, 2 * (size_t)cap));
 	DBVH_TRY(sc.get(&small_roots, (size_t)np / 1 + 2));   // every small root holds >= 1 primitive
 	const int grid_n = (np + 255) / 256;
+	lap("scratch allocation");
 	if (n > 0) prims_kernel<<<grid_n, 256, 0, st>>>(d_verts, n, g, margin_scale, plo[0], phi[0]);
+	lap("bounds + primitives");
 	// root
 	BNode root{};
 	root.left = root.right = -1; root.first = 0; root.count = n;
@@ -815,6 +829,7 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 		std::swap(lv.node, next_node);
 		cur ^= 1;
 	}
+	lap("top phase");
 	// ---- bottom phase ----
 	DBVH_TRY(cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, st));
 	DBVH_TRY(cudaStreamSynchronize(st));
@@ -823,10 +838,12 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 		bottom_kernel<<<hg.small_count, 32 * kBotWarps, 0, st>>>(plo[cur], phi[cur], plo[cur ^ 1], phi[cur ^ 1], nodes, g, small_roots, max_leaf, sah_ct);
 		DBVH_TRY(cudaGetLastError());
 	}
+	lap("bottom phase");
 	const float4* final_lo = plo[cur ^ 1];
 	// ---- records ----
 	DBVH_TRY(cudaMalloc(&out.d_tris, (size_t)np * sizeof(TriRecord)));
 	if (n > 0) records_kernel<<<grid_n, 256, 0, st>>>(d_verts, d_mat, final_lo, n, out.d_tris);
+	lap("triangle records");
 	// ---- collapse ----
 	DBVH_TRY(cudaMemcpyAsync(&hg, g, sizeof(hg), cudaMemcpyDeviceToHost, st));
 	DBVH_TRY(cudaStreamSynchronize(st));
@@ -869,6 +886,8 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 		out.n_nodes = base; out.depth = depth;
 	}
 	DBVH_TRY(cudaStreamSynchronize(st));
+	lap("collapse");
+	if (dbg) std::fprintf(stderr, "[ear_b200] device bvh: %d triangles, %d scratch nodes, %d wide nodes, depth %d, %d bottom subtrees\n", n, hg.node_count, out.n_nodes, out.depth, hg.small_count);
 	for (int a = 0; a < 3; ++a) {
 		int lo = hg.lo[a], hi = hg.hi[a];
 		lo = lo >= 0 ? lo : lo ^ 0x7fffffff; hi = hi >= 0 ? hi : hi ^ 0x7fffffff;

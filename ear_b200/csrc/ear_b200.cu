@@ -456,6 +456,9 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 	}
 	s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
 	if (int32_t rc = scene_finish(s.get(), h)) return rc;
+	if (std::getenv("EAR_B200_DEBUG"))
+		std::fprintf(stderr, "[ear_b200] scene_create: %d triangles, %s build %.2f ms, total %.2f ms\n", n_tris, on_device ? "device" : "host",
+		             s->bvh_build_ms, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
 	*out = s.release();
 	return 0;
 }

@@ -172,3 +172,61 @@ def test_default_culling_equals_exact_on_1e8_adversarial_rays(hall, monkeypatch)
         seed += 1
     assert mismatches == 0, f"{mismatches} of {done} rays differ between default and EXACT culling"
     assert hits > 0.5 * done
+
+
+# ---------------------------------------------------------------------------------------------------------
+# mesh-emitter sources (src/SoundFile.cpp:215-228, src/Mesh.cpp:143-154, src/Triangle.cpp:44-53)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("stereo", [False, True])
+def test_mesh_source_paths_and_histograms_match_oracle(ob, stereo):
+    from tests.test_oracle_pinning import _mesh_source_scene
+    sc = _mesh_source_scene("/tmp/click.wav", samples=60000, stereo=stereo)
+    gpu = api.Scene.from_def(sc)
+    cpu = ob.OracleScene.from_def(sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    assert ctxs[0].emitter == (0, 3)
+    # bounce paths: emission point / direction and every later hit identical (same Philox streams)
+    hg, sg = gpu.trace_paths(ctxs[1], 1, 4000, 40, seed=17)
+    hc, sc_ = cpu.trace_paths(ctxs[1], 1, 4000, 40, seed=17)
+    assert np.array_equal(hg, hc)
+    assert np.array_equal(sg.view(np.uint32), sc_.view(np.uint32))
+    res = gpu.render(ctxs, recs, max_bounces=120, seed=17)
+    tracks, cnt = cpu.render(ctxs, recs, max_bounces=120, seed=17)
+    assert (res.rays, res.segments, res.occlusion_queries, res.contributions, res.bin_updates) == \
+           (cnt["rays"], cnt["segments"], cnt["occlusion_queries"], cnt["contributions"], cnt["bin_updates"])
+    # bounce 0 is recorded for mesh sources: more Connect() calls than segments that hit something
+    assert res.occlusion_queries > res.segments - res.rays
+    for c in range(3):
+        for k in range(2 if stereo else 1):
+            a, b = res.tracks[c][0][k], tracks[c][0][k]
+            assert (a.first_sample, a.real_length) == (b.first_sample, b.real_length)
+            n = b.real_length + 1
+            assert np.abs(a.data[:n] - b.data[:n]).max() <= REL_TOL * np.abs(b.data[:n]).max()
+
+
+def test_group_render_on_one_gpu_equals_render(ob):
+    """ear_b200_group_render with a single device is ear_b200_render (the CLI always goes through the group)."""
+    sc = common.named_scene("example1")
+    gpu = api.Scene.from_def(sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    for c in ctxs:
+        c.num_samples = 4000
+    a = gpu.render(ctxs, recs, max_bounces=100, seed=5)
+    grp = api.Group(gpu, [0])
+    b = grp.render(ctxs, recs, max_bounces=100, seed=5)
+    assert (a.rays, a.segments, a.contributions, a.bin_updates) == (b.rays, b.segments, b.contributions, b.bin_updates)
+    for c in range(len(ctxs)):
+        ta, tb = a.tracks[c][0][0], b.tracks[c][0][0]
+        assert (ta.first_sample, ta.real_length) == (tb.first_sample, tb.real_length)
+        assert np.abs(ta.data - tb.data).max() <= 1e-5 * np.abs(ta.data).max()
+    # the device post chain inside render: Power / Truncate / T60 as the oracle's post chain gives them
+    post = grp.render(ctxs, recs, max_bounces=100, seed=5, post=(0.335, 256.0))
+    tracks, _ = ob.OracleScene.from_def(sc).render(ctxs, recs, max_bounces=100, seed=5)
+    want_max, want = ob.post_all(tracks)
+    assert post.maximum == pytest.approx(want_max, rel=2e-6)
+    for c in range(len(ctxs)):
+        data, first, real, w_t60 = want[c][0][0]
+        t = post.tracks[c][0][0]
+        assert (t.first_sample, t.real_length) == (first, real)
+        assert abs(post.t60[c][0][0] - w_t60) <= 1.5 / 44100.0
+    grp.close()

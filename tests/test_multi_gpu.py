@@ -61,7 +61,7 @@ def test_replicated_scene_and_sharded_render_match_one_gpu(tmp_path):
 
 
 def test_cli_output_does_not_depend_on_gpu_count(tmp_path):
-    """18 contexts dealt to 1 GPU and to 2 GPUs: the contexts carry their global stream ids, so both runs trace the
+    """18 contexts, rays sharded over 1 GPU and over 2 GPUs: the contexts carry their global stream ids, so both runs trace the
     same paths and the written wav agrees to the last bit or two of the 16-bit samples (float atomics reorder sums)."""
     import subprocess
     import wave
@@ -93,3 +93,59 @@ def test_cli_output_does_not_depend_on_gpu_count(tmp_path):
         outs.append(_read(sc.recorders[0].filename)[0])
     assert outs[0].shape == outs[1].shape
     assert np.abs(outs[0].astype(np.int32) - outs[1]).max() <= 2
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_group_render_shards_rays_and_reduces_over_peer_memory():
+    """ear_b200_group_render (one process, several GPUs; src/EAR.cpp:196-207 is the seam): every GPU traces a share of
+    the ray ids of every context, the partial histograms meet on GPU 0 in one sliced peer reduce.  Same paths as the
+    one-GPU render (Philox keyed by context and ray id): counters and track ranges identical, bins up to float sum order.
+    Covers mono + stereo, three contexts, and a ray count that does not divide by the GPU count."""
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    from ear_b200 import api, scenes
+    sc = scenes.example1_scene(samples=30010, stereo=True)
+    ctxs, recs = api.contexts_from_def(sc)
+    gpu = api.Scene.from_def(sc)
+    one = gpu.render(ctxs, recs, max_bounces=60, seed=23)
+    for g in sorted({2, min(n, 3), n}):
+        grp = api.Group(gpu, list(range(g)))
+        res = grp.render(ctxs, recs, max_bounces=60, seed=23)
+        assert (res.rays, res.segments, res.occlusion_queries, res.contributions, res.bin_updates) == \
+               (one.rays, one.segments, one.occlusion_queries, one.contributions, one.bin_updates), g
+        for c in range(len(ctxs)):
+            for k in range(2):
+                a, b = res.tracks[c][0][k], one.tracks[c][0][k]
+                assert (a.first_sample, a.real_length) == (b.first_sample, b.real_length)
+                assert np.abs(a.data - b.data).max() <= 1e-4 * np.abs(b.data).max()
+        grp.close()
+
+
+def test_cli_calc_t60_uses_every_gpu_for_one_context(tmp_path):
+    """`EAR calc T60` has ONE context: with whole contexts dealt to GPUs it could only ever use one GPU.  Ray sharding
+    gives the same T60 on 1 and on all GPUs (same paths; the T60 estimator thresholds the summed track, so allow a
+    few samples of difference from the float sum order)."""
+    import re
+    import subprocess
+    n = _gpu_count()
+    if n < 2:
+        pytest.skip("needs 2 GPUs")
+    from ear_b200 import scenes
+    from tests.test_cli_animated_gpu import EAR
+    wav = scenes.write_click_wav(str(tmp_path / "click.wav"))
+    sc = scenes.rt60_scene(samples=200000, wav=wav)
+    path = str(tmp_path / "rt60.ear")
+    sc.write(path)
+    t60 = []
+    for gpus in ("1", str(n)):
+        r = subprocess.run([EAR, "calc", "T60", path], capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, EAR_SEED="77", EAR_GPUS=gpus))
+        assert r.returncode == 0, r.stdout[-500:]
+        assert f"on {gpus} GPU(s)" in r.stdout
+        t60.append(float(re.search(r"T60_ear\s*: ([0-9.]+)s", r.stdout).group(1)))
+    assert abs(t60[0] - t60[1]) <= 5.0 / 44100.0, t60
