@@ -74,7 +74,7 @@ EXPORTS = [
     "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
     "ear_b200_post_power_device", "ear_b200_post_truncate_device", "ear_b200_tracks_per_recorder",
     "ear_b200_scene_set_emitters", "ear_b200_group_create", "ear_b200_group_destroy", "ear_b200_group_size",
-    "ear_b200_group_render",
+    "ear_b200_group_render", "ear_b200_release_cached_memory",
 ]
 
 _lib = None

@@ -34,6 +34,10 @@
 #include "bvh_build.h"
 #include "device_exact.cuh"
 
+// device allocations go through the library's cache (ear_b200.cu)
+template <class T> static cudaError_t dev_alloc(T** out, size_t bytes);
+static void dev_free(void* p);
+
 namespace earb {
 namespace dbvh {
 
@@ -723,10 +727,10 @@ struct Result {
 
 struct Scratch {   // freed on every return path
 	std::vector<void*> ptrs;
-	~Scratch() { for (void* p : ptrs) cudaFree(p); }
+	~Scratch() { for (void* p : ptrs) dev_free(p); }
 	template <class T> cudaError_t get(T** out, size_t count) {
 		void* p = nullptr;
-		const cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+		const cudaError_t e = dev_alloc(&p, std::max<size_t>(count, 1) * sizeof(T));
 		if (e == cudaSuccess) { ptrs.push_back(p); *out = (T*)p; }
 		return e;
 	}
@@ -841,7 +845,7 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 	lap("bottom phase");
 	const float4* final_lo = plo[cur ^ 1];
 	// ---- records ----
-	DBVH_TRY(cudaMalloc(&out.d_tris, (size_t)np * sizeof(TriRecord)));
+	DBVH_TRY(dev_alloc(&out.d_tris, (size_t)np * sizeof(TriRecord)));
 	if (n > 0) records_kernel<<<grid_n, 256, 0, st>>>(d_verts, d_mat, final_lo, n, out.d_tris);
 	lap("triangle records");
 	// ---- collapse ----
@@ -852,7 +856,7 @@ static bool build(const float* d_verts, const int32_t* d_mat, int n, cudaStream_
 	DBVH_TRY(cudaMemcpyAsync(&hroot, nodes, sizeof(hroot), cudaMemcpyDeviceToHost, st));
 	DBVH_TRY(cudaStreamSynchronize(st));
 	const size_t wide_cap = (size_t)hg.node_count / 2 + 2;     // inner binary nodes bound the wide nodes
-	DBVH_TRY(cudaMalloc(&out.d_nodes, wide_cap * sizeof(Node)));
+	DBVH_TRY(dev_alloc(&out.d_nodes, wide_cap * sizeof(Node)));
 	if (hroot.left < 0) {
 		single_leaf_kernel<<<1, 1, 0, st>>>(nodes, n, out.d_nodes);
 		out.n_nodes = 1; out.depth = 1;

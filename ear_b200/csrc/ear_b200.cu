@@ -16,8 +16,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <unordered_map>
 #include <thread>
 #include <vector>
 
@@ -33,6 +36,67 @@ using namespace earb;
 static thread_local std::string g_last_error;
 static int32_t fail(const std::string& msg) { g_last_error = msg; return 1; }
 
+// Device allocations go through a small per-process cache: cudaMalloc / cudaFree of the multi-GB ray pool, the BVH
+// scratch and the visibility maps cost tens of milliseconds per scene (more on a busy host), which is most of what a
+// short render spends outside its kernels.  A released block is kept (per device, by size) and handed to the next
+// request of about that size; the cache is trimmed when it holds more than EAR_B200_CACHE_MB (default 32768) and when
+// an allocation fails.  Contents are never assumed: every user initialises what it reads.
+namespace devcache {
+struct Block { void* p; size_t bytes; int device; };
+static std::mutex g_lock;
+static std::unordered_map<void*, Block> g_live;
+static std::multimap<std::pair<int, size_t>, void*> g_free;   // (device, bytes) -> block
+static size_t g_cached = 0;
+static size_t limit() {
+	static size_t v = 0;
+	if (!v) { const char* e = std::getenv("EAR_B200_CACHE_MB"); v = (size_t)(e ? std::max(0, std::atoi(e)) : 32768) << 20; if (!v) v = 1; }
+	return v;
+}
+static void trim_locked(size_t keep) {
+	while (g_cached > keep && !g_free.empty()) {
+		auto it = std::prev(g_free.end());
+		int cur = 0;
+		cudaGetDevice(&cur);
+		cudaSetDevice(it->first.first);
+		cudaFree(it->second);
+		cudaSetDevice(cur);
+		g_cached -= it->first.second;
+		g_free.erase(it);
+	}
+}
+static cudaError_t alloc(void** out, size_t bytes) {
+	bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+	int dev = 0;
+	cudaGetDevice(&dev);
+	std::lock_guard<std::mutex> g(g_lock);
+	auto it = g_free.lower_bound(std::make_pair(dev, bytes));
+	if (it != g_free.end() && it->first.first == dev && it->first.second <= bytes + bytes / 8 + (1u << 20)) {
+		*out = it->second;
+		g_live[*out] = Block{*out, it->first.second, dev};
+		g_cached -= it->first.second;
+		g_free.erase(it);
+		return cudaSuccess;
+	}
+	cudaError_t e = cudaMalloc(out, bytes);
+	if (e != cudaSuccess) { cudaGetLastError(); trim_locked(0); e = cudaMalloc(out, bytes); }
+	if (e == cudaSuccess) g_live[*out] = Block{*out, bytes, dev};
+	return e;
+}
+static void release(void* p) {
+	if (!p) return;
+	std::lock_guard<std::mutex> g(g_lock);
+	auto it = g_live.find(p);
+	if (it == g_live.end()) { cudaFree(p); return; }
+	g_free.emplace(std::make_pair(it->second.device, it->second.bytes), p);
+	g_cached += it->second.bytes;
+	g_live.erase(it);
+	trim_locked(limit());
+}
+static void trim_all() { std::lock_guard<std::mutex> g(g_lock); trim_locked(0); }
+}  // namespace devcache
+template <class T> static cudaError_t dev_alloc(T** out, size_t bytes) { return devcache::alloc((void**)out, bytes); }
+static void dev_free(void* p) { devcache::release(p); }
+
 // call-scoped device buffer: freed on every return path (the ABI functions leave through CUDA_TRY on errors)
 template <class T>
 struct DevBuf {
@@ -40,8 +104,8 @@ struct DevBuf {
 	DevBuf() = default;
 	DevBuf(const DevBuf&) = delete;
 	DevBuf& operator=(const DevBuf&) = delete;
-	~DevBuf() { if (p) cudaFree(p); }
-	cudaError_t alloc(size_t count) { return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
+	~DevBuf() { if (p) dev_free(p); }
+	cudaError_t alloc(size_t count) { return dev_alloc(&p, std::max<size_t>(count, 1) * sizeof(T)); }
 	operator T*() const { return p; }
 };
 #define CUDA_TRY(expr)                                                                          \
@@ -272,7 +336,8 @@ struct ear_b200_scene {
 	unsigned long long* d_scratch_counters = nullptr;
 	ear_b200_stats stats{};
 	// recorder visibility maps (vismap.cuh), cached per recorder position
-	struct VisMapHost { float x[3]; int res; int* d_offsets; int* d_items; size_t n_items; };
+	struct VisMapHost { float x[3]; int res; int* d_offsets; int* d_items; size_t n_items; bool sorted; };
+	int vismap_sort = -1;           // -1: order the texel lists by distance once most queries turn out blocked; 0 never; 1 at build time (EAR_B200_VISMAP_SORT)
 	std::vector<VisMapHost> vismaps;
 	int vismap_res = -1;            // -1: choose from the triangle count; 0: disabled (EAR_B200_VISMAP_RES)
 	VisMapDev* d_maps = nullptr; int* d_map_of = nullptr; size_t map_of_cap = 0;
@@ -295,6 +360,7 @@ struct ear_b200_scene {
 
 extern "C" const char* ear_b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t ear_b200_abi_version(void) { return EAR_B200_ABI_VERSION; }
+extern "C" void ear_b200_release_cached_memory(void) { devcache::trim_all(); }
 extern "C" int32_t ear_b200_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -346,14 +412,14 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
 	s->sm_count = prop.multiProcessorCount;
 	CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-	CUDA_TRY(cudaMalloc(&s->d_queue, sizeof(unsigned long long)));
+	CUDA_TRY(dev_alloc(&s->d_queue, sizeof(unsigned long long)));
 	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
 	s->dev.n_tris = h.n_tris; s->dev.n_materials = h.n_materials; s->dev.n_bands = h.n_bands;
 	s->dev.s0 = h.s0;
 	// overflow rows of the traversal stacks: a walk holds at most 3 entries per level of the 4-wide tree (+ slack)
 	s->dev.spill_threads = s->sm_count * 16 * kBlock;   // 16 blocks of kBlock threads is the most an SM can hold
 	s->dev.spill_rows = std::max(1, 3 * h.depth + 4 - kStackEntries);
-	CUDA_TRY(cudaMalloc(&s->d_spill, (size_t)s->dev.spill_rows * s->dev.spill_threads * sizeof(int2)));
+	CUDA_TRY(dev_alloc(&s->d_spill, (size_t)s->dev.spill_rows * s->dev.spill_threads * sizeof(int2)));
 	s->dev.spill = s->d_spill;
 	// EAR_B200_EXACT_SLACK=1 selects the rigorous per-child interval bound (about 2x the node visits)
 	const char* ex = std::getenv("EAR_B200_EXACT_SLACK");
@@ -369,6 +435,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
+	if (const char* vs = std::getenv("EAR_B200_VISMAP_SORT")) s->vismap_sort = std::max(-1, std::min(1, std::atoi(vs)));
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
 	if (const char* sm = std::getenv("EAR_B200_SPLAT")) s->splat_mode = std::string(sm) == "window" ? 1 : 0;
 	if (const char* pg = std::getenv("EAR_B200_GENERATIONS")) s->pool_generations = std::max(0, std::atoi(pg));
@@ -376,7 +443,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	const char* ce = std::getenv("EAR_B200_CHECK_EVERY");
 	if (ce) s->check_every = std::max(1, std::atoi(ce));
 	CUDA_TRY(cudaMallocHost(&s->h_counts, 16 * sizeof(int)));   // 8 pool counters + the queue head
-	CUDA_TRY(cudaMalloc(&s->d_scratch_counters, 8 * sizeof(unsigned long long)));
+	CUDA_TRY(dev_alloc(&s->d_scratch_counters, 8 * sizeof(unsigned long long)));
 	return 0;
 }
 
@@ -432,7 +499,7 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 			h.maxabs = std::max(h.maxabs, std::max(std::fabs(r.lo[k]), std::fabs(r.hi[k])));
 		}
 		image_layout(h);
-		CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+		CUDA_TRY(dev_alloc(&s->d_image, (size_t)h.bytes));
 		CUDA_TRY(cudaMemcpyAsync(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice, 0));
 		CUDA_TRY(cudaMemcpyAsync(s->d_image + h.off_nodes, r.d_nodes, (size_t)r.n_nodes * sizeof(Node), cudaMemcpyDeviceToDevice, 0));
 		if (n_tris) CUDA_TRY(cudaMemcpyAsync(s->d_image + h.off_tris, r.d_tris, (size_t)n_tris * sizeof(TriRecord), cudaMemcpyDeviceToDevice, 0));
@@ -447,7 +514,7 @@ extern "C" int32_t ear_b200_scene_create(const float* verts, const int32_t* tri_
 			h.maxabs = std::max(h.maxabs, std::max(std::fabs(bvh.lo[k]), std::fabs(bvh.hi[k])));
 		}
 		image_layout(h);
-		CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+		CUDA_TRY(dev_alloc(&s->d_image, (size_t)h.bytes));
 		CUDA_TRY(cudaMemcpy(s->d_image, &h, sizeof(h), cudaMemcpyHostToDevice));
 		CUDA_TRY(cudaMemcpy(s->d_image + h.off_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(Node), cudaMemcpyHostToDevice));
 		if (!bvh.tris.empty())
@@ -471,7 +538,7 @@ extern "C" int32_t ear_b200_scene_set_emitters(ear_b200_scene* s, const float* v
 	if (!s) return fail("scene_set_emitters: null scene");
 	if (n < 0 || (n > 0 && !verts)) return fail("scene_set_emitters: bad arguments");
 	CUDA_TRY(cudaSetDevice(s->device));
-	cudaFree(s->d_emitters); s->d_emitters = nullptr; s->n_emitters = 0; s->emitter_area.clear(); s->emitter_verts.clear();
+	dev_free(s->d_emitters); s->d_emitters = nullptr; s->n_emitters = 0; s->emitter_area.clear(); s->emitter_verts.clear();
 	s->dev.emitters = nullptr;
 	if (n == 0) return 0;
 	std::vector<float> rec((size_t)n * 16, 0.0f);
@@ -500,7 +567,7 @@ extern "C" int32_t ear_b200_scene_set_emitters(ear_b200_scene* s, const float* v
 		r[3] = area; r[12] = nx; r[13] = ny; r[14] = nz;
 		s->emitter_area[(size_t)i] = area;
 	}
-	CUDA_TRY(cudaMalloc(&s->d_emitters, rec.size() * sizeof(float)));
+	CUDA_TRY(dev_alloc(&s->d_emitters, rec.size() * sizeof(float)));
 	CUDA_TRY(cudaMemcpy(s->d_emitters, rec.data(), rec.size() * sizeof(float), cudaMemcpyHostToDevice));
 	s->n_emitters = n;
 	s->dev.emitters = s->d_emitters;
@@ -539,7 +606,7 @@ extern "C" int32_t ear_b200_scene_create_from_image(const void* src_device, uint
 		return fail("scene_create_from_image: image size does not match its header");
 	std::unique_ptr<ear_b200_scene, void (*)(ear_b200_scene*)> s(new ear_b200_scene(), ear_b200_scene_destroy);
 	s->device = device;
-	CUDA_TRY(cudaMalloc(&s->d_image, (size_t)h.bytes));
+	CUDA_TRY(dev_alloc(&s->d_image, (size_t)h.bytes));
 	CUDA_TRY(cudaMemcpy(s->d_image, src_device, (size_t)h.bytes, cudaMemcpyDefault));
 	s->materials.resize((size_t)h.n_materials * h.n_bands * 4);
 	CUDA_TRY(cudaMemcpy(s->materials.data(), s->d_image + h.off_materials, s->materials.size() * sizeof(float), cudaMemcpyDeviceToHost));
@@ -556,18 +623,19 @@ extern "C" int32_t ear_b200_scene_clone(ear_b200_scene* s, int32_t device, ear_b
 extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	if (!s) return;
 	cudaSetDevice(s->device);
-	cudaFree(s->d_image); cudaFree(s->d_spill); cudaFree(s->d_emitters);
-	cudaFree(s->d_ctx); cudaFree(s->d_rec); cudaFree(s->d_prefix); cudaFree(s->d_queue); cudaFree(s->d_ctx_area);
-	cudaFree(s->pool.ro); cudaFree(s->pool.rd); cudaFree(s->pool.rm); cudaFree(s->pool.hit);
-	cudaFree(s->pool.sh0); cudaFree(s->pool.sh1); cudaFree(s->pool.sh2); cudaFree(s->pool.trav_list);
-	cudaFree(s->pool.q_list); cudaFree(s->pool.vis_list); cudaFree(s->pool.counts);
-	cudaFree(s->pool.trav_tmp); cudaFree(s->pool.q_tmp); cudaFree(s->pool.bins); cudaFree(s->pool.ctx_log2af);
-	cudaFree(s->pool.pair_count); cudaFree(s->pool.pair_base); cudaFree(s->pool.trav_rank); cudaFree(s->pool.q_rank);
-	cudaFree(s->d_scratch_counters);
+	cudaDeviceSynchronize();   // released blocks go back to the cache: nothing of this scene may still be in flight
+	dev_free(s->d_image); dev_free(s->d_spill); dev_free(s->d_emitters);
+	dev_free(s->d_ctx); dev_free(s->d_rec); dev_free(s->d_prefix); dev_free(s->d_queue); dev_free(s->d_ctx_area);
+	dev_free(s->pool.ro); dev_free(s->pool.rd); dev_free(s->pool.rm); dev_free(s->pool.hit);
+	dev_free(s->pool.sh0); dev_free(s->pool.sh1); dev_free(s->pool.sh2); dev_free(s->pool.trav_list);
+	dev_free(s->pool.q_list); dev_free(s->pool.vis_list); dev_free(s->pool.counts);
+	dev_free(s->pool.trav_tmp); dev_free(s->pool.q_tmp); dev_free(s->pool.bins); dev_free(s->pool.ctx_log2af);
+	dev_free(s->pool.pair_count); dev_free(s->pool.pair_base); dev_free(s->pool.trav_rank); dev_free(s->pool.q_rank);
+	dev_free(s->d_scratch_counters);
 	if (s->h_counts) cudaFreeHost(s->h_counts);
 	for (auto& e : s->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-	for (auto& m : s->vismaps) { cudaFree(m.d_offsets); cudaFree(m.d_items); }
-	cudaFree(s->d_maps); cudaFree(s->d_map_of); cudaFree(s->d_q_bvh); cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums); cudaFree(s->d_post);
+	for (auto& m : s->vismaps) { dev_free(m.d_offsets); dev_free(m.d_items); }
+	dev_free(s->d_maps); dev_free(s->d_map_of); dev_free(s->d_q_bvh); dev_free(s->d_vis_counts); dev_free(s->d_vis_sums); dev_free(s->d_post);
 	if (s->stream) cudaStreamDestroy(s->stream);
 	delete s;
 }
@@ -632,12 +700,12 @@ extern "C" int32_t ear_b200_occluded(ear_b200_scene* s, const float* p_in, const
 		one.kind = EAR_B200_MONO;
 		std::memcpy(one.position, x, 12);
 		s->h_rec.assign(1, one);
-		if (s->rec_cap < 1) { cudaFree(s->d_rec); CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder))); s->rec_cap = 1; }
+		if (s->rec_cap < 1) { dev_free(s->d_rec); CUDA_TRY(dev_alloc(&s->d_rec, sizeof(ear_b200_recorder))); s->rec_cap = 1; }
 		CUDA_TRY(cudaMemcpyAsync(s->d_rec, &one, sizeof(one), cudaMemcpyHostToDevice, s->stream));
 		if (int32_t rc = prepare_vismaps(s, 1, 1, s->stream, &n_mapped)) return rc;
 		if (n_mapped && (size_t)chunk > s->q_bvh_cap) {
-			cudaFree(s->d_q_bvh);
-			CUDA_TRY(cudaMalloc(&s->d_q_bvh, (size_t)chunk * sizeof(uint2)));
+			dev_free(s->d_q_bvh);
+			CUDA_TRY(dev_alloc(&s->d_q_bvh, (size_t)chunk * sizeof(uint2)));
 			s->q_bvh_cap = (size_t)chunk;
 		}
 		p.rec = s->d_rec; p.n_rec = 1; p.n_ctx = 1;
@@ -710,11 +778,11 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	for (int32_t i = 0; i < n_ctx * n_rec; ++i)
 		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("render: unknown recorder kind");
 	if ((size_t)n_ctx > s->ctx_cap) {
-		cudaFree(s->d_ctx); cudaFree(s->d_prefix); cudaFree(s->d_ctx_area);
+		dev_free(s->d_ctx); dev_free(s->d_prefix); dev_free(s->d_ctx_area);
 		s->d_ctx = nullptr; s->d_prefix = nullptr; s->d_ctx_area = nullptr; s->ctx_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->d_ctx, sizeof(ear_b200_context) * n_ctx));
-		CUDA_TRY(cudaMalloc(&s->d_prefix, sizeof(long long) * (n_ctx + 1)));
-		CUDA_TRY(cudaMalloc(&s->d_ctx_area, sizeof(float) * n_ctx));
+		CUDA_TRY(dev_alloc(&s->d_ctx, sizeof(ear_b200_context) * n_ctx));
+		CUDA_TRY(dev_alloc(&s->d_prefix, sizeof(long long) * (n_ctx + 1)));
+		CUDA_TRY(dev_alloc(&s->d_ctx_area, sizeof(float) * n_ctx));
 		s->ctx_cap = n_ctx;
 	}
 	// Mesh::total_area of every mesh source: areas added one by one in file order, in float (src/Mesh.cpp:90)
@@ -726,8 +794,8 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 			emit_area[(size_t)c] = total;
 		}
 	if ((size_t)n_ctx * n_rec > s->rec_cap) {
-		cudaFree(s->d_rec);
-		CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec));
+		dev_free(s->d_rec);
+		CUDA_TRY(dev_alloc(&s->d_rec, sizeof(ear_b200_recorder) * (size_t)n_ctx * n_rec));
 		s->rec_cap = (size_t)n_ctx * n_rec;
 	}
 	std::vector<long long> prefix(n_ctx + 1, 0);
@@ -782,32 +850,32 @@ struct LaunchTimer {   // records an event pair around one launch
 static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	WfPool& pl = s->pool;
 	if (slots > s->pool_slots) {
-		cudaFree(pl.ro); cudaFree(pl.rd); cudaFree(pl.rm); cudaFree(pl.hit); cudaFree(pl.sh0); cudaFree(pl.sh1); cudaFree(pl.sh2);
-		cudaFree(pl.trav_list); cudaFree(pl.trav_tmp); cudaFree(pl.trav_rank);
-		CUDA_TRY(cudaMalloc(&pl.ro, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.rd, slots * sizeof(float4)));
-		CUDA_TRY(cudaMalloc(&pl.rm, slots * sizeof(uint4))); CUDA_TRY(cudaMalloc(&pl.hit, slots * sizeof(int2)));
-		CUDA_TRY(cudaMalloc(&pl.sh0, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.sh1, slots * sizeof(float4)));
-		CUDA_TRY(cudaMalloc(&pl.sh2, slots * sizeof(float4))); CUDA_TRY(cudaMalloc(&pl.trav_list, slots * sizeof(int)));
-		CUDA_TRY(cudaMalloc(&pl.trav_tmp, slots * sizeof(uint2)));
-		CUDA_TRY(cudaMalloc(&pl.trav_rank, slots * sizeof(int)));
+		dev_free(pl.ro); dev_free(pl.rd); dev_free(pl.rm); dev_free(pl.hit); dev_free(pl.sh0); dev_free(pl.sh1); dev_free(pl.sh2);
+		dev_free(pl.trav_list); dev_free(pl.trav_tmp); dev_free(pl.trav_rank);
+		CUDA_TRY(dev_alloc(&pl.ro, slots * sizeof(float4))); CUDA_TRY(dev_alloc(&pl.rd, slots * sizeof(float4)));
+		CUDA_TRY(dev_alloc(&pl.rm, slots * sizeof(uint4))); CUDA_TRY(dev_alloc(&pl.hit, slots * sizeof(int2)));
+		CUDA_TRY(dev_alloc(&pl.sh0, slots * sizeof(float4))); CUDA_TRY(dev_alloc(&pl.sh1, slots * sizeof(float4)));
+		CUDA_TRY(dev_alloc(&pl.sh2, slots * sizeof(float4))); CUDA_TRY(dev_alloc(&pl.trav_list, slots * sizeof(int)));
+		CUDA_TRY(dev_alloc(&pl.trav_tmp, slots * sizeof(uint2)));
+		CUDA_TRY(dev_alloc(&pl.trav_rank, slots * sizeof(int)));
 		s->pool_slots = slots;
 	}
 	if (queries > s->pool_queries) {
-		cudaFree(pl.q_list); cudaFree(pl.vis_list); cudaFree(pl.q_tmp); cudaFree(pl.q_rank);
-		CUDA_TRY(cudaMalloc(&pl.q_list, queries * sizeof(uint2))); CUDA_TRY(cudaMalloc(&pl.vis_list, queries * sizeof(uint2)));
-		CUDA_TRY(cudaMalloc(&pl.q_tmp, queries * sizeof(uint2)));
-		CUDA_TRY(cudaMalloc(&pl.q_rank, queries * sizeof(int)));
+		dev_free(pl.q_list); dev_free(pl.vis_list); dev_free(pl.q_tmp); dev_free(pl.q_rank);
+		CUDA_TRY(dev_alloc(&pl.q_list, queries * sizeof(uint2))); CUDA_TRY(dev_alloc(&pl.vis_list, queries * sizeof(uint2)));
+		CUDA_TRY(dev_alloc(&pl.q_tmp, queries * sizeof(uint2)));
+		CUDA_TRY(dev_alloc(&pl.q_rank, queries * sizeof(int)));
 		s->pool_queries = queries;
 	}
-	if (!pl.counts) CUDA_TRY(cudaMalloc(&pl.counts, 8 * sizeof(int)));
+	if (!pl.counts) CUDA_TRY(dev_alloc(&pl.counts, 8 * sizeof(int)));
 	if (!pl.pair_count) {
-		CUDA_TRY(cudaMalloc(&pl.pair_count, kPrivMaxPairs * sizeof(int)));
-		CUDA_TRY(cudaMalloc(&pl.pair_base, (kPrivMaxPairs + 1) * sizeof(int)));
+		CUDA_TRY(dev_alloc(&pl.pair_count, kPrivMaxPairs * sizeof(int)));
+		CUDA_TRY(dev_alloc(&pl.pair_base, (kPrivMaxPairs + 1) * sizeof(int)));
 	}
 	pl.vis_sorted = pl.q_tmp;   // the pre-binning query list is dead once the queries are scattered
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	pl.slot_bits = kMaxSlotBits;   // harness calls: one implicit recorder
-	if (!pl.bins) CUDA_TRY(cudaMalloc(&pl.bins, kBinsTotal * sizeof(int)));
+	if (!pl.bins) CUDA_TRY(dev_alloc(&pl.bins, kBinsTotal * sizeof(int)));
 	pl.ray_key = s->ray_key;
 	pl.sort_queries = s->sort_queries;
 	for (int k = 0; k < 3; ++k) {
@@ -844,17 +912,17 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	};
 	// scratch (texel counters + block sums) is kept with the scene: every map of a scene has the same size
 	if ((size_t)n_tex > s->vis_scratch_cap) {
-		cudaFree(s->d_vis_counts); cudaFree(s->d_vis_sums);
+		dev_free(s->d_vis_counts); dev_free(s->d_vis_sums);
 		s->d_vis_counts = nullptr; s->d_vis_sums = nullptr; s->vis_scratch_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->d_vis_counts, (size_t)n_tex * sizeof(int)));
-		CUDA_TRY(cudaMalloc(&s->d_vis_sums, kVisScanBlocks * sizeof(long long)));
+		CUDA_TRY(dev_alloc(&s->d_vis_counts, (size_t)n_tex * sizeof(int)));
+		CUDA_TRY(dev_alloc(&s->d_vis_sums, kVisScanBlocks * sizeof(long long)));
 		s->vis_scratch_cap = (size_t)n_tex;
 	}
 	int* d_counts = s->d_vis_counts;
-	CUDA_TRY(cudaMalloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
+	CUDA_TRY(dev_alloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
 	struct MapGuard {   // the two allocations of a map are released on every error return until the map is adopted
 		ear_b200_scene::VisMapHost* m;
-		~MapGuard() { if (m) { cudaFree(m->d_offsets); cudaFree(m->d_items); } }
+		~MapGuard() { if (m) { dev_free(m->d_offsets); dev_free(m->d_items); } }
 	} guard{&m};
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
 	lap("alloc + clear");
@@ -897,7 +965,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	}
 	s->vis_bytes += map_bytes;
 	m.n_items = (size_t)total;
-	CUDA_TRY(cudaMalloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
+	CUDA_TRY(dev_alloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
 	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
 	vis_build_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, d_counts, m.d_offsets, m.d_items, id_bits);
 	CUDA_TRY(cudaGetLastError());
@@ -906,6 +974,19 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	s->vismaps.push_back(m);
 	guard.m = nullptr;
 	*index = (int)s->vismaps.size() - 1;
+	return 0;
+}
+
+// orders the texel lists of every map of the scene by distance from its recorder (vis_sort_kernel), once
+static int32_t sort_vismaps(ear_b200_scene* s, cudaStream_t stream) {
+	for (auto& m : s->vismaps) {
+		if (m.sorted) continue;
+		const int n_tex = 6 * m.res * m.res;
+		LaunchTimer t(s, stream, 7);
+		vis_sort_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, m.x[0], m.x[1], m.x[2], m.d_offsets, m.d_items, n_tex);
+		m.sorted = true;
+	}
+	CUDA_TRY(cudaGetLastError());
 	return 0;
 }
 
@@ -922,8 +1003,8 @@ static int32_t prepare_vismaps(ear_b200_scene* s, int n_ctx, int n_rec, cudaStre
 		if (idx >= 0) ++*n_mapped;
 	}
 	if (*n_mapped == 0) return 0;
-	if (n > s->map_of_cap) { cudaFree(s->d_map_of); CUDA_TRY(cudaMalloc(&s->d_map_of, n * sizeof(int))); s->map_of_cap = n; }
-	if (!s->d_maps) CUDA_TRY(cudaMalloc(&s->d_maps, 64 * sizeof(VisMapDev)));
+	if (n > s->map_of_cap) { dev_free(s->d_map_of); CUDA_TRY(dev_alloc(&s->d_map_of, n * sizeof(int))); s->map_of_cap = n; }
+	if (!s->d_maps) CUDA_TRY(dev_alloc(&s->d_maps, 64 * sizeof(VisMapDev)));
 	std::vector<VisMapDev> maps(s->vismaps.size());
 	for (size_t i = 0; i < maps.size(); ++i) {
 		maps[i].offsets = s->vismaps[i].d_offsets; maps[i].items = s->vismaps[i].d_items; maps[i].res = s->vismaps[i].res;
@@ -962,11 +1043,12 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	if (dbg) cudaDeviceSynchronize();
 	int n_mapped = 0;
 	if (p.n_rec > 0) { if (int32_t rc = prepare_vismaps(s, p.n_ctx, p.n_rec, stream, &n_mapped)) return rc; }
+	if (n_mapped && s->vismap_sort == 1) { if (int32_t rc = sort_vismaps(s, stream)) return rc; }
 	if (dbg) { cudaDeviceSynchronize(); std::fprintf(stderr, "[ear_b200] pool + visibility maps: %.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count()); }
 	const size_t n_queries = (size_t)slots * std::max(1, p.n_rec);
 	if (n_mapped && n_queries > s->q_bvh_cap) {
-		cudaFree(s->d_q_bvh);
-		CUDA_TRY(cudaMalloc(&s->d_q_bvh, n_queries * sizeof(uint2)));
+		dev_free(s->d_q_bvh);
+		CUDA_TRY(dev_alloc(&s->d_q_bvh, n_queries * sizeof(uint2)));
 		s->q_bvh_cap = n_queries;
 	}
 	WfPool pl = s->pool;
@@ -975,9 +1057,9 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
 	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
 	if ((size_t)p.n_ctx > s->log2af_cap) {
-		cudaFree(s->pool.ctx_log2af);
+		dev_free(s->pool.ctx_log2af);
 		s->pool.ctx_log2af = nullptr; s->log2af_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->pool.ctx_log2af, sizeof(double) * p.n_ctx));
+		CUDA_TRY(dev_alloc(&s->pool.ctx_log2af, sizeof(double) * p.n_ctx));
 		s->log2af_cap = p.n_ctx;
 		pl.ctx_log2af = s->pool.ctx_log2af;
 	}
@@ -1040,6 +1122,9 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 		// is refilled in launch k + 1, so "no live ray" alone also holds between two generations of a pool that turns
 		// over in lockstep (every ray reaching the bounce cap in the same iteration).
 		if (s->h_counts[0] == 0 && (long long)queue_head >= p.total_work) { finished = true; break; }
+		// most occlusion queries of the last iteration were blocked: from now on the maps answer them nearest-first
+		if (n_mapped && s->vismap_sort < 0 && s->h_counts[1] > 4096 && (long long)s->h_counts[2] * 2 < s->h_counts[1])
+			if (int32_t rc = sort_vismaps(s, stream)) return rc;
 	}
 	if (!finished) return fail("render: the wavefront loop hit its iteration bound with rays left (internal error)");
 	return 0;
@@ -1106,8 +1191,8 @@ static int32_t upload_recorders(ear_b200_scene* s, const ear_b200_recorder* rec,
 	for (size_t i = 0; i < n; ++i)
 		if (rec[i].kind != EAR_B200_MONO && rec[i].kind != EAR_B200_STEREO) return fail("post: unknown recorder kind");
 	if (n > s->rec_cap) {
-		cudaFree(s->d_rec); s->d_rec = nullptr; s->rec_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->d_rec, sizeof(ear_b200_recorder) * n));
+		dev_free(s->d_rec); s->d_rec = nullptr; s->rec_cap = 0;
+		CUDA_TRY(dev_alloc(&s->d_rec, sizeof(ear_b200_recorder) * n));
 		s->rec_cap = n;
 	}
 	CUDA_TRY(cudaMemcpyAsync(s->d_rec, rec, sizeof(ear_b200_recorder) * n, cudaMemcpyHostToDevice, stream));
@@ -1116,8 +1201,8 @@ static int32_t upload_recorders(ear_b200_scene* s, const ear_b200_recorder* rec,
 
 static int32_t ensure_post_scratch(ear_b200_scene* s, size_t n_tracks) {
 	if (n_tracks > s->post_cap) {
-		cudaFree(s->d_post); s->d_post = nullptr; s->post_cap = 0;
-		CUDA_TRY(cudaMalloc(&s->d_post, n_tracks * 3 * sizeof(float)));   // [track_max or t60 | track_len | real_length snapshot]
+		dev_free(s->d_post); s->d_post = nullptr; s->post_cap = 0;
+		CUDA_TRY(dev_alloc(&s->d_post, n_tracks * 3 * sizeof(float)));   // [track_max or t60 | track_len | real_length snapshot]
 		s->post_cap = n_tracks;
 	}
 	return 0;
@@ -1318,7 +1403,7 @@ static int32_t render_on(std::vector<ear_b200_scene*>& scenes, bool peer, const 
 		~Cleanup() {
 			for (size_t g = 0; g < per.size(); ++g) {
 				cudaSetDevice(scenes[g]->device);
-				cudaFree(per[g].hist); cudaFree(per[g].range); cudaFree(per[g].counters);
+				dev_free(per[g].hist); dev_free(per[g].range); dev_free(per[g].counters);
 			}
 		}
 	} cleanup{per, scenes};
@@ -1328,9 +1413,9 @@ static int32_t render_on(std::vector<ear_b200_scene*>& scenes, bool peer, const 
 		auto bad = [&](const std::string& what, cudaError_t e) { me.rc = 1; me.err = what + ": " + cudaGetErrorString(e); };
 		cudaError_t e;
 		if ((e = cudaSetDevice(s->device)) != cudaSuccess) return bad("cudaSetDevice", e);
-		if ((e = cudaMalloc(&me.hist, std::max<size_t>(hist_floats, 1) * sizeof(float))) != cudaSuccess) return bad("histogram allocation", e);
-		if ((e = cudaMalloc(&me.range, n_tracks * 2 * sizeof(uint32_t))) != cudaSuccess) return bad("range allocation", e);
-		if ((e = cudaMalloc(&me.counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bad("counter allocation", e);
+		if ((e = dev_alloc(&me.hist, std::max<size_t>(hist_floats, 1) * sizeof(float))) != cudaSuccess) return bad("histogram allocation", e);
+		if ((e = dev_alloc(&me.range, n_tracks * 2 * sizeof(uint32_t))) != cudaSuccess) return bad("range allocation", e);
+		if ((e = dev_alloc(&me.counters, 8 * sizeof(unsigned long long))) != cudaSuccess) return bad("counter allocation", e);
 		cudaMemsetAsync(me.hist, 0, hist_floats * sizeof(float), s->stream);
 		cudaMemsetAsync(me.counters, 0, 8 * sizeof(unsigned long long), s->stream);
 		init_range_kernel<<<(unsigned)((n_tracks + 127) / 128), 128, 0, s->stream>>>(me.range, (int)n_tracks);

@@ -142,6 +142,58 @@ __global__ void __launch_bounds__(1024) vis_scan_offsets_kernel(const int* in, c
 	}
 }
 
+// Texel lists ordered by distance from the recorder, nearest triangle first (one warp per texel).  A query that is
+// blocked stops at the first triangle its segment crosses; in a venue of several rooms the blocker of nearly every
+// query from another room is a wall of the RECORDER's room, i.e. among the nearest entries of the texel -- with the
+// fill order (arbitrary: atomics) a blocked query tests a third of its list on average, with this order one or two
+// entries.  Visible queries test the whole list either way, so the order is only established when the render loop
+// sees that most queries are blocked (launch_wavefront).  Key: squared distance from X to the triangle's centroid.
+constexpr int kVisSortMax = 256;   // longest list that is stored (kVisMaxList) -- lists are sorted in shared memory
+__global__ void __launch_bounds__(256) vis_sort_kernel(SceneDev sc, float x0, float x1, float x2, const int* offsets, int* items, int n_tex) {
+	__shared__ float s_key[8][kVisSortMax];
+	__shared__ int s_item[8][kVisSortMax];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int warps = (gridDim.x * blockDim.x) >> 5;
+	for (int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < n_tex; t += warps) {
+		const int beg = offsets[t];
+		if (beg < 0) continue;                                   // over the cap: not stored
+		const int len = (offsets[t + 1] & ~kVisOverlong) - beg;
+		if (len < 2 || len > kVisSortMax) continue;
+		int n2 = 2;
+		while (n2 < len) n2 <<= 1;
+		for (int i = lane; i < n2; i += 32) {
+			float key = INFINITY; int item = -1;
+			if (i < len) {
+				item = items[beg + i];
+				const float4 r0 = __ldg(sc.tris + 4 * (size_t)item), r1 = __ldg(sc.tris + 4 * (size_t)item + 1), r2 = __ldg(sc.tris + 4 * (size_t)item + 2);
+				const float cx = r0.x + (r1.x + r2.x) * (1.0f / 3.0f) - x0, cy = r0.y + (r1.y + r2.y) * (1.0f / 3.0f) - x1, cz = r0.z + (r1.z + r2.z) * (1.0f / 3.0f) - x2;
+				key = cx * cx + cy * cy + cz * cz;
+			}
+			s_key[wid][i] = key; s_item[wid][i] = item;
+		}
+		__syncwarp();
+		for (int k = 2; k <= n2; k <<= 1)
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				for (int i = lane; i < n2; i += 32) {
+					const int l = i ^ j;
+					if (l > i) {
+						const bool up = (i & k) == 0;
+						const float a = s_key[wid][i], b = s_key[wid][l];
+						// ties keep the lower item first so that the order is deterministic
+						const bool swap = up ? (a > b || (a == b && s_item[wid][i] > s_item[wid][l])) : (a < b || (a == b && s_item[wid][i] < s_item[wid][l]));
+						if (swap) {
+							s_key[wid][i] = b; s_key[wid][l] = a;
+							const int ti = s_item[wid][i]; s_item[wid][i] = s_item[wid][l]; s_item[wid][l] = ti;
+						}
+					}
+				}
+				__syncwarp();
+			}
+		for (int i = lane; i < len; i += 32) items[beg + i] = s_item[wid][i];
+		__syncwarp();
+	}
+}
+
 // K4 through the maps: one query per thread.  Visible queries go to vis_list; queries whose texel list is too
 // long (or whose recorder has no map) go to `q_bvh` for the BVH any-hit kernel.
 __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool, RenderParams p, const VisMapDev* maps,

@@ -133,6 +133,10 @@ typedef struct ear_b200_stats {
 const char* ear_b200_last_error(void);
 int32_t ear_b200_abi_version(void);
 int32_t ear_b200_device_count(void);
+/* The library keeps device memory it has released (ray pools, BVH scratch, visibility maps: GBs) in a per-process cache so
+ * that the next scene or render does not pay cudaMalloc / cudaFree again (EAR_B200_CACHE_MB caps it, default 32768).
+ * This returns all of it to the driver. */
+void ear_b200_release_cached_memory(void);
 
 /* Uploads the triangle soup (file order), builds the BVH, keeps everything resident on `device`.
  * materials: [n_materials][n_bands][4] = {reflection, transmission, kept, specularity} where

@@ -67,11 +67,21 @@ def _render_both(tmp_path, sc, name, env):
 
 
 def _same_files(a_dir, b_dir, pattern):
+    """Same file set and sizes; 16-bit PCM within 2 LSB and float dumps within 1e-5 of the peak: the two runs trace the
+    same paths, but the float atomics of two GPU runs add in different orders (the byte-identity bar is checked where the
+    tracks are deterministic, tests/test_host_surface.py)."""
     names = sorted(n for n in os.listdir(a_dir) if re.search(pattern, n))
     assert names and names == sorted(n for n in os.listdir(b_dir) if re.search(pattern, n)), (names, os.listdir(b_dir))
     for n in names:
         a, b = open(os.path.join(a_dir, n), "rb").read(), open(os.path.join(b_dir, n), "rb").read()
-        assert a == b, f"{n}: {len(a)} vs {len(b)} bytes, first difference at {next((i for i, (x, y) in enumerate(zip(a, b)) if x != y), -1)}"
+        assert len(a) == len(b), f"{n}: {len(a)} vs {len(b)} bytes"
+        if n.endswith(".wav"):
+            assert a[:44] == b[:44], n
+            pa, pb = np.frombuffer(a[44:], "<i2").astype(np.int32), np.frombuffer(b[44:], "<i2").astype(np.int32)
+            assert np.abs(pa - pb).max() <= 2, f"{n}: PCM differs by {np.abs(pa - pb).max()} LSB"
+        else:
+            fa, fb = np.frombuffer(a, "<f4"), np.frombuffer(b, "<f4")
+            assert np.abs(fa - fb).max() <= 1e-5 * max(np.abs(fb).max(), 1e-30), n
     return names
 
 
