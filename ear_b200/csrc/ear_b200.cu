@@ -979,14 +979,23 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 
 // orders the texel lists of every map of the scene by distance from its recorder (vis_sort_kernel), once
 static int32_t sort_vismaps(ear_b200_scene* s, cudaStream_t stream) {
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
+	if (dbg) cudaStreamSynchronize(stream);
+	int n_sorted = 0;
 	for (auto& m : s->vismaps) {
 		if (m.sorted) continue;
 		const int n_tex = 6 * m.res * m.res;
 		LaunchTimer t(s, stream, 7);
 		vis_sort_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, m.x[0], m.x[1], m.x[2], m.d_offsets, m.d_items, n_tex);
 		m.sorted = true;
+		++n_sorted;
 	}
 	CUDA_TRY(cudaGetLastError());
+	if (dbg && n_sorted) {
+		cudaStreamSynchronize(stream);
+		std::fprintf(stderr, "[ear_b200] vismap: %d map(s) ordered by distance in %.2f ms\n", n_sorted, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+	}
 	return 0;
 }
 

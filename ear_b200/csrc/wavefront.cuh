@@ -481,8 +481,16 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		if (shaded) {
 			++lc.occlusion;
 			const float* x = p.rec[(size_t)c * p.n_rec + r].position;
-			const V3 lsdir = vnormalized(vsub(mk(x[0], x[1], x[2]), pnt));
-			facing = mesh_emit || vdot(lsdir, n) > 0.0f;
+			// dot(lsdir, n) > 0 with lsdir = normalize(x - p) (src/Scene.cpp:202-209).  The sign is that of dot(x - p, n);
+			// normalising (three divisions by the rounded length) and the three roundings of the dot move the value by a
+			// few ulp of |x - p| at most, so the unnormalised dot decides whenever it is clearly away from zero and the
+			// exact expression is evaluated only in between (64 recorders: this loop is a third of the kernel at C5).
+			const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
+			const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
+			const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
+			if (mesh_emit) facing = true;
+			else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;
+			else facing = vdot(vnormalized(seg), n) > 0.0f;
 		}
 		const unsigned mq = __ballot_sync(0xffffffffu, facing);
 		if (mq) {

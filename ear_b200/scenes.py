@@ -5,6 +5,8 @@
                      `[v0,v1,v2],[v0,v2,v3]`, blender/render_EAR/__init__.py:274).
 * `example1_scene`   BASELINE config 2: a 40 x 52 x 18 m hall with a 0.36 m thick, 3.47 m
                      high partition, 44 triangles, stereo recorder with exporter defaults.
+* `example2_scene`   BASELINE config 3: the reference's example2 (232 triangles, 2 materials, 10 keyframes,
+                     3 sources, animated listener), recovered from its .blend (ear_b200/data/example2.npz).
 * `synthetic_complex` BASELINE config 5: grid of coupled halls (C4 halls joined by door tunnels), 64 recorders.
 * `synthetic_hall`   BASELINE config 4 generator: 60 x 40 x 20 m shoebox whose six walls are
                      tessellated to an exact triangle count with seeded +-5 cm displacement,
@@ -67,6 +69,41 @@ def example1_scene(samples=1000000, wav="/tmp/click.wav", stereo=True) -> SceneD
     sc.sources.append(SourceDef([wav], position=(-5.0, 5.0, 1.6)))
     sc.recorders.append(RecorderDef("/tmp/example1.out.wav", position=(5.0, -5.0, 1.6), stereo=stereo,
                                     right_ear=(-1.0, 0.0, 0.0), head_size=0.2, head_absorption=(0.1, 0.3, 0.9)))
+    return sc
+
+
+def example2_scene(samples=100000, bach=("/tmp/bach-low.wav", "/tmp/bach-mid.wav", "/tmp/bach-high.wav"),
+                   steps="/tmp/steps.wav", door="/tmp/door.wav", out="/tmp/example2.out.wav") -> SceneDef:
+    """BASELINE config 3: the reference's example2 -- 232 triangles (three meshes of 24 + 102 + 106, split over two
+    materials), air absorption (0.01, 0.03, 0.05), 10 keyframes (frames 1, 51, ..., 451 of 500 @ 24 fps), three sources
+    x 10 keyframes x 3 bands = 90 contexts, a keyframed mono listener.  Geometry, materials, settings, the `Bach`
+    position and the Listener / Person paths are the reference's own, recovered from example2/example2.blend without
+    Blender (tests/golden/make_example2.py -> ear_b200/data/example2.npz).  Substitution: the two
+    storyboard sources the add-on would synthesise with bpy ray casts (foot steps of `Listener` and `Person`, the door
+    of `Portal`) are a steps recording moving with the Listener and door.wav moving with the Person.  `bach` is the
+    triple-band source (3SRC: bach-bwv999-{low,mid,high}.wav, 705 600 samples each in the reference)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "example2.npz"))
+    sc = SceneDef(samples=samples, air_absorption=[float(x) for x in d["air"]], drylevel=float(d["dry"]),
+                  freq=[float(x) for x in d["freq"]], keys=[float(k) for k in d["keys"]])
+    names = [str(n) for n in d["mat_names"]]
+    for m, name in enumerate(names):
+        refl, refr, spec = d["materials"][m]
+        sc.materials.append(MaterialDef(name, [float(x) for x in refl], [float(x) for x in refr], [float(x) for x in spec]))
+    tris, tri_mat = d["tris"], d["tri_mat"]
+    # MESH blocks in file order: runs of equal material (one block per object and material slot, as the exporter writes)
+    start = 0
+    for i in range(1, tris.shape[0] + 1):
+        if i == tris.shape[0] or tri_mat[i] != tri_mat[start]:
+            sc.meshes.append(MeshDef(names[int(tri_mat[start])], tris[start:i].astype(np.float32)))
+            start = i
+    n_keys = len(sc.keys)
+    sc.sources.append(SourceDef(list(bach), animation=np.tile(d["bach"][None, :], (n_keys, 1)).astype(np.float32)))
+    # foot steps sound at floor level under the walker (heads are 1.65 m above their floors in the file)
+    feet = np.array([0.0, 0.0, -1.65], np.float32)
+    sc.sources.append(SourceDef([steps], animation=(d["listener"] + feet).astype(np.float32)))
+    sc.sources.append(SourceDef([door], animation=(d["person"] + feet).astype(np.float32)))
+    sc.recorders.append(RecorderDef(out, animation=d["listener"].astype(np.float32)))
     return sc
 
 

@@ -189,8 +189,11 @@ def test_mesh_source_paths_and_histograms_match_oracle(ob, stereo):
     hg, sg = gpu.trace_paths(ctxs[1], 1, 4000, 40, seed=17)
     hc, sc_ = cpu.trace_paths(ctxs[1], 1, 4000, 40, seed=17)
     assert np.array_equal(hg, hc)
-    bad = np.nonzero((sg.view(np.uint32) != sc_.view(np.uint32)).any(1))[0]
-    assert bad.size == 0, f"{bad.size} final states differ; first rows:\n{sg[bad[:4]]}\n{sc_[bad[:4]]}\nhits {hg[bad[:2], :6]}"
+    # geometry of the final state bit for bit; the running intensity within an ulp or two: it is a product of
+    # pow(af, length) factors, and the GPU's pow (exp2(y log2 x) in double, rounded once) differs from the host libm's powf
+    # by one ulp in ~3e-4 of the evaluations (which variant of powf runs even depends on the CPU: glibc selects an FMA build)
+    assert np.array_equal(sg[:, :6].view(np.uint32), sc_[:, :6].view(np.uint32)) and np.array_equal(sg[:, 7], sc_[:, 7])
+    assert np.abs(sg[:, 6] - sc_[:, 6]).max() <= 1e-6 * np.abs(sc_[:, 6]).max()
     res = gpu.render(ctxs, recs, max_bounces=120, seed=17)
     tracks, cnt = cpu.render(ctxs, recs, max_bounces=120, seed=17)
     assert (res.rays, res.segments, res.occlusion_queries, res.contributions, res.bin_updates) == \
@@ -231,3 +234,27 @@ def test_group_render_on_one_gpu_equals_render(ob):
         assert (t.first_sample, t.real_length) == (first, real)
         assert abs(post.t60[c][0][0] - w_t60) <= 1.5 / 44100.0
     grp.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE config 3: example2 (232 triangles, 2 materials, 10 keyframes, 3 sources -> 90 contexts)
+# ---------------------------------------------------------------------------------------------------------
+def test_example2_ninety_contexts_match_oracle(ob):
+    sc = scenes.example2_scene(samples=10000)          # 1000 rays per context here; C3 itself uses 1e4
+    gpu = api.Scene.from_def(sc)
+    cpu = ob.OracleScene.from_def(sc)
+    ctxs, recs = api.contexts_from_def(sc)
+    assert len(ctxs) == 90
+    res = gpu.render(ctxs, recs, max_bounces=100, seed=33, finalise=False)
+    want, cnt = common.oracle_render_parallel(cpu, ctxs, recs, max_bounces=100, seed=33)
+    assert (res.rays, res.segments, res.occlusion_queries, res.contributions, res.bin_updates) == \
+           (90 * 1000, cnt["segments"], cnt["occlusion_queries"], cnt["contributions"], cnt["bin_updates"])
+    for c in range(90):
+        a, (data, first, real) = res.tracks[c][0][0], want[c][0][0]
+        assert (a.first_sample, a.real_length) == (first, real), c
+        n = real + 1
+        assert np.abs(a.data[:n] - data[:n]).max() <= REL_TOL * max(np.abs(data[:n]).max(), 1e-30), c
+    # and the bounce paths of a keyframed context late in the list
+    hg, _ = gpu.trace_paths(ctxs[77], 77, 3000, 60, seed=33)
+    hc, _ = cpu.trace_paths(ctxs[77], 77, 3000, 60, seed=33)
+    assert np.array_equal(hg, hc)

@@ -135,3 +135,35 @@ def test_error_lines_match(tmp_path, shim):
     out = _both(tmp_path, sc, ["render"], {"EAR_SEED": "1"}, shim)
     for tag in ("ours", "ref"):
         assert out[tag][1].returncode == 1 and "Error: Failed to open sound file" in out[tag][1].stdout, out[tag][1].stdout[-300:]
+
+
+def test_example2_fixture_is_the_reference_scene():
+    """BASELINE config 3: 232 triangles (24 + 102 + 106 over three meshes) in two materials, 10 keyframes at
+    (frame - 1) / 24 s for frames 1, 51, ..., 451, three sources x 10 keyframes x 3 bands = 90 contexts with 1e4 rays,
+    animated mono listener (values recovered from example2.blend by tests/golden/make_example2.py)."""
+    from ear_b200 import api
+    sc = scenes.example2_scene()
+    assert sc.triangles().shape == (232, 3, 3) and len(sc.materials) == 2
+    assert [m.name for m in sc.materials] == ["Material", "Ground floor"]
+    assert np.allclose(sc.materials[0].refl, (0.93, 0.97, 0.99)) and np.allclose(sc.materials[1].spec, (0.2, 0.3, 0.4))
+    assert len(sc.keys) == 10 and np.allclose(sc.keys, [(f - 1) / 24.0 for f in range(1, 500, 50)])
+    assert np.allclose(sc.air_absorption, (0.01, 0.03, 0.05)) and np.allclose(sc.freq, (0.4, 2.0, 6.0))
+    ctxs, recs = api.contexts_from_def(sc)
+    assert len(ctxs) == 90 and ctxs[0].num_samples == 10000 and len(sc.sources[0].wavs) == 3
+    assert not recs[0][0].stereo and recs[0][0].position != recs[89][0].position     # the listener walks
+    import tempfile
+    from ear_b200.earfile import read_ear
+    with tempfile.NamedTemporaryFile(suffix=".ear") as f:
+        sc.write(f.name)
+        back = read_ear(f.name)
+    assert back.triangles().shape == (232, 3, 3) and len(back.keys) == 10 and len(back.sources) == 3
+
+
+def test_example2_render_is_byte_identical(tmp_path, shim):
+    """example2 through both host surfaces (reduced ray count, short dry signals): 90 contexts, the keyframe cross-fade
+    between every pair of successive keyframes, a 3SRC and two SSRC sources, animated listener."""
+    wavs = [_tone(str(tmp_path / f"w{k}.wav"), f, n=3000) for k, f in enumerate((110.0, 900.0, 4000.0, 300.0, 1500.0))]
+    sc = scenes.example2_scene(samples=600, bach=wavs[:3], steps=wavs[3], door=wavs[4])
+    out = _both(tmp_path, sc, ["render"], {"EAR_SEED": "21", "EAR_MAX_BOUNCES": "25"}, shim)
+    assert out["ours"][1].returncode == 0 and out["ref"][1].returncode == 0, (out["ours"][1].stdout[-400:], out["ref"][1].stdout[-400:])
+    _assert_same_tree(out["ours"][0], out["ref"][0], 1 + 9 + 3 * 90)
