@@ -74,7 +74,7 @@ EXPORTS = [
     "ear_b200_scene_image_size", "ear_b200_scene_image_write", "ear_b200_scene_create_from_image", "ear_b200_scene_clone",
     "ear_b200_post_power_device", "ear_b200_post_truncate_device", "ear_b200_tracks_per_recorder",
     "ear_b200_scene_set_emitters", "ear_b200_group_create", "ear_b200_group_destroy", "ear_b200_group_size",
-    "ear_b200_group_render", "ear_b200_release_cached_memory",
+    "ear_b200_group_render", "ear_b200_release_cached_memory", "ear_b200_convolve_fft",
 ]
 
 _lib = None
@@ -128,6 +128,7 @@ def load_library(path: Optional[str] = None) -> C.CDLL:
     lib.ear_b200_scene_stats_reset.restype = None
     u32 = C.c_uint32
     lib.ear_b200_convolve.argtypes = [i32, vp, u32, u32, u32, vp, u32, u32, u32, vp, u32, u32, vp, u32, C.POINTER(u32), C.POINTER(u32)]
+    lib.ear_b200_convolve_fft.argtypes = lib.ear_b200_convolve.argtypes
     if path is None:
         _lib = lib
     return lib
@@ -258,9 +259,11 @@ class RenderResult:
     t60: Optional[list] = None         # [context][recorder][track]
 
 
-def convolve(response: "Track", dry: np.ndarray, offset: int = 0, response2: Optional["Track"] = None, device: int = 0) -> "Track":
+def convolve(response: "Track", dry: np.ndarray, offset: int = 0, response2: Optional["Track"] = None, device: int = 0,
+             fft: bool = False) -> "Track":
     """RecorderTrack::Process (src/Recorder.cpp:247-292) on the GPU: direct convolution of a dry signal with a
-    response track (cross-faded into `response2` for keyframed scenes).  Returns the result track."""
+    response track (cross-faded into `response2` for keyframed scenes).  Returns the result track.
+    fft=True: the frequency-domain form (src/Recorder.cpp:145-243), equal up to float32 FFT rounding."""
     lib = load_library()
     dry = np.ascontiguousarray(dry, np.float32)
     r1 = np.ascontiguousarray(response.data, np.float32)
@@ -272,7 +275,8 @@ def convolve(response: "Track", dry: np.ndarray, offset: int = 0, response2: Opt
     out_len = max(3 * SAMPLE_RATE, dry.shape[0] + offset + length)
     out = np.zeros(out_len, np.float32)
     of, orl = C.c_uint32(), C.c_uint32()
-    _check(lib, lib.ear_b200_convolve(
+    fn = lib.ear_b200_convolve_fft if fft else lib.ear_b200_convolve
+    _check(lib, fn(
         device, r1.ctypes.data, r1.shape[0], response.first_sample, response.real_length,
         r2.ctypes.data if r2 is not None else None, r2.shape[0] if r2 is not None else 0,
         response2.first_sample if response2 is not None else 0, response2.real_length if response2 is not None else 0,

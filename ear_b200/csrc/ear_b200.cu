@@ -1628,6 +1628,130 @@ extern "C" int32_t ear_b200_convolve(int32_t device, const float* response, uint
 	return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// RecorderTrack::Process in the frequency domain (the reference's USE_FFTW build, src/Recorder.cpp:145-243)
+// ------------------------------------------------------------------------------------------
+// out = dry (*) response, or for keyframed scenes dry.(1 - i/n) (*) response + dry.(i/n) (*) response2 -- which is the SAME
+// linear map as the direct form's per-sample interpolation of the two responses (the weight depends on the dry index only),
+// so both forms agree up to float rounding.  One zero-padded real FFT of size N >= n_dry + len per signal (cuFFT, loaded on
+// first use), a complex multiply-add, one inverse transform.  705 600 dry samples x 1e6 response samples: N = 2^21.
+#include <dlfcn.h>
+namespace fftconv {
+typedef int cufftHandle;
+typedef float2 cufftComplex;
+struct Api {
+	void* lib = nullptr;
+	int (*plan1d)(cufftHandle*, int, int, int) = nullptr;
+	int (*exec_r2c)(cufftHandle, float*, cufftComplex*) = nullptr;
+	int (*exec_c2r)(cufftHandle, cufftComplex*, float*) = nullptr;
+	int (*destroy)(cufftHandle) = nullptr;
+	bool ok() const { return plan1d && exec_r2c && exec_c2r && destroy; }
+};
+static Api& api() {
+	static Api a;
+	static std::once_flag once;
+	std::call_once(once, [] {
+		for (const char* name : {"libcufft.so.11", "libcufft.so", "/usr/local/cuda/lib64/libcufft.so.11", "/usr/local/cuda/lib64/libcufft.so"}) {
+			a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+			if (a.lib) break;
+		}
+		if (!a.lib) return;
+		a.plan1d = (int (*)(cufftHandle*, int, int, int))dlsym(a.lib, "cufftPlan1d");
+		a.exec_r2c = (int (*)(cufftHandle, float*, cufftComplex*))dlsym(a.lib, "cufftExecR2C");
+		a.exec_c2r = (int (*)(cufftHandle, cufftComplex*, float*))dlsym(a.lib, "cufftExecC2R");
+		a.destroy = (int (*)(cufftHandle))dlsym(a.lib, "cufftDestroy");
+	});
+	return a;
+}
+constexpr int kR2C = 0x2a, kC2R = 0x2c;   // CUFFT_R2C, CUFFT_C2R
+// padded, optionally faded copy of the dry signal: mode 0 plain, 1 x (1 - i/n), 2 x (i/n)   (src/Recorder.cpp:267-292)
+__global__ void load_dry_kernel(const float* dry, uint32_t n_dry, float* dst, size_t n_fft, int mode) {
+	const float inv_n = fdiv(1.0f, (float)n_dry);
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fft; i += (size_t)gridDim.x * blockDim.x) {
+		float v = 0.0f;
+		if (i < n_dry) {
+			v = dry[i];
+			const float w = fmul((float)(uint32_t)i, inv_n);
+			if (mode == 1) v = fmul(v, fsub(1.0f, w)); else if (mode == 2) v = fmul(v, w);
+		}
+		dst[i] = v;
+	}
+}
+// response samples [first, len) shifted to start at 0, zero elsewhere
+__global__ void load_response_kernel(const float* r, uint32_t have, uint32_t first, uint32_t len, float* dst, size_t n_fft) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_fft; i += (size_t)gridDim.x * blockDim.x) {
+		const size_t j = i + first;
+		dst[i] = (j < len && j < have) ? r[j] : 0.0f;
+	}
+}
+__global__ void multiply_kernel(const float2* a, const float2* b, const float2* c, const float2* d, float2* out, size_t n, float scale) {
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+		float2 v = make_float2(a[i].x * b[i].x - a[i].y * b[i].y, a[i].x * b[i].y + a[i].y * b[i].x);
+		if (c) { v.x += c[i].x * d[i].x - c[i].y * d[i].y; v.y += c[i].x * d[i].y + c[i].y * d[i].x; }
+		out[i] = make_float2(v.x * scale, v.y * scale);
+	}
+}
+}  // namespace fftconv
+
+extern "C" int32_t ear_b200_convolve_fft(int32_t device, const float* response, uint32_t length, uint32_t first_sample,
+                                         uint32_t real_length, const float* response2, uint32_t length2, uint32_t first_sample2,
+                                         uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
+                                         uint32_t out_len, uint32_t* out_first, uint32_t* out_real) {
+	using namespace fftconv;
+	if (!response || !out || (n_dry && !dry)) return fail("convolve_fft: null argument");
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail("no CUDA device: ear_b200 has no CPU fallback"); }
+	if (device < 0 || device >= ndev) return fail("convolve_fft: device index out of range");
+	CUDA_TRY(cudaSetDevice(device));
+	const bool fade = response2 != nullptr;
+	const uint32_t first = fade ? std::min(first_sample, first_sample2) : first_sample;
+	const uint32_t len = fade ? std::max(real_length, real_length2) : real_length;
+	const uint32_t init_first = 3 * EAR_B200_SAMPLE_RATE - 1;
+	if (out_first) *out_first = init_first;
+	if (out_real) *out_real = 0;
+	if (out_len) std::memset(out, 0, (size_t)out_len * sizeof(float));
+	if (n_dry == 0 || len <= first) return 0;
+	const unsigned long long last = (unsigned long long)(n_dry - 1) + offset + (len - 1);
+	if (out_first) *out_first = std::min<uint32_t>(init_first, offset + first);
+	if (out_real) *out_real = (uint32_t)last;
+	if (last + 1 > out_len) return fail("convolve_fft: output buffer shorter than n_dry - 1 + offset + real_length");
+	Api& f = api();
+	if (!f.ok()) return fail("convolve_fft: libcufft could not be loaded");
+	const size_t span = (size_t)n_dry + (len - first);        // linear convolution length (+1)
+	size_t n_fft = 1;
+	while (n_fft < span) n_fft <<= 1;
+	if (n_fft > ((size_t)1 << 30)) return fail("convolve_fft: signal too long for one transform");
+	const size_t n_c = n_fft / 2 + 1;
+	DevBuf<float> d_in, d_dry, d_sig;
+	DevBuf<float2> d_fd, d_fr, d_fd2, d_fr2;
+	const uint32_t n1 = std::min(length, len), n2 = fade ? std::min(length2, len) : 0;
+	CUDA_TRY(d_in.alloc(std::max<size_t>(std::max(n1, n2), 1))); CUDA_TRY(d_dry.alloc(n_dry)); CUDA_TRY(d_sig.alloc(n_fft));
+	CUDA_TRY(d_fd.alloc(n_c)); CUDA_TRY(d_fr.alloc(n_c));
+	if (fade) { CUDA_TRY(d_fd2.alloc(n_c)); CUDA_TRY(d_fr2.alloc(n_c)); }
+	cufftHandle fwd = 0, inv = 0;
+	if (f.plan1d(&fwd, (int)n_fft, kR2C, 1) != 0) return fail("convolve_fft: cufftPlan1d failed");
+	if (f.plan1d(&inv, (int)n_fft, kC2R, 1) != 0) { f.destroy(fwd); return fail("convolve_fft: cufftPlan1d failed"); }
+	struct Plans { Api& f; cufftHandle a, b; ~Plans() { f.destroy(a); f.destroy(b); } } plans{f, fwd, inv};
+	CUDA_TRY(cudaMemcpy(d_dry, dry, (size_t)n_dry * 4, cudaMemcpyHostToDevice));
+	const int grid = 148 * 8;
+	auto transform = [&](int dry_mode, const float* resp, uint32_t have, float2* fd, float2* fr) -> int32_t {
+		load_dry_kernel<<<grid, 256>>>(d_dry, n_dry, d_sig, n_fft, dry_mode);
+		if (f.exec_r2c(fwd, d_sig, fd) != 0) return fail("convolve_fft: forward transform failed");
+		CUDA_TRY(cudaMemcpy(d_in, resp, (size_t)have * 4, cudaMemcpyHostToDevice));
+		load_response_kernel<<<grid, 256>>>(d_in, have, first, len, d_sig, n_fft);
+		if (f.exec_r2c(fwd, d_sig, fr) != 0) return fail("convolve_fft: forward transform failed");
+		return 0;
+	};
+	if (int32_t rc = transform(fade ? 1 : 0, response, n1, d_fd, d_fr)) return rc;
+	if (fade) { if (int32_t rc = transform(2, response2, n2, d_fd2, d_fr2)) return rc; }
+	multiply_kernel<<<grid, 256>>>(d_fd, d_fr, fade ? d_fd2.p : nullptr, fade ? d_fr2.p : nullptr, d_fd, n_c, 1.0f / (float)n_fft);
+	if (f.exec_c2r(inv, d_fd, d_sig) != 0) return fail("convolve_fft: inverse transform failed");
+	CUDA_TRY(cudaGetLastError());
+	// sample k of the linear convolution lands at out[offset + first + k]
+	CUDA_TRY(cudaMemcpy(out + offset + first, d_sig, (size_t)(span - 1) * 4, cudaMemcpyDeviceToHost));
+	return 0;
+}
+
 extern "C" int32_t ear_b200_scene_stats(ear_b200_scene* s, ear_b200_stats* out) {
 	if (!s || !out) return fail("scene_stats: null argument");
 	CUDA_TRY(cudaSetDevice(s->device));

@@ -271,6 +271,8 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 		std::vector<std::thread> pool;
 		const unsigned hw = (unsigned)std::max(1, 2 * n_gpus);   // two host threads per GPU keep its copy engines busy
 		std::atomic<int> next(0);
+		const char* conv_mode = std::getenv("EAR_CONVOLUTION");
+		const bool use_fft = conv_mode && std::string(conv_mode) == "fft";
 		std::string conv_error;
 		std::mutex conv_error_lock;
 		std::atomic<bool> conv_failed(false);
@@ -322,7 +324,9 @@ int run(const std::string& filename, float* calc_t60, float* t60_sabine, float* 
 					}
 					std::vector<float> out(alloc, 0.0f);
 					uint32_t of = 0, orl = 0;
-					if (ear_b200_convolve(job % n_gpus, tr->data(), tr->allocated(), tr->first_sample, tr->real_length,
+					// EAR_CONVOLUTION=fft: the frequency-domain form (the reference's USE_FFTW build); default: the direct
+					// form, bit-identical with the reference's default build
+					if ((use_fft ? ear_b200_convolve_fft : ear_b200_convolve)(job % n_gpus, tr->data(), tr->allocated(), tr->first_sample, tr->real_length,
 					                      next ? next->data() : nullptr, next ? next->allocated() : 0, next ? next->first_sample : 0,
 					                      next ? next->real_length : 0, n ? ptr : nullptr, n, off, out.data(), (uint32_t)out.size(), &of, &orl)) {
 						std::lock_guard<std::mutex> lock(conv_error_lock);

@@ -38,7 +38,10 @@ struct SceneDev {
 };
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
-constexpr int kStackEntries = 24;       // shared-memory entries per lane; deeper pushes go to SceneDev::spill
+#ifndef EARB_STACK_ENTRIES
+#define EARB_STACK_ENTRIES 24
+#endif
+constexpr int kStackEntries = EARB_STACK_ENTRIES;       // shared-memory entries per lane; deeper pushes go to SceneDev::spill
 constexpr int kStackSpill = 160;        // host emulation only: rows of its local overflow array
 constexpr int kLeafVote = 12;           // do a leaf step once this many lanes wait on a leaf
 constexpr float kKappa = 1.0f / 1024.0f;

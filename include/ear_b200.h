@@ -240,6 +240,17 @@ int32_t ear_b200_convolve(int32_t device, const float* response, uint32_t length
                           uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
                           uint32_t out_len, uint32_t* out_first, uint32_t* out_real);
 
+/* The same convolution in the frequency domain -- the reference's optional USE_FFTW build of RecorderTrack::Process
+ * (src/Recorder.cpp:145-243): zero-padded real FFTs (cuFFT), one complex multiply, one inverse transform.  For keyframed
+ * scenes the dry signal is faded out / in before the two transforms, which is the same linear map as the direct form's
+ * per-sample interpolation of the two responses.  Same arguments and bookkeeping as ear_b200_convolve; the samples agree
+ * with the direct form to float32 FFT accuracy (tests/test_convolve_gpu.py states the tolerance: 2e-5 of the peak), not bit
+ * for bit -- the CLI uses it only when EAR_CONVOLUTION=fft is set. */
+int32_t ear_b200_convolve_fft(int32_t device, const float* response, uint32_t length, uint32_t first_sample,
+                              uint32_t real_length, const float* response2, uint32_t length2, uint32_t first_sample2,
+                              uint32_t real_length2, const float* dry, uint32_t n_dry, uint32_t offset, float* out,
+                              uint32_t out_len, uint32_t* out_first, uint32_t* out_real);
+
 /* SURVEY.md section 8(f) rank 2 -- the post chain of Render() (src/EAR.cpp:209-228) on device-resident tracks, in
  * the two phases the reference runs it in (every track is compressed before the global maximum is known):
  *   post_power     Recorder::Power(exponent) in place on every track (FloatBuffer::Power, src/Recorder.cpp:101-106:

@@ -53,3 +53,25 @@ def test_matches_numpy_convolve_numerically():
     ref = np.convolve(dry.astype(np.float64), resp.data[:20000].astype(np.float64))   # [first, real_length) only
     n = ref.shape[0]
     assert np.abs(got.data[:n] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+FFT_TOL = 2e-5    # |fft - direct| <= FFT_TOL * peak of the direct result (float32 transforms of up to 2^21 points)
+
+
+@pytest.mark.parametrize("n_dry,offset,first,real,fade", [(443, 0, 1028, 30000, False), (2000, 44100, 4589, 60000, False),
+                                                           (1500, 88200, 2000, 50000, True), (705600, 0, 3000, 400000, False),
+                                                           (100000, 1000, 1500, 300000, True)])
+def test_fft_convolution_agrees_with_the_direct_form(n_dry, offset, first, real, fade):
+    """ear_b200_convolve_fft (the reference's USE_FFTW form of RecorderTrack::Process, src/Recorder.cpp:145-243) against the
+    bit-exact direct form on the same inputs, including BASELINE config 3's 705 600-sample dry signal and the keyframe
+    cross-fade (faded dry signals in the FFT form == interpolated responses in the direct form)."""
+    rng = np.random.default_rng(n_dry + first)
+    a = _track(rng, first, real)
+    b = _track(rng, max(0, first - 400), real - 7000, length=real - 2000) if fade else None
+    dry = (rng.normal(size=n_dry) * np.hanning(n_dry)).astype(np.float32)
+    direct = api.convolve(a, dry, offset, response2=b)
+    fft = api.convolve(a, dry, offset, response2=b, fft=True)
+    assert (fft.first_sample, fft.real_length) == (direct.first_sample, direct.real_length)
+    assert fft.data.shape == direct.data.shape
+    peak = np.abs(direct.data).max()
+    assert peak > 0 and np.abs(fft.data - direct.data).max() <= FFT_TOL * peak
