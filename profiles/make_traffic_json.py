@@ -23,7 +23,8 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "traffic_*.csv")))
     for (lid, name), m in launches.items():
         def val(k, scale=1.0):
             v, u = m[k]
-            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1.0, "usecond": 1e-3, "nsecond": 1e-6, "second": 1e3}.get(u, 1.0)
+            mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1.0, "ms": 1.0, "usecond": 1e-3, "us": 1e-3,
+                    "nsecond": 1e-6, "ns": 1e-6, "second": 1e3, "s": 1e3}.get(u, 1.0)
             return float(v) * mult * scale
         e = {"kernel": name.split("(")[0], "ncu_launch_id": lid,
              "dram_bytes_read": int(val("dram__bytes_read.sum")), "dram_bytes_write": int(val("dram__bytes_write.sum")),
@@ -40,6 +41,8 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "traffic_*.csv")))
             # two kernels answer occlusion queries at C5: keep both, report their sum as the traffic of the class
             out.setdefault(key, {"kernels": []})["kernels"].append(e)
             continue
+        if "<1," in name:
+            continue     # an (empty) BVH any-hit launch of the same template
         if best is None or e["dram_bytes_read"] > best["dram_bytes_read"]:
             best = e
     if best:
@@ -57,4 +60,4 @@ for key, e in out.items():
         e["source"] = e["kernels"][0]["source"]
 with open(os.path.join(ROOT, "profiles", "r2_traffic.json"), "w") as f:
     json.dump(out, f, indent=1)
-print(json.dumps(out, indent=1)[:3000])
+print(json.dumps({k: {kk: vv for kk, vv in v.items() if kk != "kernels"} for k, v in out.items()}, indent=1))

@@ -8,13 +8,16 @@
 mkdir -p gpurun_out
 M="dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__thread_inst_executed_per_inst_executed.ratio,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,lts__t_sector_hit_rate.pct,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active,lts__t_bytes.sum"
 cap() {   # key workload rays kernel-regex skip
-  timeout 400 ncu --metrics $M --cache-control none --clock-control none -k regex:$4 -s $5 -c 2 --csv --log-file gpurun_out/traffic_$1.csv \
+  timeout 500 ncu --metrics $M --cache-control none --clock-control none --kernel-name-base demangled -k "regex:$4" -s $5 -c $6 --csv --log-file gpurun_out/traffic_$1.csv \
     python bench.py --workload $2 --rays $3 --steps 1 --warmup 0 --no-e2e --no-cpu-baseline > gpurun_out/traffic_$1.log 2>&1
   echo "$1 rc=$?"
 }
-# closest-hit launches alternate with the (empty) BVH any-hit launches of the same kernel template: 2 x 100 -> iteration 100
-cap c4_n1 c4 1e8 wf_traverse_kernel 200
-cap c4_n2 c4 5e7 wf_traverse_kernel 200
-cap c4_n4 c4 2.5e7 wf_traverse_kernel 200
-cap c4_n8 c4 1.25e7 wf_traverse_kernel 60
-cap c5_n1 c5 1e7 "wf_vismap_kernel|wf_traverse_kernel" 60
+# key workload rays kernel(s) launches-to-skip launches-to-capture; the demangled name selects the closest-hit instance
+# <0, 0> (the any-hit instance <1, 0> of the same template runs every iteration too, with an empty list at C4)
+if [ "${1:-all}" = all ]; then
+cap c4_n1 c4 1e8 "wf_traverse_kernel<0" 100 1
+cap c4_n2 c4 5e7 "wf_traverse_kernel<0" 100 1
+cap c4_n4 c4 2.5e7 "wf_traverse_kernel<0" 100 1
+cap c4_n8 c4 1.25e7 "wf_traverse_kernel<0" 30 1
+fi
+cap c5_n1 c5 1e7 "wf_vismap_kernel|wf_traverse_kernel<1" 40 2
