@@ -39,7 +39,7 @@ struct SceneDev {
 
 constexpr int32_t kEmptyChildDev = 0x7fffffff;
 #ifndef EARB_STACK_ENTRIES
-#define EARB_STACK_ENTRIES 24
+#define EARB_STACK_ENTRIES 20   // 20 x 128 x 8 B = 20 KB per block: ten blocks fit an SM's shared memory
 #endif
 constexpr int kStackEntries = EARB_STACK_ENTRIES;       // shared-memory entries per lane; deeper pushes go to SceneDev::spill
 constexpr int kStackSpill = 160;        // host emulation only: rows of its local overflow array

@@ -66,8 +66,11 @@ constexpr int kMaxSlotBits = 28;   // a query word is slot | recorder << slot_bi
 // ---------------------------------------------------------------------------------------------------
 // K2 / K4: persistent traversal with dynamic fetch
 // ---------------------------------------------------------------------------------------------------
+// resident blocks per SM of the closest-hit kernel: 10 x 128 threads at 48 registers and 20 shared-memory stack entries.
+// Measured per 4e7 rays (profiles/r2_ab_closest.txt): 6 blocks (72 regs) 757 ms, 8 (62) 685, 9 (56) 640, 10 (48, 20-entry
+// stack) 629, 12 (40 regs, spills, 16-entry stack) 718 -- the kernel is latency-bound, warps in flight pay until spills start
 #ifndef EARB_TRAV_MIN_BLOCKS
-#define EARB_TRAV_MIN_BLOCKS 8
+#define EARB_TRAV_MIN_BLOCKS 10
 #endif
 template <bool ANY_HIT, bool EXACT>
 __global__ void __launch_bounds__(kBlock, ANY_HIT || EXACT ? 6 : EARB_TRAV_MIN_BLOCKS) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {

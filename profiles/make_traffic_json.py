@@ -26,7 +26,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "traffic_*.csv")))
             mult = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "msecond": 1.0, "ms": 1.0, "usecond": 1e-3, "us": 1e-3,
                     "nsecond": 1e-6, "ns": 1e-6, "second": 1e3, "s": 1e3}.get(u, 1.0)
             return float(v) * mult * scale
-        e = {"kernel": name.split("(")[0], "ncu_launch_id": lid,
+        e = {"kernel": name.split("(earb::")[0].split("(SceneDev")[0], "ncu_launch_id": lid,
              "dram_bytes_read": int(val("dram__bytes_read.sum")), "dram_bytes_write": int(val("dram__bytes_write.sum")),
              "ncu_duration_ms": val("gpu__time_duration.sum"),
              "lanes_per_instruction": float(m["smsp__thread_inst_executed_per_inst_executed.ratio"][0]),
@@ -41,7 +41,7 @@ for path in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", "traffic_*.csv")))
             # two kernels answer occlusion queries at C5: keep both, report their sum as the traffic of the class
             out.setdefault(key, {"kernels": []})["kernels"].append(e)
             continue
-        if "<1," in name:
+        if "<1," in name or "<(bool)1" in name:
             continue     # an (empty) BVH any-hit launch of the same template
         if best is None or e["dram_bytes_read"] > best["dram_bytes_read"]:
             best = e

@@ -15,9 +15,9 @@ cap() {   # key workload rays kernel-regex skip
 # key workload rays kernel(s) launches-to-skip launches-to-capture; the demangled name selects the closest-hit instance
 # <0, 0> (the any-hit instance <1, 0> of the same template runs every iteration too, with an empty list at C4)
 if [ "${1:-all}" = all ]; then
-cap c4_n1 c4 1e8 "wf_traverse_kernel<0" 100 1
-cap c4_n2 c4 5e7 "wf_traverse_kernel<0" 100 1
-cap c4_n4 c4 2.5e7 "wf_traverse_kernel<0" 100 1
-cap c4_n8 c4 1.25e7 "wf_traverse_kernel<0" 30 1
+cap c4_n1 c4 1e8 "wf_traverse_kernel<.bool.0" 100 1
+cap c4_n2 c4 5e7 "wf_traverse_kernel<.bool.0" 100 1
+cap c4_n4 c4 2.5e7 "wf_traverse_kernel<.bool.0" 100 1
+cap c4_n8 c4 1.25e7 "wf_traverse_kernel<.bool.0" 30 1
 fi
-cap c5_n1 c5 1e7 "wf_vismap_kernel|wf_traverse_kernel<1" 40 2
+cap c5_n1 c5 1e7 "wf_vismap_kernel|wf_traverse_kernel<.bool.1" 40 2
