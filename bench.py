@@ -296,7 +296,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "includes": "scene upload + BVH build + image broadcast + visibility maps + trace + reduce + finalise + track download",
                     "steps": e2e_steps,
-                    "ms_per_step": sum(e2e_ms) / max(1, len(e2e_ms)), "scene_create_ms": sum(e2e_create_ms) / max(1, len(e2e_create_ms))},
+                    "ms_per_step": sum(e2e_ms) / max(1, len(e2e_ms)), "scene_create_ms": sum(e2e_create_ms) / max(1, len(e2e_create_ms)),
+                    "step_ms_rank0": [round(x, 1) for x in e2e_ms], "scene_create_ms_rank0": [round(x, 1) for x in e2e_create_ms]},
             "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
             "launches_per_step": {k: v / args.steps for k, v in st["launches"].items()},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -24,6 +24,8 @@
 #include <thread>
 #include <vector>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "../../include/ear_b200.h"
 #include "bvh_build.h"
 #include "traverse.cuh"
@@ -337,6 +339,7 @@ struct ear_b200_scene {
 	ear_b200_stats stats{};
 	// recorder visibility maps (vismap.cuh), cached per recorder position
 	struct VisMapHost { float x[3]; int res; int* d_offsets; int* d_items; size_t n_items; bool sorted; };
+	int vismap_build = 0;           // 0: sort-based build (no returning atomics, lists nearest-first); 1: count + atomic fill (EAR_B200_VISMAP_BUILD=atomic)
 	int vismap_sort = -1;           // -1: order the texel lists by distance once most queries turn out blocked; 0 never; 1 at build time (EAR_B200_VISMAP_SORT)
 	std::vector<VisMapHost> vismaps;
 	int vismap_res = -1;            // -1: choose from the triangle count; 0: disabled (EAR_B200_VISMAP_RES)
@@ -435,6 +438,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
+	if (const char* vb = std::getenv("EAR_B200_VISMAP_BUILD")) s->vismap_build = std::string(vb) == "atomic" ? 1 : 0;
 	if (const char* vs = std::getenv("EAR_B200_VISMAP_SORT")) s->vismap_sort = std::max(-1, std::min(1, std::atoi(vs)));
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
 	if (const char* sm = std::getenv("EAR_B200_SPLAT")) s->splat_mode = std::string(sm) == "window" ? 1 : 0;
@@ -887,6 +891,8 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 }
 
 // Builds (or finds) the visibility map of one recorder position; returns its index or -1 when maps are disabled.
+static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res, cudaStream_t stream, int* index);
+
 static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stream, int* index) {
 	*index = -1;
 	int res = s->vismap_res;
@@ -898,6 +904,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	for (size_t i = 0; i < s->vismaps.size(); ++i)
 		if (s->vismaps[i].res == res && std::memcmp(s->vismaps[i].x, x, 12) == 0) { *index = (int)i; return 0; }
 	if (s->vismaps.size() >= 64 || s->vis_budget_spent) return 0;   // the remaining recorder positions use the BVH
+	if (s->vismap_build == 0) return build_vismap_sorted(s, x, res, stream, index);
 	ear_b200_scene::VisMapHost m{};
 	std::memcpy(m.x, x, 12); m.res = res;
 	const int n_tex = 6 * res * res;
@@ -936,7 +943,7 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	lap("count pass");
 	vis_scan_sums_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, n_tex, per, cap);
 	vis_scan_top_kernel<<<1, kVisScanBlocks, 0, stream>>>(s->d_vis_sums, m.d_offsets, n_tex);
-	vis_scan_offsets_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, m.d_offsets, n_tex, per, cap);
+	vis_scan_offsets_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, m.d_offsets, n_tex, per, cap, cap);
 	int total = 0;
 	CUDA_TRY(cudaMemcpyAsync(&total, m.d_offsets + n_tex, sizeof(int), cudaMemcpyDeviceToHost, stream));
 	CUDA_TRY(cudaStreamSynchronize(stream));
@@ -971,6 +978,92 @@ static int32_t get_vismap(ear_b200_scene* s, const float x[3], cudaStream_t stre
 	CUDA_TRY(cudaGetLastError());
 	CUDA_TRY(cudaStreamSynchronize(stream));
 	lap("fill pass");
+	s->vismaps.push_back(m);
+	guard.m = nullptr;
+	*index = (int)s->vismaps.size() - 1;
+	return 0;
+}
+
+// Sort-based build of one visibility map (vis_emit_kernel + one radix sort): no returning atomics, lists nearest-first.
+static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res, cudaStream_t stream, int* index) {
+	ear_b200_scene::VisMapHost m{};
+	std::memcpy(m.x, x, 12); m.res = res;
+	const int n_tex = 6 * res * res;
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!dbg) return;
+		cudaDeviceSynchronize();
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[ear_b200] vismap (sort build): %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+		t_prev = now;
+	};
+	if ((size_t)n_tex > s->vis_scratch_cap) {
+		dev_free(s->d_vis_counts); dev_free(s->d_vis_sums);
+		s->d_vis_counts = nullptr; s->d_vis_sums = nullptr; s->vis_scratch_cap = 0;
+		CUDA_TRY(dev_alloc(&s->d_vis_counts, (size_t)n_tex * sizeof(int)));
+		CUDA_TRY(dev_alloc(&s->d_vis_sums, kVisScanBlocks * sizeof(long long)));
+		s->vis_scratch_cap = (size_t)n_tex;
+	}
+	int* d_counts = s->d_vis_counts;
+	CUDA_TRY(dev_alloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
+	struct MapGuard {
+		ear_b200_scene::VisMapHost* m;
+		~MapGuard() { if (m) { dev_free(m->d_offsets); dev_free(m->d_items); } }
+	} guard{&m};
+	int id_bits = 7;
+	while ((1LL << id_bits) < 6LL * s->n_tris) ++id_bits;
+	const size_t n_ids = (size_t)1 << id_bits;
+	const unsigned grid = (unsigned)(n_ids / 128);
+	DevBuf<int> d_pair_count, d_pair_base, d_pair_sums;
+	CUDA_TRY(d_pair_count.alloc(n_ids)); CUDA_TRY(d_pair_base.alloc(n_ids + 1));
+	CUDA_TRY(d_pair_sums.alloc(n_ids / (dbvh::kScanBlock * dbvh::kScanPer) + 2));
+	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
+	const double reach = 2.0 * (double)s->diagonal + 1.0;
+	int texel_bits = 1;
+	while ((1 << texel_bits) < n_tex) ++texel_bits;
+	const int dist_bits = 32 - texel_bits;
+	const float dist_scale = (float)((double)(1u << dist_bits) / reach);
+	const int cap = s->dev.vis_cap;
+	const int per = (n_tex + kVisScanBlocks - 1) / kVisScanBlocks;
+	vis_emit_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_counts, d_pair_count, nullptr, nullptr, nullptr, dist_bits, dist_scale);
+	lap("count pass");
+	vis_scan_sums_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, n_tex, per, -1);
+	vis_scan_top_kernel<<<1, kVisScanBlocks, 0, stream>>>(s->d_vis_sums, m.d_offsets, n_tex);
+	vis_scan_offsets_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, m.d_offsets, n_tex, per, -1, cap);
+	dbvh::exclusive_scan(d_pair_count, (int)n_ids, d_pair_base, d_pair_sums, stream);
+	int total = 0;
+	CUDA_TRY(cudaMemcpyAsync(&total, m.d_offsets + n_tex, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	lap("scans");
+	if (s->vis_budget == 0) {
+		size_t free_b = 0, total_b = 0;
+		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+		s->vis_budget = std::max<size_t>(free_b / 4, 1);
+		if (const char* vb = std::getenv("EAR_B200_VISMAP_BUDGET")) s->vis_budget = std::max<size_t>((size_t)std::atof(vb), 1);
+	}
+	const size_t map_bytes = ((size_t)n_tex + 1) * sizeof(int) + (total < 0 ? 0 : (size_t)total * sizeof(int));
+	if (total < 0 || s->vis_bytes + map_bytes > s->vis_budget) { s->vis_budget_spent = true; return 0; }
+	s->vis_bytes += map_bytes;
+	m.n_items = (size_t)total;
+	CUDA_TRY(dev_alloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
+	if (total > 0) {
+		DevBuf<uint32_t> d_keys_a, d_keys_b;
+		DevBuf<int> d_vals_a;
+		DevBuf<unsigned char> d_tmp;
+		CUDA_TRY(d_keys_a.alloc((size_t)total)); CUDA_TRY(d_keys_b.alloc((size_t)total)); CUDA_TRY(d_vals_a.alloc((size_t)total));
+		vis_emit_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_counts, d_pair_count, d_pair_base, d_keys_a, d_vals_a, dist_bits, dist_scale);
+		CUDA_TRY(cudaGetLastError());
+		lap("emit pass");
+		size_t tmp_bytes = 0;
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys_a.p, d_keys_b.p, d_vals_a.p, m.d_items, total, 0, 32, stream));
+		CUDA_TRY(d_tmp.alloc(tmp_bytes));
+		CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys_a.p, d_keys_b.p, d_vals_a.p, m.d_items, total, 0, 32, stream));
+		CUDA_TRY(cudaStreamSynchronize(stream));
+		lap("radix sort");
+	}
+	if (dbg) std::fprintf(stderr, "[ear_b200] vismap (sort build): %d entries, %d distance bits\n", total, dist_bits);
+	m.sorted = true;
 	s->vismaps.push_back(m);
 	guard.m = nullptr;
 	*index = (int)s->vismaps.size() - 1;
@@ -1086,6 +1179,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	const bool windowed = s->splat_mode == 1 && n_pairs <= kPrivMaxPairs && p.n_rec > 0;
 	if (windowed) CUDA_TRY(cudaFuncSetAttribute(wf_splat_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPrivWindow * sizeof(float))));
 	// upper bound on iterations: every slot hosts ceil(work/slots) rays of at most max_bounces iterations each
+	const auto t_loop = std::chrono::steady_clock::now();
 	const long long max_iter = ((p.total_work + slots - 1) / slots + 1) * (long long)(p.max_bounces + 2) + 4 + s->check_every;
 	bool finished = false;
 	for (long long it = 0; it < max_iter;) {
@@ -1136,6 +1230,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 			if (int32_t rc = sort_vismaps(s, stream)) return rc;
 	}
 	if (!finished) return fail("render: the wavefront loop hit its iteration bound with rays left (internal error)");
+	if (dbg) std::fprintf(stderr, "[ear_b200] wavefront loop: %.2f ms after set-up\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count());
 	return 0;
 }
 
@@ -1176,10 +1271,19 @@ extern "C" int32_t ear_b200_trace_device(ear_b200_scene* s, const ear_b200_conte
 	if (!s) return fail("trace_device: null scene");
 	if (!d_hist || !d_range || !d_counters || n_bins <= 0) return fail("trace_device: null device buffer");
 	CUDA_TRY(cudaSetDevice(s->device));
+	const bool dbg = std::getenv("EAR_B200_DEBUG") != nullptr;
+	const auto t0 = std::chrono::steady_clock::now();
 	RenderParams p{};
 	if (int32_t rc = upload_params(s, ctx, n_ctx, rec, n_rec, opt, (cudaStream_t)stream, p)) return rc;
 	p.n_bins = n_bins; p.hist = d_hist; p.range = d_range; p.counters = (unsigned long long*)d_counters;
-	return launch_trace(s, p, (cudaStream_t)stream);
+	const auto t1 = std::chrono::steady_clock::now();
+	const int32_t rc = launch_trace(s, p, (cudaStream_t)stream);
+	if (dbg) {
+		cudaStreamSynchronize((cudaStream_t)stream);
+		std::fprintf(stderr, "[ear_b200] trace_device: upload %.2f ms, trace (pool, maps, wavefront loop) %.2f ms\n",
+		             std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+	}
+	return rc;
 }
 
 extern "C" int32_t ear_b200_finalise_device(ear_b200_scene* s, const ear_b200_context* ctx, int32_t n_ctx,

@@ -81,11 +81,87 @@ __global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, 
 	}
 }
 
+// Sort-based build (default).  The fill pass above takes one RETURNING atomic per (triangle, texel) entry -- 132 M of
+// them for the 1M-triangle hall, 34 ms -- and leaves every list in arbitrary order.  Instead: pass 0 counts list lengths
+// (fire-and-forget REDs) and the number of entries each footprint emits; one scan gives every footprint its place in a flat
+// array; pass 1 writes (key, triangle) pairs there without any atomic, key = texel << d | distance of the triangle from the
+// recorder in d bits; ONE radix sort (cub::DeviceRadixSort) then yields all lists at once, each ordered nearest-first --
+// which is the order the lookups want (a blocked query stops at the first triangle its segment crosses).
+template <int PASS>
+__global__ void __launch_bounds__(128) vis_emit_kernel(SceneDev sc, double x0, double x1, double x2, int res, double reach, double maxabs,
+                                                       int id_bits, int* counts, int* pair_count, const int* pair_base,
+                                                       uint32_t* keys, int* vals, int dist_bits, float dist_scale) {
+	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	const long long id = (long long)(__brevll(tid) >> (64 - id_bits));
+	const int lane = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const double X[3] = {x0, x1, x2};
+	int i0 = 0, i1 = -1, j0 = 0, j1 = -1, t = 0, face = 0;
+	float edge[9] = {0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f, 0.0f, 0.0f, 1.0f};
+	bool valid = id < 6LL * sc.n_tris;
+	uint32_t dq = 0;
+	if (valid) {
+		bool has_edges;
+		t = (int)(id / 6); face = (int)(id % 6);
+		valid = vis_footprint(sc, t, X, res, face, reach, maxabs, i0, i1, j0, j1, edge, has_edges);
+		if (!has_edges) { for (int k = 0; k < 3; ++k) { edge[3 * k] = 0.0f; edge[3 * k + 1] = 0.0f; edge[3 * k + 2] = 1.0f; } }
+		if (PASS == 1 && valid) {
+			const float4 r0 = __ldg(sc.tris + 4 * (size_t)t), r1 = __ldg(sc.tris + 4 * (size_t)t + 1), r2 = __ldg(sc.tris + 4 * (size_t)t + 2);
+			const float cx = r0.x + (r1.x + r2.x) * (1.0f / 3.0f) - (float)x0, cy = r0.y + (r1.y + r2.y) * (1.0f / 3.0f) - (float)x1,
+			            cz = r0.z + (r1.z + r2.z) * (1.0f / 3.0f) - (float)x2;
+			dq = (uint32_t)min((float)((1u << dist_bits) - 1u), sqrtf(cx * cx + cy * cy + cz * cz) * dist_scale);
+		}
+	}
+	const int w = valid ? i1 - i0 + 1 : 0;
+	const int area = valid ? w * (j1 - j0 + 1) : 0;
+	const int base = PASS == 1 ? pair_base[tid] : 0;
+	int mine = 0;
+	constexpr int kOwn = 4;
+	if (area > 0 && area <= kOwn)
+		for (int k = 0; k < area; ++k) {
+			const int i = i0 + k % w, j = j0 + k / w;
+			if (vis_covers(edge, res, i, j)) {
+				const int texel = (face * res + j) * res + i;
+				if (PASS == 0) atomicAdd(counts + texel, 1);
+				else { keys[base + mine] = ((uint32_t)texel << dist_bits) | dq; vals[base + mine] = t; }
+				++mine;
+			}
+		}
+	unsigned big = __ballot_sync(0xffffffffu, area > kOwn);
+	while (big) {
+		const int src = __ffs(big) - 1;
+		big &= big - 1;
+		const int b_i0 = __shfl_sync(0xffffffffu, i0, src), b_j0 = __shfl_sync(0xffffffffu, j0, src), b_w = __shfl_sync(0xffffffffu, w, src);
+		const int b_area = __shfl_sync(0xffffffffu, area, src), b_t = __shfl_sync(0xffffffffu, t, src), b_face = __shfl_sync(0xffffffffu, face, src);
+		const int b_base = __shfl_sync(0xffffffffu, base, src);
+		const uint32_t b_dq = __shfl_sync(0xffffffffu, dq, src);
+		float e[9];
+#pragma unroll
+		for (int k = 0; k < 9; ++k) e[k] = __shfl_sync(0xffffffffu, edge[k], src);
+		int run = 0;
+		for (int k0 = 0; k0 < b_area; k0 += 32) {   // warp-uniform trip count: every lane votes
+			const int k = k0 + lane;
+			const int i = b_i0 + k % b_w, j = b_j0 + k / b_w;
+			const bool covered = k < b_area && vis_covers(e, res, i, j);
+			const unsigned m = __ballot_sync(0xffffffffu, covered);
+			if (covered) {
+				const int texel = (b_face * res + j) * res + i;
+				if (PASS == 0) atomicAdd(counts + texel, 1);
+				else { const int at = b_base + run + __popc(m & lt_mask); keys[at] = ((uint32_t)texel << dist_bits) | b_dq; vals[at] = b_t; }
+			}
+			run += __popc(m);
+		}
+		if (lane == src) mine = run;
+	}
+	if (PASS == 0) pair_count[tid] = mine;
+}
+
 // Exclusive scan of the list lengths in three launches (block sums, scan of the sums, offsets).  Lengths above
 // `cap` count as zero and mark their offset with kVisOverlong.  out[n] = total (negative on overflow).
 constexpr int kVisScanBlocks = 1024;
 
-__device__ __forceinline__ int vis_len(int v, int cap) { return v > cap ? 0 : v; }
+// cap < 0: every list is stored (the sort-based build keeps the long ones too, flagged; they are never looked up)
+__device__ __forceinline__ int vis_len(int v, int cap) { return (cap >= 0 && v > cap) ? 0 : v; }
 
 __global__ void __launch_bounds__(1024) vis_scan_sums_kernel(const int* in, long long* sums, int n, int per, int cap) {
 	__shared__ long long part[32];
@@ -115,7 +191,7 @@ __global__ void __launch_bounds__(1024) vis_scan_top_kernel(long long* sums, int
 	sums[threadIdx.x] = part[threadIdx.x];
 }
 
-__global__ void __launch_bounds__(1024) vis_scan_offsets_kernel(const int* in, const long long* sums, int* out, int n, int per, int cap) {
+__global__ void __launch_bounds__(1024) vis_scan_offsets_kernel(const int* in, const long long* sums, int* out, int n, int per, int cap, int flag_cap) {
 	__shared__ int warp_tot[32];
 	__shared__ int tile_tot;
 	const int beg = min(n, (int)blockIdx.x * per), end = min(n, beg + per);
@@ -136,7 +212,7 @@ __global__ void __launch_bounds__(1024) vis_scan_offsets_kernel(const int* in, c
 			if (lane == 31) tile_tot = winc;
 		}
 		__syncthreads();
-		if (i < end) out[i] = (int)(run + warp_tot[wid] + inc - v) | (raw > cap ? kVisOverlong : 0);
+		if (i < end) out[i] = (int)(run + warp_tot[wid] + inc - v) | (raw > flag_cap ? kVisOverlong : 0);
 		run += tile_tot;
 		__syncthreads();
 	}

@@ -72,8 +72,11 @@ constexpr int kMaxSlotBits = 28;   // a query word is slot | recorder << slot_bi
 #ifndef EARB_TRAV_MIN_BLOCKS
 #define EARB_TRAV_MIN_BLOCKS 10
 #endif
+#ifndef EARB_ANYHIT_MIN_BLOCKS
+#define EARB_ANYHIT_MIN_BLOCKS 9   // measured at C5 (profiles/r2_ab_closest.txt): 6 blocks 814 ms, 8 758, 9 706, 10 729
+#endif
 template <bool ANY_HIT, bool EXACT>
-__global__ void __launch_bounds__(kBlock, ANY_HIT || EXACT ? 6 : EARB_TRAV_MIN_BLOCKS) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {
+__global__ void __launch_bounds__(kBlock, EXACT ? 6 : (ANY_HIT ? EARB_ANYHIT_MIN_BLOCKS : EARB_TRAV_MIN_BLOCKS)) wf_traverse_kernel(SceneDev sc, WfPool pool, RenderParams p) {
 	extern __shared__ int2 stack_smem[];
 	const int lane = threadIdx.x & 31;
 	const unsigned lt_mask = (1u << lane) - 1u;

@@ -95,6 +95,16 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
         n_bins = scene.default_bins(opt)
     tpr = api.tracks_per_recorder(rec_c)          # device layout: [context][recorder][tpr][bins]
     n_tracks = n_ctx * n_rec * tpr
+    import os
+    import sys
+    import time
+    dbg = bool(os.environ.get("EAR_B200_DEBUG"))
+    laps = [("start", time.perf_counter())]
+
+    def lap(what):
+        if dbg:
+            torch.cuda.synchronize(dev)
+            laps.append((what, time.perf_counter()))
     with torch.cuda.device(dev):
         hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
         rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
@@ -104,6 +114,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
         sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         api._check(lib, lib.ear_b200_trace_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, C.byref(opt), n_bins,
                                                   hist.data_ptr(), rng.data_ptr(), counters.data_ptr(), sp))
+        lap("buffers + trace")
         if world > 1:
             first = rng[:, 0].contiguous()
             real = rng[:, 1].contiguous()
@@ -113,6 +124,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
                 return None
             rng[:, 0] = first
             rng[:, 1] = real
+        lap("reduce")
         api._check(lib, lib.ear_b200_finalise_device(scene.handle, ctx_c, n_ctx, rec_c, n_rec, n_bins,
                                                      hist.data_ptr(), rng.data_ptr(), sp))
         maximum, t60 = 0.0, None
@@ -132,6 +144,7 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
         # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
         longest = min(n_bins, int(h_rng[:, 1].max()) + 1) if n_tracks else 0
         h_hist = hist[:, :longest].cpu().numpy()
+    lap("finalise + download")
     tracks = []
     for ci in range(n_ctx):
         per_rec = []
@@ -145,6 +158,9 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
                 pair.append(api.Track(data, int(h_rng[t, 0]), real_len))
             per_rec.append(pair)
         tracks.append(per_rec)
+    lap("track objects")
+    if dbg:
+        print("[ear_b200.sharding] render_sharded: " + ", ".join(f"{w} {1e3 * (t - laps[i][1]):.1f} ms" for i, (w, t) in enumerate(laps[1:])), file=sys.stderr)
     res = api.RenderResult(tracks, int(c[0]), int(c[1]), int(c[2]), int(c[3]), int(c[4]), int(c[5]), 0.0)
     res.maximum = maximum
     res.t60 = t60
