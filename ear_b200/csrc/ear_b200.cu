@@ -1026,6 +1026,7 @@ static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res,
 	const float dist_scale = (float)((double)(1u << dist_bits) / reach);
 	const int cap = s->dev.vis_cap;
 	const int per = (n_tex + kVisScanBlocks - 1) / kVisScanBlocks;
+	lap("alloc + clear");
 	vis_emit_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_counts, d_pair_count, nullptr, nullptr, nullptr, dist_bits, dist_scale);
 	lap("count pass");
 	vis_scan_sums_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, n_tex, per, -1);
