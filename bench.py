@@ -1,22 +1,26 @@
 #!/usr/bin/env python
 """bench.py -- ray-bounce segments/sec of the Scene::Render replacement on B200.
 
-Workload (BASELINE.json configs[3], SURVEY.md section 8d "C4"): synthetic 1M-triangle hall
-(60 x 40 x 20 m, displaced wall tessellation + 2000 box obstacles, 4 materials), 8 frequency bands
-= 8 contexts, 1e8 rays in total (1.25e7 per band), max 50 bounces, one mono recorder, point source.
-A "step" is one full render of that ray budget.  Total work is fixed as N grows (strong scaling):
-rank g traces ray ids [g*R/N, (g+1)*R/N) of every context into its own partial histogram, then ONE
-NCCL reduce (sum) of the histograms (+ min/max of the track ranges) to rank 0, which finalises.
+Workloads:
+  c4 (default, the headline; BASELINE.json configs[3]): synthetic 1M-triangle hall (60 x 40 x 20 m, displaced wall
+     tessellation + 2000 box obstacles, 4 materials), 8 frequency bands = 8 contexts, 1e8 rays in total (1.25e7 per
+     band), max 50 bounces, one mono recorder, point source.
+  c5 (--workload c5; configs[4]): 10M-triangle complex of 8 coupled halls, 3 bands, 1e9 rays, 64 mono recorders.
+A "step" is one full render of that ray budget.  Total work is fixed as N grows (strong scaling): rank g traces ray ids
+[g*R/N, (g+1)*R/N) of every context into its own partial histogram, then ONE NCCL reduce (sum) of the histograms
+(+ min/max of the track ranges) to rank 0, which finalises.  No other collective is on the data path.
 
-  value : segments / second, whole job, scene + contexts already resident in HBM
+  value : segments / second, whole job, scene + contexts already resident in HBM (ear_b200_trace_device +
+          ear_b200_finalise_device on torch's current stream, CUDA events, max over ranks)
   e2e   : same metric through the public API with host buffers, every step: sharding.create_replicated_scene
-          (triangle upload + BVH build on rank 0, scene image broadcast) + sharding.render_sharded (context upload,
-          visibility maps, trace, one reduce, finalise, track download); at N=1 that is ear_b200_scene_create +
-          ear_b200_render
-  roofline : closest-hit traversal kernel; traffic from the committed ncu capture (profiles/r1_traffic.json)
-  --impl reference : the reference's own CPU render (oracle/_ref/ref_harness, built from the
-          unmodified sources) on this host's cores, one 50-ray context per process
-          (50 is the reference's minimum: DrawProgressBar divides by samples/50).
+          (triangle upload + device BVH build on every rank) + sharding.render_sharded (context upload, visibility
+          maps, trace, one reduce, finalise, track download); at N=1 that is ear_b200_scene_create + ear_b200_render
+  roofline : c4 -- the closest-hit traversal kernel; c5 -- the occlusion-query kernels (visibility-map lookups + BVH
+          any-hit).  Duration live from the library's per-launch CUDA events; traffic and issue statistics from the
+          committed ncu capture of the same configuration (profiles/r2_traffic.json, scripts/capture_traffic.sh)
+  --impl reference : the reference's own CPU render (oracle/_ref/ref_harness, built from the unmodified sources) on
+          this host's cores, one 50-ray context per process, time-boxed (50 is the reference's minimum:
+          DrawProgressBar divides by samples/50).
 """
 from __future__ import annotations
 
@@ -147,6 +151,10 @@ def run_ours(args):
     rays_per_ctx = ctxs[0].num_samples
     lo, hi = shard_bounds(rays_per_ctx, rank, world)
     opt = api.make_options(max_bounces=MAX_BOUNCES, seed=1234, first_ray=lo, ray_count=hi - lo, finalise=False)
+    opt_warm = opt
+    if args.warmup_rays is not None:   # C5 at full size: a warm-up step of 1e9 rays costs as much as the timed one
+        wlo, whi = shard_bounds(max(1, int(float(args.warmup_rays)) // n_ctx), rank, world)
+        opt_warm = api.make_options(max_bounces=MAX_BOUNCES, seed=1234, first_ray=wlo, ray_count=whi - wlo, finalise=False)
     n_bins = scene.default_bins(opt)
     n_tracks = n_ctx * n_rec * api.tracks_per_recorder(rec_c)
     hist = torch.zeros((n_tracks, n_bins), dtype=torch.float32, device=dev)
@@ -158,7 +166,7 @@ def run_ours(args):
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
 
-    def step():
+    def step(opt=opt):
         flush.zero_()
         hist.zero_()
         counters.zero_()
@@ -181,7 +189,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        step()
+        step(opt_warm)
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -207,6 +215,8 @@ def run_ours(args):
     total_ms = float(ms.item())
     segments, occl, bins, dropped = (int(x) for x in tot.tolist())
     value = segments / (total_ms * 1e-3)
+    if rank == 0 and os.environ.get("EAR_BENCH_VERBOSE"):
+        print(f"[bench] device-timed: {value:.4e} segments/s, {total_ms / args.steps:.1f} ms/step, kernels {st['ms']}", file=sys.stderr)
 
     # ---- e2e: host buffers through the public C ABI, every step ----
     e2e_ms = []
@@ -214,7 +224,7 @@ def run_ours(args):
     h2d = verts.nbytes + tri_mat.nbytes + table.nbytes + C.sizeof(ctx_c) + C.sizeof(rec_c)
     d2h = 0
     e2e_segments = 0
-    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps, 5))
+    e2e_steps = 0 if args.no_e2e else max(1, min(args.steps if args.e2e_steps is None else args.e2e_steps, 5))
     from ear_b200.sharding import create_replicated_scene, render_sharded
     for _ in range(e2e_steps):
         barrier()
@@ -287,7 +297,7 @@ def run_ours(args):
             "metric": "ray-bounce segments/sec", "value": value, "unit": "segments/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
+            "config": {"workload": WORKLOAD, **({"warmup_rays": int(float(args.warmup_rays))} if args.warmup_rays is not None else {}), "triangles": N_TRIS, "bands": N_BANDS, "rays": TOTAL_RAYS,
                        "max_bounces": MAX_BOUNCES, "recorders": N_RECORDERS, "bins_per_track": n_bins,
                        "sharding": f"ray ranges over {world} GPU(s), one NCCL reduce",
                        "l2": "flushed by a 256 MiB memset before every step"},
@@ -407,6 +417,8 @@ def main():
     ap.add_argument("--rays", default=None, help="override the workload's ray budget (the line then says REDUCED)")
     ap.add_argument("--tris", default=None, help="override the workload's triangle count (the line then says REDUCED)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--warmup-rays", default=None, help="ray budget of the untimed warm-up steps (default: the workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=None, help="steps of the end-to-end leg (default: min(steps, 5))")
     ap.add_argument("--no-e2e", action="store_true", help="tuning runs only: skip the host-buffer end-to-end leg")
     args = ap.parse_args()
     select_workload(args.workload, args.rays, args.tris)
