@@ -226,21 +226,26 @@ def run_ours(args):
     e2e_segments = 0
     e2e_steps = 0 if args.no_e2e else max(1, min(args.steps if args.e2e_steps is None else args.e2e_steps, 5))
     from ear_b200.sharding import create_replicated_scene, render_sharded
-    for _ in range(e2e_steps):
+    e2e_warm = 1 if (e2e_steps and args.warmup > 0 and args.warmup_rays is None) else 0   # one untimed pass: page-locked buffers, allocator caches
+    for it in range(e2e_warm + e2e_steps):
+        timed = it >= e2e_warm
         barrier()
         w0 = time.perf_counter()
         # the public multi-GPU path: one BVH build (rank 0), image broadcast over NVLink, sharded trace, one reduce
         s2 = create_replicated_scene(verts, tri_mat, table, device=local)
         torch.cuda.synchronize()
         wc = time.perf_counter()
-        e2e_create_ms.append((wc - w0) * 1e3)
         res = render_sharded(s2, ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234)
         torch.cuda.synchronize()
         w1 = time.perf_counter()
         s2.close()
-        if res is not None:
-            d2h = sum((t.real_length + 1) * 4 for c in res.tracks for r in c for t in r)
+        if res is not None and timed:
+            d2h = sum(t.data.nbytes for c in res.tracks for r in c for t in r)   # whole track buffers come down
             e2e_segments += res.segments
+        res = None            # hands the page-locked track block back before the next step asks for one
+        if not timed:
+            continue
+        e2e_create_ms.append((wc - w0) * 1e3)
         e2e_ms.append((w1 - w0) * 1e3)
         if os.environ.get("EAR_BENCH_VERBOSE"):
             print(f"[bench] rank {rank} e2e step: create {e2e_create_ms[-1]:.1f} ms, render {(w1 - wc) * 1e3:.1f} ms", file=sys.stderr)
@@ -305,7 +310,7 @@ def run_ours(args):
             "bin_updates_per_step": bins // args.steps, "dropped_updates": dropped,
             "e2e": {"value": e2e_value, "unit": "segments/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "includes": "scene upload + BVH build + image broadcast + visibility maps + trace + reduce + finalise + track download",
-                    "steps": e2e_steps,
+                    "steps": e2e_steps, "warmup": e2e_warm,
                     "ms_per_step": sum(e2e_ms) / max(1, len(e2e_ms)), "scene_create_ms": sum(e2e_create_ms) / max(1, len(e2e_create_ms)),
                     "step_ms_rank0": [round(x, 1) for x in e2e_ms], "scene_create_ms_rank0": [round(x, 1) for x in e2e_create_ms]},
             "gpu_launches": n_launch, "kernel_ms_per_step": {k: v / args.steps for k, v in st["ms"].items()},
@@ -320,6 +325,8 @@ def run_ours(args):
                          "kernel_share_of_step": dom_ms / total_ms,
                          "whole_step_achieved": whole, "whole_step_frac": whole / peak,
                          "peak_source": which,
+                         **({"note": "frac > 1 is possible here: SURVEY 8(d) prices every occlusion query at a BVH walk (Q(T) bytes); "
+                                     "the visibility maps answer most of them from a short triangle list instead"} if WORKLOAD_KEY == "c5" else {}),
                          "bytes_model": "dominant kernel: (32*ceil(log2(ceil(T/4)))+192) B per query it answers (SURVEY 8d Q(T)); "
                                         "whole step: 64*S + Q(T)*(S+O) + 8*U"},
             "cpu_baseline": cpu_base, "clocks": clocks,

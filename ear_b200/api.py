@@ -395,6 +395,21 @@ class Scene:
                             first_ray, ray_count, finalise, post)
 
 
+class _ResultOwner:
+    """Keeps an ear_b200_result alive while numpy views of its tracks exist; frees it with the last of them."""
+
+    def __init__(self, lib, res):
+        self.lib, self.res = lib, res
+
+    def __del__(self):
+        try:
+            if self.res is not None:
+                self.lib.ear_b200_result_free(self.res)
+                self.res = None
+        except Exception:
+            pass
+
+
 def _render_call(lib, fn, handle, contexts, recorders, max_bounces, seed, n_bins, first_ray, ray_count, finalise, post):
     import time
     t0 = time.perf_counter()
@@ -405,37 +420,33 @@ def _render_call(lib, fn, handle, contexts, recorders, max_bounces, seed, n_bins
     t1 = time.perf_counter()
     _check(lib, fn(handle, ctx, len(contexts), rec, n_rec, C.byref(opt), C.byref(res)))
     t2 = time.perf_counter()
-    try:
-        r = res.contents
-        tracks, t60 = [], []
-        for c in range(r.n_contexts):
-            per_rec, per_t60 = [], []
-            for k in range(r.n_recorders):
-                pair, pair_t60 = [], []
-                n_tracks = 2 if rec[c * n_rec + k].kind == STEREO else 1
-                for tr in range(n_tracks):
-                    t = r.tracks[(c * r.n_recorders + k) * 2 + tr]
-                    # one memcpy out of the library-owned buffer (np.ctypeslib.as_array on a pointer builds a ctypes
-                    # array type per call and is an order of magnitude slower for 1e6-sample tracks)
-                    data = np.empty((t.length,), np.float32)
-                    C.memmove(data.ctypes.data, t.data, t.length * 4)
-                    pair.append(Track(data, int(t.first_sample), int(t.real_length)))
-                    if r.t60:
-                        pair_t60.append(float(r.t60[(c * r.n_recorders + k) * 2 + tr]))
-                per_rec.append(pair)
-                per_t60.append(pair_t60)
-            tracks.append(per_rec)
-            t60.append(per_t60)
-        out = RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
-                           int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
-        if r.t60:
-            out.maximum, out.t60 = float(r.maximum), t60
-    finally:
-        lib.ear_b200_result_free(res)
+    owner = _ResultOwner(lib, res)     # the tracks below are views of the library's (page-locked) block: no copy
+    r = res.contents
+    tracks, t60 = [], []
+    for c in range(r.n_contexts):
+        per_rec, per_t60 = [], []
+        for k in range(r.n_recorders):
+            pair, pair_t60 = [], []
+            n_tracks = 2 if rec[c * n_rec + k].kind == STEREO else 1
+            for tr in range(n_tracks):
+                t = r.tracks[(c * r.n_recorders + k) * 2 + tr]
+                buf = (C.c_float * t.length).from_address(C.cast(t.data, C.c_void_p).value or 0) if t.length else (C.c_float * 0)()
+                buf._owner = owner             # the result is freed when the last track view is gone
+                pair.append(Track(np.frombuffer(buf, np.float32), int(t.first_sample), int(t.real_length)))
+                if r.t60:
+                    pair_t60.append(float(r.t60[(c * r.n_recorders + k) * 2 + tr]))
+            per_rec.append(pair)
+            per_t60.append(pair_t60)
+        tracks.append(per_rec)
+        t60.append(per_t60)
+    out = RenderResult(tracks, int(r.rays), int(r.segments), int(r.occlusion_queries), int(r.contributions),
+                       int(r.bin_updates), int(r.dropped_updates), float(r.device_ms))
+    if r.t60:
+        out.maximum, out.t60 = float(r.maximum), t60
     if os.environ.get("EAR_B200_DEBUG"):
         t3 = time.perf_counter()
         print(f"[ear_b200.api] render: pack {1e3 * (t1 - t0):.1f} ms, library call {1e3 * (t2 - t1):.1f} ms, "
-              f"track copies {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
+              f"track views {1e3 * (t3 - t2):.1f} ms", file=sys.stderr)
     return out
 
 

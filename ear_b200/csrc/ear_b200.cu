@@ -99,6 +99,49 @@ static void trim_all() { std::lock_guard<std::mutex> g(g_lock); trim_locked(0); 
 template <class T> static cudaError_t dev_alloc(T** out, size_t bytes) { return devcache::alloc((void**)out, bytes); }
 static void dev_free(void* p) { devcache::release(p); }
 
+// Page-locked host blocks for the tracks a render hands out (one block per result).  cudaHostAlloc of tens of MB costs
+// milliseconds, and a pageable destination makes the download a staged copy through page faults; a released block is kept
+// for the next result of about that size (bounded: at most kHostCacheBlocks blocks).
+namespace hostcache {
+struct Block { void* p; size_t bytes; };
+static std::mutex g_lock;
+static std::vector<Block> g_free;
+constexpr size_t kHostCacheBlocks = 4;
+static void* take(size_t bytes, size_t* got) {
+	bytes = std::max<size_t>((bytes + 4095) / 4096 * 4096, 4096);
+	{
+		std::lock_guard<std::mutex> g(g_lock);
+		size_t best = g_free.size();
+		for (size_t i = 0; i < g_free.size(); ++i)
+			if (g_free[i].bytes >= bytes && g_free[i].bytes <= bytes + bytes / 4 + (1u << 20) && (best == g_free.size() || g_free[i].bytes < g_free[best].bytes)) best = i;
+		if (best != g_free.size()) {
+			const Block b = g_free[best];
+			g_free.erase(g_free.begin() + (long)best);
+			*got = b.bytes;
+			return b.p;
+		}
+	}
+	void* p = nullptr;
+	if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	*got = bytes;
+	return p;
+}
+static void give(void* p, size_t bytes) {
+	if (!p) return;
+	std::lock_guard<std::mutex> g(g_lock);
+	g_free.push_back(Block{p, bytes});
+	while (g_free.size() > kHostCacheBlocks) {   // drop the oldest
+		cudaFreeHost(g_free.front().p);
+		g_free.erase(g_free.begin());
+	}
+}
+static void trim_all() {
+	std::lock_guard<std::mutex> g(g_lock);
+	for (auto& b : g_free) cudaFreeHost(b.p);
+	g_free.clear();
+}
+}  // namespace hostcache
+
 // call-scoped device buffer: freed on every return path (the ABI functions leave through CUDA_TRY on errors)
 template <class T>
 struct DevBuf {
@@ -363,7 +406,7 @@ struct ear_b200_scene {
 
 extern "C" const char* ear_b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t ear_b200_abi_version(void) { return EAR_B200_ABI_VERSION; }
-extern "C" void ear_b200_release_cached_memory(void) { devcache::trim_all(); }
+extern "C" void ear_b200_release_cached_memory(void) { devcache::trim_all(); hostcache::trim_all(); }
 extern "C" int32_t ear_b200_device_count(void) {
 	int n = 0;
 	if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
@@ -437,6 +480,8 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	read_slot_knob(s);
 	s->dev.vis_cap = kVisMaxList;
 	if (const char* vc = std::getenv("EAR_B200_VISMAP_CAP")) s->dev.vis_cap = std::max(0, std::min(4096, std::atoi(vc)));
+	s->dev.vis_prefix = 32;
+	if (const char* vp = std::getenv("EAR_B200_VISMAP_PREFIX")) s->dev.vis_prefix = std::max(0, std::min(4096, std::atoi(vp)));
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	if (const char* vb = std::getenv("EAR_B200_VISMAP_BUILD")) s->vismap_build = std::string(vb) == "atomic" ? 1 : 0;
 	if (const char* vs = std::getenv("EAR_B200_VISMAP_SORT")) s->vismap_sort = std::max(-1, std::min(1, std::atoi(vs)));
@@ -1437,6 +1482,15 @@ extern "C" void ear_b200_group_destroy(ear_b200_group* g) {
 }
 extern "C" int32_t ear_b200_group_size(ear_b200_group* g) { return g ? (int32_t)g->scenes.size() : 0; }
 
+// What ear_b200_render hands out is the head of this box; ear_b200_result_free finds the track block through it.
+constexpr uint64_t kResultMagic = 0x6561725f72657331ull;
+struct ResultBox {
+	ear_b200_result pub;
+	uint64_t magic;
+	void* block;          // page-locked block holding every track of the result, or null (tracks calloc'ed one by one)
+	size_t block_bytes;
+};
+
 // host tracks out of GPU 0's buffers (shared by the single- and multi-GPU renders)
 static int32_t assemble_result(ear_b200_scene* s, const ear_b200_recorder* rec, int32_t n_ctx, int32_t n_rec, int tpr, int32_t n_bins,
                                const float* d_hist, const uint32_t* d_range, const unsigned long long counters[8], double ms,
@@ -1446,10 +1500,12 @@ static int32_t assemble_result(ear_b200_scene* s, const ear_b200_recorder* rec, 
 	CUDA_TRY(cudaMemcpyAsync(range.data(), d_range, range.size() * 4, cudaMemcpyDeviceToHost, s->stream));
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
 	// the result is the caller's once it is handed out; until then every error path frees it
-	std::unique_ptr<ear_b200_result, void (*)(ear_b200_result*)> holder((ear_b200_result*)calloc(1, sizeof(ear_b200_result)),
+	std::unique_ptr<ear_b200_result, void (*)(ear_b200_result*)> holder((ear_b200_result*)calloc(1, sizeof(ResultBox)),
 	                                                                    ear_b200_result_free);
 	ear_b200_result* res = holder.get();
 	if (!res) return fail("render: out of host memory");
+	ResultBox* box = (ResultBox*)res;
+	box->magic = kResultMagic;
 	res->n_contexts = n_ctx; res->n_recorders = n_rec;
 	// the result keeps the [context][recorder][2] shape whatever the device layout was (mono: slot 0 only)
 	res->tracks = (ear_b200_track*)calloc((size_t)n_ctx * n_rec * 2, sizeof(ear_b200_track));
@@ -1458,6 +1514,13 @@ static int32_t assemble_result(ear_b200_scene* s, const ear_b200_recorder* rec, 
 		res->t60 = (float*)calloc((size_t)n_ctx * n_rec * 2, sizeof(float));
 		if (!res->t60) return fail("render: out of host memory");
 	}
+	// all tracks of the result live in ONE page-locked block (whole rows come down: the device rows are zero beyond what
+	// was recorded, so no host-side clearing is needed); pageable memory only if the block cannot be had
+	size_t n_used = 0;
+	for (size_t j = 0; j < (size_t)n_ctx * n_rec; ++j) n_used += rec[j].kind == EAR_B200_STEREO ? 2 : 1;
+	const size_t row = ((size_t)n_bins + 63) / 64 * 64;   // floats; rows start on 256-byte boundaries
+	box->block = hostcache::take(std::max<size_t>(n_used * row, 1) * sizeof(float), &box->block_bytes);
+	size_t at = 0;
 	for (size_t j = 0; j < (size_t)n_ctx * n_rec; ++j)
 		for (int k = 0; k < 2; ++k) {
 			ear_b200_track& tr = res->tracks[2 * j + k];
@@ -1466,10 +1529,19 @@ static int32_t assemble_result(ear_b200_scene* s, const ear_b200_recorder* rec, 
 			if (!used) continue;
 			const size_t t = j * tpr + k;   // device track
 			tr.first_sample = range[2 * t]; tr.real_length = range[2 * t + 1]; tr.length = (uint32_t)n_bins;
-			tr.data = (float*)calloc((size_t)n_bins, sizeof(float));
-			if (!tr.data) return fail("render: out of host memory");
-			const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
-			CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + t * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+			if (box->block) {
+				tr.data = (float*)box->block + at * row;
+				++at;
+				// (after the post chain the device row still holds samples beyond the truncated length: those are cleared here)
+				const size_t live = t60 ? std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins) : (size_t)n_bins;
+				CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + t * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+				if (live < (size_t)n_bins) std::memset(tr.data + live, 0, ((size_t)n_bins - live) * sizeof(float));
+			} else {
+				tr.data = (float*)calloc((size_t)n_bins, sizeof(float));
+				if (!tr.data) return fail("render: out of host memory");
+				const size_t live = std::min<size_t>((size_t)tr.real_length + 1, (size_t)n_bins);
+				CUDA_TRY(cudaMemcpyAsync(tr.data, d_hist + t * (size_t)n_bins, live * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+			}
 			if (t60) res->t60[2 * j + k] = t60[t];
 		}
 	CUDA_TRY(cudaStreamSynchronize(s->stream));
@@ -1873,11 +1945,14 @@ extern "C" void ear_b200_scene_stats_reset(ear_b200_scene* s) {
 
 extern "C" void ear_b200_result_free(ear_b200_result* r) {
 	if (!r) return;
+	ResultBox* box = (ResultBox*)r;   // results only ever come from assemble_result
+	const bool boxed = box->magic == kResultMagic && box->block != nullptr;
 	if (r->tracks) {
 		const size_t n = (size_t)r->n_contexts * r->n_recorders * 2;
-		for (size_t k = 0; k < n; ++k) free(r->tracks[k].data);
+		if (!boxed) for (size_t k = 0; k < n; ++k) free(r->tracks[k].data);
 		free(r->tracks);
 	}
+	if (boxed) hostcache::give(box->block, box->block_bytes);
 	free(r->t60);
 	free(r);
 }

@@ -31,6 +31,7 @@ struct SceneDev {
 	int32_t leaf_vote;        // lanes that must wait on a leaf before the warp runs a leaf step
 	int32_t fetch_vote;       // idle lanes that trigger a fetch of new work in the persistent kernels
 	int32_t vis_cap;          // visibility-map texel lists longer than this are traced through the BVH instead
+	int32_t vis_prefix;       // ... after their first vis_prefix (nearest) entries failed to block the query
 	int2* spill;              // [spill_rows][spill_threads] overflow of the shared-memory traversal stacks
 	int32_t spill_threads;    // columns of `spill`; kernels that walk the BVH launch at most this many threads
 	int32_t spill_rows;       // sized at scene creation from the depth of the tree: 3 pushes per level at most

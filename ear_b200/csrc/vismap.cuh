@@ -292,9 +292,17 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 				const float4 s0 = ld_stream(pool.sh0 + slot);
 				const V3 pnt = mk(s0.x, s0.y, s0.z), x = mk(mp.x[0], mp.x[1], mp.x[2]);
 				const int texel = vis_texel(mp, pnt.x - x.x, pnt.y - x.y, pnt.z - x.z);
-				const int beg = mp.offsets[texel], end = mp.offsets[texel + 1] & ~kVisOverlong;
-				if (beg < 0) fallback = true;   // list longer than the cap: not stored
-				else {
+				const int raw = mp.offsets[texel];
+				const bool overlong = raw < 0;   // list longer than the cap
+				const int beg = raw & ~kVisOverlong;
+				int end = mp.offsets[texel + 1] & ~kVisOverlong;
+				// An over-long list is never walked to its end (that is what the BVH is for), but "blocked" needs only ONE
+				// crossing triangle, whichever list it came from: the sort-based build stores these lists too, nearest first,
+				// and in a venue of several rooms the blocker of most queries is a wall next to the recorder -- so the first
+				// vis_prefix entries settle most of them; the rest go to the any-hit kernel as before.  (The atomic build
+				// does not store over-long lists: beg == end there.)
+				if (overlong) end = min(end, beg + sc.vis_prefix);
+				{
 					const V3 d = vsub(x, pnt);   // LineSeg(p, x) = Ray(p, x - p)
 					visible = true;
 					// The loop is a chain of dependent loads (item -> triangle record -> test; ncu: long-scoreboard stalls
@@ -321,6 +329,7 @@ __global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool
 							    t > 1e-5f && t < 1.0f) visible = false;
 						}
 					}
+					if (overlong && visible) { visible = false; fallback = true; }   // not blocked by the prefix: the BVH decides
 				}
 			}
 		}

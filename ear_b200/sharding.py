@@ -141,9 +141,12 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
             t60 = h_t60.reshape(n_ctx, n_rec, tpr).tolist()
         h_rng = rng.cpu().numpy()
         c = counters.cpu().numpy()
-        # download only what each track holds (FloatBuffer semantics: real_length + 1 samples are meaningful)
-        longest = min(n_bins, int(h_rng[:, 1].max()) + 1) if n_tracks else 0
-        h_hist = hist[:, :longest].cpu().numpy()
+        # whole rows into ONE page-locked buffer (torch's host allocator keeps it for the next call); the device rows are
+        # zero beyond what was recorded, and the Track objects below are views of this buffer -- no host-side copies
+        h_pinned = torch.empty((n_tracks, n_bins), dtype=torch.float32, pin_memory=True)
+        h_pinned.copy_(hist, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        h_hist = h_pinned.numpy()
     lap("finalise + download")
     tracks = []
     for ci in range(n_ctx):
@@ -153,9 +156,9 @@ def render_sharded(scene, contexts, recorders, max_bounces: int = 1000, seed: in
             for tr in range(2 if rec_c[ci * n_rec + k].kind == api.STEREO else 1):
                 t = (ci * n_rec + k) * tpr + tr
                 real_len = int(h_rng[t, 1])
-                data = np.zeros((n_bins,), np.float32)       # Track.data spans the whole buffer, like Scene.render()
-                data[:real_len + 1] = h_hist[t, :real_len + 1]
-                pair.append(api.Track(data, int(h_rng[t, 0]), real_len))
+                if post is not None:
+                    h_hist[t, real_len + 1:] = 0.0     # the device row keeps the samples beyond the truncated length
+                pair.append(api.Track(h_hist[t], int(h_rng[t, 0]), real_len))   # spans the whole buffer, like Scene.render()
             per_rec.append(pair)
         tracks.append(per_rec)
     lap("track objects")
