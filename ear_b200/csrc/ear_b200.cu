@@ -1043,14 +1043,6 @@ static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res,
 		std::fprintf(stderr, "[ear_b200] vismap (sort build): %-18s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(now - t_prev).count());
 		t_prev = now;
 	};
-	if ((size_t)n_tex > s->vis_scratch_cap) {
-		dev_free(s->d_vis_counts); dev_free(s->d_vis_sums);
-		s->d_vis_counts = nullptr; s->d_vis_sums = nullptr; s->vis_scratch_cap = 0;
-		CUDA_TRY(dev_alloc(&s->d_vis_counts, (size_t)n_tex * sizeof(int)));
-		CUDA_TRY(dev_alloc(&s->d_vis_sums, kVisScanBlocks * sizeof(long long)));
-		s->vis_scratch_cap = (size_t)n_tex;
-	}
-	int* d_counts = s->d_vis_counts;
 	CUDA_TRY(dev_alloc(&m.d_offsets, ((size_t)n_tex + 1) * sizeof(int)));
 	struct MapGuard {
 		ear_b200_scene::VisMapHost* m;
@@ -1061,35 +1053,36 @@ static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res,
 	const size_t n_ids = (size_t)1 << id_bits;
 	const unsigned grid = (unsigned)(n_ids / 128);
 	DevBuf<int> d_pair_count, d_pair_base, d_pair_sums;
+	DevBuf<unsigned long long> d_total;
 	CUDA_TRY(d_pair_count.alloc(n_ids)); CUDA_TRY(d_pair_base.alloc(n_ids + 1));
 	CUDA_TRY(d_pair_sums.alloc(n_ids / (dbvh::kScanBlock * dbvh::kScanPer) + 2));
-	CUDA_TRY(cudaMemsetAsync(d_counts, 0, (size_t)n_tex * sizeof(int), stream));
+	CUDA_TRY(d_total.alloc(1));
+	CUDA_TRY(cudaMemsetAsync(d_total.p, 0, sizeof(unsigned long long), stream));
 	const double reach = 2.0 * (double)s->diagonal + 1.0;
 	int texel_bits = 1;
 	while ((1 << texel_bits) < n_tex) ++texel_bits;
 	const int dist_bits = 32 - texel_bits;
 	const float dist_scale = (float)((double)(1u << dist_bits) / reach);
 	const int cap = s->dev.vis_cap;
-	const int per = (n_tex + kVisScanBlocks - 1) / kVisScanBlocks;
 	lap("alloc + clear");
-	vis_emit_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_counts, d_pair_count, nullptr, nullptr, nullptr, dist_bits, dist_scale);
+	vis_emit_kernel<0><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_pair_count, nullptr, nullptr, nullptr, dist_bits, dist_scale);
 	lap("count pass");
-	vis_scan_sums_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, n_tex, per, -1);
-	vis_scan_top_kernel<<<1, kVisScanBlocks, 0, stream>>>(s->d_vis_sums, m.d_offsets, n_tex);
-	vis_scan_offsets_kernel<<<kVisScanBlocks, 1024, 0, stream>>>(d_counts, s->d_vis_sums, m.d_offsets, n_tex, per, -1, cap);
+	vis_pair_total_kernel<<<s->sm_count * 4, 256, 0, stream>>>(d_pair_count, n_ids, d_total);
 	dbvh::exclusive_scan(d_pair_count, (int)n_ids, d_pair_base, d_pair_sums, stream);
-	int total = 0;
-	CUDA_TRY(cudaMemcpyAsync(&total, m.d_offsets + n_tex, sizeof(int), cudaMemcpyDeviceToHost, stream));
+	unsigned long long total64 = 0;
+	CUDA_TRY(cudaMemcpyAsync(&total64, d_total.p, sizeof(total64), cudaMemcpyDeviceToHost, stream));
 	CUDA_TRY(cudaStreamSynchronize(stream));
-	lap("scans");
+	lap("scan");
 	if (s->vis_budget == 0) {
 		size_t free_b = 0, total_b = 0;
 		CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
 		s->vis_budget = std::max<size_t>(free_b / 4, 1);
 		if (const char* vb = std::getenv("EAR_B200_VISMAP_BUDGET")) s->vis_budget = std::max<size_t>((size_t)std::atof(vb), 1);
 	}
-	const size_t map_bytes = ((size_t)n_tex + 1) * sizeof(int) + (total < 0 ? 0 : (size_t)total * sizeof(int));
-	if (total < 0 || s->vis_bytes + map_bytes > s->vis_budget) { s->vis_budget_spent = true; return 0; }
+	const bool too_many = total64 >= 0x7fffffffull;
+	const int total = too_many ? 0 : (int)total64;
+	const size_t map_bytes = ((size_t)n_tex + 1) * sizeof(int) + (size_t)total * sizeof(int);
+	if (too_many || s->vis_bytes + map_bytes > s->vis_budget) { s->vis_budget_spent = true; return 0; }
 	s->vis_bytes += map_bytes;
 	m.n_items = (size_t)total;
 	CUDA_TRY(dev_alloc(&m.d_items, std::max<size_t>(m.n_items, 1) * sizeof(int)));
@@ -1098,15 +1091,21 @@ static int32_t build_vismap_sorted(ear_b200_scene* s, const float x[3], int res,
 		DevBuf<int> d_vals_a;
 		DevBuf<unsigned char> d_tmp;
 		CUDA_TRY(d_keys_a.alloc((size_t)total)); CUDA_TRY(d_keys_b.alloc((size_t)total)); CUDA_TRY(d_vals_a.alloc((size_t)total));
-		vis_emit_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_counts, d_pair_count, d_pair_base, d_keys_a, d_vals_a, dist_bits, dist_scale);
+		vis_emit_kernel<1><<<grid, 128, 0, stream>>>(s->dev, x[0], x[1], x[2], res, reach, s->maxabs, id_bits, d_pair_count, d_pair_base, d_keys_a, d_vals_a, dist_bits, dist_scale);
 		CUDA_TRY(cudaGetLastError());
 		lap("emit pass");
 		size_t tmp_bytes = 0;
 		CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, d_keys_a.p, d_keys_b.p, d_vals_a.p, m.d_items, total, 0, 32, stream));
 		CUDA_TRY(d_tmp.alloc(tmp_bytes));
 		CUDA_TRY(cub::DeviceRadixSort::SortPairs(d_tmp.p, tmp_bytes, d_keys_a.p, d_keys_b.p, d_vals_a.p, m.d_items, total, 0, 32, stream));
-		CUDA_TRY(cudaStreamSynchronize(stream));
 		lap("radix sort");
+		vis_offsets_from_keys_kernel<<<s->sm_count * 8, 256, 0, stream>>>(d_keys_b, total, dist_bits, n_tex, m.d_offsets);
+		vis_flag_overlong_kernel<<<(n_tex + 255) / 256, 256, 0, stream>>>(m.d_offsets, n_tex, cap);
+		CUDA_TRY(cudaGetLastError());
+		CUDA_TRY(cudaStreamSynchronize(stream));   // the key buffers go back to the cache when this scope ends
+		lap("offsets");
+	} else {
+		CUDA_TRY(cudaMemsetAsync(m.d_offsets, 0, ((size_t)n_tex + 1) * sizeof(int), stream));
 	}
 	if (dbg) std::fprintf(stderr, "[ear_b200] vismap (sort build): %d entries, %d distance bits\n", total, dist_bits);
 	m.sorted = true;

@@ -82,14 +82,16 @@ __global__ void __launch_bounds__(128) vis_build_kernel(SceneDev sc, double x0, 
 }
 
 // Sort-based build (default).  The fill pass above takes one RETURNING atomic per (triangle, texel) entry -- 132 M of
-// them for the 1M-triangle hall, 34 ms -- and leaves every list in arbitrary order.  Instead: pass 0 counts list lengths
-// (fire-and-forget REDs) and the number of entries each footprint emits; one scan gives every footprint its place in a flat
-// array; pass 1 writes (key, triangle) pairs there without any atomic, key = texel << d | distance of the triangle from the
-// recorder in d bits; ONE radix sort (cub::DeviceRadixSort) then yields all lists at once, each ordered nearest-first --
-// which is the order the lookups want (a blocked query stops at the first triangle its segment crosses).
+// them for the 1M-triangle hall, 34 ms -- and leaves every list in arbitrary order.  Instead, with NO atomic at all: pass 0
+// counts the entries each footprint emits; one scan gives every footprint its place in a flat array; pass 1 writes
+// (key, triangle) pairs there, key = texel << d | distance of the triangle from the recorder in d bits; ONE radix sort
+// (cub::DeviceRadixSort) then yields all lists at once, each ordered nearest-first -- the order the lookups want (a
+// blocked query stops at the first triangle its segment crosses) -- and the list offsets are read off the sorted keys
+// (vis_offsets_from_keys_kernel).  (The first version of pass 0 also counted list lengths with one RED per entry: 10 ms
+// of its 14.6.)
 template <int PASS>
 __global__ void __launch_bounds__(128) vis_emit_kernel(SceneDev sc, double x0, double x1, double x2, int res, double reach, double maxabs,
-                                                       int id_bits, int* counts, int* pair_count, const int* pair_base,
+                                                       int id_bits, int* pair_count, const int* pair_base,
                                                        uint32_t* keys, int* vals, int dist_bits, float dist_scale) {
 	const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	const long long id = (long long)(__brevll(tid) >> (64 - id_bits));
@@ -122,8 +124,7 @@ __global__ void __launch_bounds__(128) vis_emit_kernel(SceneDev sc, double x0, d
 			const int i = i0 + k % w, j = j0 + k / w;
 			if (vis_covers(edge, res, i, j)) {
 				const int texel = (face * res + j) * res + i;
-				if (PASS == 0) atomicAdd(counts + texel, 1);
-				else { keys[base + mine] = ((uint32_t)texel << dist_bits) | dq; vals[base + mine] = t; }
+				if (PASS == 1) { keys[base + mine] = ((uint32_t)texel << dist_bits) | dq; vals[base + mine] = t; }
 				++mine;
 			}
 		}
@@ -144,16 +145,65 @@ __global__ void __launch_bounds__(128) vis_emit_kernel(SceneDev sc, double x0, d
 			const int i = b_i0 + k % b_w, j = b_j0 + k / b_w;
 			const bool covered = k < b_area && vis_covers(e, res, i, j);
 			const unsigned m = __ballot_sync(0xffffffffu, covered);
-			if (covered) {
+			if (PASS == 1 && covered) {
 				const int texel = (b_face * res + j) * res + i;
-				if (PASS == 0) atomicAdd(counts + texel, 1);
-				else { const int at = b_base + run + __popc(m & lt_mask); keys[at] = ((uint32_t)texel << dist_bits) | b_dq; vals[at] = b_t; }
+				const int at = b_base + run + __popc(m & lt_mask);
+				keys[at] = ((uint32_t)texel << dist_bits) | b_dq; vals[at] = b_t;
 			}
 			run += __popc(m);
 		}
 		if (lane == src) mine = run;
 	}
 	if (PASS == 0) pair_count[tid] = mine;
+}
+
+// 64-bit total of the per-footprint entry counts (the scan that places them works in 32 bits: a map with 2^31 entries or
+// more is not built, its recorder's queries walk the BVH)
+__global__ void __launch_bounds__(256) vis_pair_total_kernel(const int* pair_count, size_t n, unsigned long long* total) {
+	__shared__ unsigned long long part[8];
+	unsigned long long s = 0;
+	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += (unsigned long long)pair_count[i];
+	for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+	if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		for (int k = 1; k < 8; ++k) s += part[k];
+		atomicAdd(total, s);
+	}
+}
+
+// offsets[t] = first position in the sorted pair array whose texel is >= t (offsets[n_tex] = total): entry i closes the
+// texels after its predecessor's up to its own.  Long runs of empty texels (a cube face that sees nothing) are filled by
+// the whole warp.
+__global__ void __launch_bounds__(256) vis_offsets_from_keys_kernel(const uint32_t* keys, int total, int dist_bits, int n_tex, int* offsets) {
+	const int lane = threadIdx.x & 31;
+	const long long stride = (long long)gridDim.x * blockDim.x;
+	for (long long base = (long long)blockIdx.x * blockDim.x; base <= total; base += stride) {   // warp-uniform trip count
+		const long long i = base + threadIdx.x;
+		int first = 0, last = -1;   // texels [first, last] get offset i
+		if (i <= total) {
+			last = i < total ? (int)(keys[i] >> dist_bits) : n_tex;
+			first = i > 0 ? (int)(keys[i - 1] >> dist_bits) + 1 : 0;
+		}
+		constexpr int kInline = 4;
+		if (last - first < kInline) for (int t = first; t <= last; ++t) offsets[t] = (int)i;
+		unsigned big = __ballot_sync(0xffffffffu, last - first >= kInline);
+		while (big) {
+			const int src = __ffs(big) - 1;
+			big &= big - 1;
+			const int b_first = __shfl_sync(0xffffffffu, first, src), b_last = __shfl_sync(0xffffffffu, last, src);
+			const int b_i = (int)__shfl_sync(0xffffffffu, (int)i, src);
+			for (int t = b_first + lane; t <= b_last; t += 32) offsets[t] = b_i;
+		}
+	}
+}
+
+// lists longer than `cap` carry kVisOverlong in their offset (readers mask the bit off their neighbour's word)
+__global__ void __launch_bounds__(256) vis_flag_overlong_kernel(int* offsets, int n_tex, int cap) {
+	const int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_tex) return;
+	const int beg = offsets[t] & ~kVisOverlong, end = offsets[t + 1] & ~kVisOverlong;
+	if (end - beg > cap) offsets[t] = beg | kVisOverlong;
 }
 
 // Exclusive scan of the list lengths in three launches (block sums, scan of the sums, offsets).  Lengths above
