@@ -246,8 +246,21 @@ __device__ __forceinline__ float half_bits_to_float(uint32_t h) {   // fp16 bits
 	return __int_as_float((int)(((e + 112u) << 23) | (m << 13)));
 }
 __device__ __forceinline__ void cswap(uint32_t& a, uint32_t& b) { const uint32_t lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+// c[k] for k in 0..3 out of registers.  Written as a ternary chain this compiled into a BRANCH tree (BSSY / BRA / BSYNC,
+// ~12 instructions and a divergent reconvergence per pick, four picks per node step: profiles/r2_ncu_wf_traverse_kernel.txt);
+// three selects on the two bits of k instead.
 __device__ __forceinline__ int32_t pick4(int32_t c0, int32_t c1, int32_t c2, int32_t c3, uint32_t k) {
+#ifdef EARB_HOST_EMULATION
 	return k == 0u ? c0 : k == 1u ? c1 : k == 2u ? c2 : c3;
+#else
+	int32_t r;
+	asm("{\n\t.reg .pred p, q;\n\t.reg .b32 a, b;\n\t"
+	    "and.b32 a, %5, 1;\n\tsetp.ne.b32 p, a, 0;\n\t"
+	    "and.b32 b, %5, 2;\n\tsetp.ne.b32 q, b, 0;\n\t"
+	    "selp.b32 a, %2, %1, p;\n\tselp.b32 b, %4, %3, p;\n\tselp.b32 %0, b, a, q;\n\t}"
+	    : "=r"(r) : "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(k));
+	return r;
+#endif
 }
 
 #ifndef EARB_DECODE_PRMT
