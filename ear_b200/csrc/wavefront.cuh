@@ -274,6 +274,28 @@ __global__ void __launch_bounds__(256) wf_scatter_kernel(WfPool pool) {
 #ifndef EARB_SHADE_MIN_BLOCKS
 #define EARB_SHADE_MIN_BLOCKS 4
 #endif
+#ifndef EARB_COOP_REJECTION
+#define EARB_COOP_REJECTION 1
+#endif
+// One try of Sample_Sphere / Sample_Hemi (src/Distributions.h:48-67) from the three words of a Philox block.
+__device__ __forceinline__ V3 rejection_candidate(uint32_t w0, uint32_t w1, uint32_t w2) {
+	return mk(fsub(fmul(Rng::to_unit(w0), 2.0f), 1.0f), fsub(fmul(Rng::to_unit(w1), 2.0f), 1.0f), fsub(fmul(Rng::to_unit(w2), 2.0f), 1.0f));
+}
+// sphere: 0.001 <= |cand|^2 <= 1; hemisphere: n . (cand / |cand|) >= 0 as well.  |cand| <= 1 and the float evaluation of
+// n.v is off by ~4e-7 at most, so n.cand < -1e-5 means the exact test rejects and n.cand > 1e-5 means it accepts; only in
+// between (probability ~1e-5 per try) is the reference's expression evaluated.
+__device__ __forceinline__ bool rejection_try(uint32_t w0, uint32_t w1, uint32_t w2, V3 n, bool hemi) {
+	const V3 cand = rejection_candidate(w0, w1, w2);
+	const float l = vdot(cand, cand);
+	const bool in_sphere = !(l < 0.001f || l > 1.0f);
+	const float dc = fmaf(n.x, cand.x, fmaf(n.y, cand.y, n.z * cand.z));
+	bool accept = in_sphere && (!hemi || dc > 1e-5f);
+	if (in_sphere && hemi && fabsf(dc) <= 1e-5f) {   // too close to call on the unnormalised candidate
+		const float s = fsqrt(l);
+		accept = !(vdot(n, mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s))) < 0.0f);
+	}
+	return accept;
+}
 #ifndef EARB_DEFER_NORMALISE
 #define EARB_DEFER_NORMALISE 1
 #endif
@@ -386,32 +408,69 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	V3 v = mk(0, 0, 0);
 	{
 		// The hemisphere test n.v >= 0 is on the NORMALISED candidate v = cand / |cand| in the reference.  Its outcome is
-		// decided on the unnormalised candidate whenever that is clear-cut: |cand| <= 1 and the float evaluation of
-		// n.v is off by ~4e-7 at most, so n.cand < -1e-5 means the exact test rejects and n.cand > 1e-5 means it accepts.
-		// Only in between (probability ~1e-5 per try) is the exact expression evaluated inside the loop.  The sqrt and
-		// the three divisions then run ONCE per lane after the loop, with the warp converged, instead of once per
-		// sphere-accepted try with ~5 lanes active (ncu: that block was 24 % of this kernel's instructions).
+		// decided on the unnormalised candidate whenever that is clear-cut (rejection_try).  The sqrt and the three
+		// divisions then run ONCE per lane after the loop, with the warp converged, instead of once per sphere-accepted
+		// try with ~5 lanes active (ncu: that block was 24 % of this kernel's instructions).
+		//
+		// A hemisphere try succeeds with probability pi/12 = 0.26, so a warp that lets every lane run its own tries needs
+		// the MAXIMUM over 32 lanes -- 13.9 rounds measured, 8.7 lanes active on average (ncu: half of this kernel's
+		// instructions).  Tries are independent Philox blocks (ray id, block index), so once half of the lanes are done
+		// the idle ones evaluate LATER tries of the pending rays: T = 2, 4 .. 32 consecutive blocks per pending ray and
+		// round; the first accepted one in block order wins, which is exactly the try the serial loop stops at.
+		const bool hemi = mode == kBounce || mesh_emit;   // Sample_Hemi; point sources emit over the sphere
 		bool pending = mode != kNone;
-		V3 cand = mk(0, 0, 1);
-		float l = 1.0f;
-		while (pending) {   // one back edge, no break / continue: the warp reconverges every try
-			float u1, u2, u3;
-			rng.unit3(u1, u2, u3);
-			cand = mk(fsub(fmul(u1, 2.0f), 1.0f), fsub(fmul(u2, 2.0f), 1.0f), fsub(fmul(u3, 2.0f), 1.0f));
-			l = vdot(cand, cand);
-			const bool in_sphere = !(l < 0.001f || l > 1.0f);
-			const float dc = fmaf(n.x, cand.x, fmaf(n.y, cand.y, n.z * cand.z));
-			const bool hemi = mode == kBounce || mesh_emit;   // Sample_Hemi; point sources emit over the sphere
-			bool accept = in_sphere && (!hemi || dc > 1e-5f);
-			if (in_sphere && hemi && fabsf(dc) <= 1e-5f) {   // too close to call on the unnormalised candidate
-				const float s = fsqrt(l);
-				accept = !(vdot(n, mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s))) < 0.0f);
+		uint32_t a0 = 0x80000000u, a1 = 0x80000000u, a2 = 0xffffff00u;   // words of the accepted try (default: (0, 0, 1))
+#if EARB_COOP_REJECTION
+		__shared__ uint4 coop_a[8][32];
+		__shared__ float4 coop_b[8][32];
+		const int wid = threadIdx.x >> 5;
+#endif
+		unsigned m_pending = __ballot_sync(0xffffffffu, pending);
+		while (m_pending) {   // warp-uniform: one back edge
+#if EARB_COOP_REJECTION
+			const int n_pend = __popc(m_pending);
+			if (n_pend <= 16) {
+				const int log_t = 31 - __clz(32 / n_pend);          // T = 2^log_t tries per pending ray this round
+				const int rank = __popc(m_pending & lt_mask);
+				if (pending) {
+					coop_a[wid][rank] = make_uint4(rng.ray_lo, rng.ray_hi, rng.ctx, rng.block);
+					coop_b[wid][rank] = make_float4(n.x, n.y, n.z, hemi ? 1.0f : 0.0f);
+				}
+				__syncwarp();
+				const int j = lane >> log_t, k = lane & ((1 << log_t) - 1);
+				bool ok = false;
+				uint32_t w0 = 0, w1 = 0, w2 = 0;
+				if (j < n_pend) {
+					const uint4 ra = coop_a[wid][j];
+					const float4 rb = coop_b[wid][j];
+					Rng other = rng;                                   // same seed words for the whole call
+					other.ray_lo = ra.x; other.ray_hi = ra.y; other.ctx = ra.z; other.block = ra.w + (uint32_t)k;
+					other.draw(w0, w1, w2);
+					ok = rejection_try(w0, w1, w2, mk(rb.x, rb.y, rb.z), rb.w != 0.0f);
+				}
+				const unsigned m_ok = __ballot_sync(0xffffffffu, ok);
+				__syncwarp();                                          // the slots are rewritten next round
+				const unsigned span = log_t == 5 ? 0xffffffffu : ((1u << (1 << log_t)) - 1u);
+				const unsigned mine = pending ? ((m_ok >> (rank << log_t)) & span) : 0u;
+				const int first = __ffs(mine) - 1;                     // earliest accepted try of this lane's ray, or -1
+				const int src = first >= 0 ? (rank << log_t) + first : lane;
+				const uint32_t g0 = __shfl_sync(0xffffffffu, w0, src), g1 = __shfl_sync(0xffffffffu, w1, src), g2 = __shfl_sync(0xffffffffu, w2, src);
+				if (pending) {
+					if (first >= 0) { a0 = g0; a1 = g1; a2 = g2; rng.block += (uint32_t)first + 1u; pending = false; }
+					else rng.block += 1u << log_t;
+				}
+			} else
+#endif
+			if (pending) {
+				uint32_t w0, w1, w2;
+				rng.draw(w0, w1, w2);
+				if (rejection_try(w0, w1, w2, n, hemi)) { a0 = w0; a1 = w1; a2 = w2; pending = false; }
 			}
-			pending = !accept;
+			m_pending = __ballot_sync(0xffffffffu, pending);
 		}
-		__syncwarp();
 		if (mode != kNone) {
-			const float s = fsqrt(l);
+			const V3 cand = rejection_candidate(a0, a1, a2);
+			const float s = fsqrt(vdot(cand, cand));
 			v = mk(fdiv(cand.x, s), fdiv(cand.y, s), fdiv(cand.z, s));
 		}
 	}

@@ -182,7 +182,9 @@ int32_t ear_b200_trace_paths(ear_b200_scene* scene, const ear_b200_context* ctx,
                              const ear_b200_options* opt, int64_t n, int32_t* hits, float* final_state /*[n][8]*/);
 
 /* The hot path.  Host buffers in, host tracks out (device copies inside).
- * rec: [n_contexts][n_recorders]. */
+ * rec: [n_contexts][n_recorders].  The tracks of one result live in a single page-locked host block owned by the
+ * library (a released block is kept for the next result of about that size; ear_b200_release_cached_memory()
+ * returns it to the driver); they stay valid, and may be written, until ear_b200_result_free(). */
 int32_t ear_b200_render(ear_b200_scene* scene, const ear_b200_context* ctx, int32_t n_contexts,
                         const ear_b200_recorder* rec, int32_t n_recorders, const ear_b200_options* opt,
                         ear_b200_result** out);
