@@ -374,6 +374,7 @@ struct ear_b200_scene {
 	int check_every = 8;            // iterations between host checks for completion
 	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
 	int splat_mode = 0;             // 0: one RED per ramp sample; 1: shared-memory time-window privatisation (EAR_B200_SPLAT=window)
+	int grid_wave = 1;              // lookups / splat launch one wave of resident blocks (EAR_B200_GRID_WAVE)
 	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
 	WfPool pool{};
 	size_t pool_slots = 0, pool_queries = 0, log2af_cap = 0;
@@ -485,6 +486,7 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	if (const char* vr = std::getenv("EAR_B200_VISMAP_RES")) s->vismap_res = std::max(0, std::min(2048, std::atoi(vr)));
 	if (const char* vb = std::getenv("EAR_B200_VISMAP_BUILD")) s->vismap_build = std::string(vb) == "atomic" ? 1 : 0;
 	if (const char* vs = std::getenv("EAR_B200_VISMAP_SORT")) s->vismap_sort = std::max(-1, std::min(1, std::atoi(vs)));
+	if (const char* gw = std::getenv("EAR_B200_GRID_WAVE")) s->grid_wave = std::atoi(gw) != 0 ? 1 : 0;
 	if (const char* sq = std::getenv("EAR_B200_SORT_QUERIES")) s->sort_queries = std::atoi(sq) != 0 ? 1 : 0;
 	if (const char* sm = std::getenv("EAR_B200_SPLAT")) s->splat_mode = std::string(sm) == "window" ? 1 : 0;
 	if (const char* pg = std::getenv("EAR_B200_GENERATIONS")) s->pool_generations = std::max(0, std::atoi(pg));
@@ -1219,7 +1221,13 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, closest, kBlock, kStackBytes));
 	const int trav_grid = s->sm_count * std::max(1, bps);
 	const int shade_grid = (int)(slots / 256);
-	const int splat_grid = s->sm_count * 8;
+	// grid-stride kernels: one wave of resident blocks (a fixed 8 per SM left a partial second wave at 5 resident)
+	int splat_bps = 0, vismap_bps = 0;
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&splat_bps, wf_splat_kernel, 256, 0));
+	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vismap_bps, wf_vismap_kernel, 256, 0));
+	const int wave = s->grid_wave;   // EAR_B200_GRID_WAVE=0: the fixed 8 blocks per SM
+	const int splat_grid = s->sm_count * (wave ? std::max(1, splat_bps) : 8);
+	const int vismap_grid = s->sm_count * (wave ? std::max(1, vismap_bps) : 8);
 	const int n_pairs = p.n_ctx * p.n_rec;
 	const bool windowed = s->splat_mode == 1 && n_pairs <= kPrivMaxPairs && p.n_rec > 0;
 	if (windowed) CUDA_TRY(cudaFuncSetAttribute(wf_splat_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPrivWindow * sizeof(float))));
@@ -1242,7 +1250,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 			{ LaunchTimer t(s, stream, 1); closest<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 			if (p.n_rec > 0) {
 				if (n_mapped) {
-					{ LaunchTimer t(s, stream, 6); wf_vismap_kernel<<<s->sm_count * 8, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh); }
+					{ LaunchTimer t(s, stream, 6); wf_vismap_kernel<<<vismap_grid, 256, 0, stream>>>(s->dev, pl, p, s->d_maps, s->d_map_of, s->d_q_bvh); }
 					{ LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl_fb, p); }
 				} else { LaunchTimer t(s, stream, 2); anyhit<<<trav_grid, kBlock, kStackBytes, stream>>>(s->dev, pl, p); }
 				if (windowed) {

@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(256) vis_sort_kernel(SceneDev sc, float x0, fl
 
 // K4 through the maps: one query per thread.  Visible queries go to vis_list; queries whose texel list is too
 // long (or whose recorder has no map) go to `q_bvh` for the BVH any-hit kernel.
-__global__ void __launch_bounds__(256) wf_vismap_kernel(SceneDev sc, WfPool pool, RenderParams p, const VisMapDev* maps,
+#ifndef EARB_VISMAP_MIN_BLOCKS
+#define EARB_VISMAP_MIN_BLOCKS 5   // resident 256-thread blocks per SM asked of the compiler (5 <-> 48 registers)
+#endif
+__global__ void __launch_bounds__(256, EARB_VISMAP_MIN_BLOCKS) wf_vismap_kernel(SceneDev sc, WfPool pool, RenderParams p, const VisMapDev* maps,
                                                         const int* map_of, uint2* q_bvh) {
 	const int total = pool.counts[1];
 	const int lane = threadIdx.x & 31;

@@ -640,7 +640,10 @@ __device__ __forceinline__ bool splat_weight(const WfPool& pool, const RenderPar
 	return true;
 }
 
-__global__ void __launch_bounds__(256) wf_splat_kernel(WfPool pool, RenderParams p) {
+#ifndef EARB_SPLAT_MIN_BLOCKS
+#define EARB_SPLAT_MIN_BLOCKS 5    // resident 256-thread blocks per SM asked of the compiler (5 <-> 48 registers)
+#endif
+__global__ void __launch_bounds__(256, EARB_SPLAT_MIN_BLOCKS) wf_splat_kernel(WfPool pool, RenderParams p) {
 	const int total = pool.counts[2];
 	LocalCounters lc = {0, 0, 0, 0, 0, 0};
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
