@@ -1221,13 +1221,14 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, closest, kBlock, kStackBytes));
 	const int trav_grid = s->sm_count * std::max(1, bps);
 	const int shade_grid = (int)(slots / 256);
-	// grid-stride kernels: one wave of resident blocks (a fixed 8 per SM left a partial second wave at 5 resident)
-	int splat_bps = 0, vismap_bps = 0;
-	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&splat_bps, wf_splat_kernel, 256, 0));
+	// Grid-stride kernels.  Lookups: one wave of resident blocks (5 per SM at 48 registers) instead of a fixed 8 per SM,
+	// which left a partial second wave: 108 -> 99 ms per 4e7 rays at C4, 489 -> 453 ms per 3e6 rays at C5.  The splat
+	// kernel is the other way round (8 per SM: 97 / 99 ms, one wave: 100 / 110 ms).  Capping either kernel at 40 or 32
+	// registers for 6 or 8 resident blocks spills and loses (profiles/r2_ab_closest.txt, call 15).
+	int vismap_bps = 0;
 	CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&vismap_bps, wf_vismap_kernel, 256, 0));
-	const int wave = s->grid_wave;   // EAR_B200_GRID_WAVE=0: the fixed 8 blocks per SM
-	const int splat_grid = s->sm_count * (wave ? std::max(1, splat_bps) : 8);
-	const int vismap_grid = s->sm_count * (wave ? std::max(1, vismap_bps) : 8);
+	const int splat_grid = s->sm_count * 8;
+	const int vismap_grid = s->sm_count * (s->grid_wave ? std::max(1, vismap_bps) : 8);   // EAR_B200_GRID_WAVE=0: fixed 8
 	const int n_pairs = p.n_ctx * p.n_rec;
 	const bool windowed = s->splat_mode == 1 && n_pairs <= kPrivMaxPairs && p.n_rec > 0;
 	if (windowed) CUDA_TRY(cudaFuncSetAttribute(wf_splat_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kPrivWindow * sizeof(float))));

@@ -540,38 +540,69 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	}
 
 	// ---- K4 enqueue: Scene::Connect is called for every recorder (src/Scene.cpp:188-195); its answer is only
-	// used when dot(lsdir, n) > 0 (:209), so only those queries are traced ----
-	for (int r = 0; r < p.n_rec; ++r) {
-		bool facing = false;
-		if (shaded) {
-			++lc.occlusion;
-			const float* x = p.rec[(size_t)c * p.n_rec + r].position;
-			// dot(lsdir, n) > 0 with lsdir = normalize(x - p) (src/Scene.cpp:202-209).  The sign is that of dot(x - p, n);
-			// normalising (three divisions by the rounded length) and the three roundings of the dot move the value by a
-			// few ulp of |x - p| at most, so the unnormalised dot decides whenever it is clearly away from zero and the
-			// exact expression is evaluated only in between (64 recorders: this loop is a third of the kernel at C5).
-			const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
-			const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
-			const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
-			if (mesh_emit) facing = true;
-			else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;
-			else facing = vdot(vnormalized(seg), n) > 0.0f;
+	// used when dot(lsdir, n) > 0 (:209), so only those queries are traced.
+	// Two passes over the recorders.  Pass 1 decides `facing` per (lane, recorder) and keeps the warp's ballot per recorder
+	// in shared memory; ONE counter atomic then reserves the warp's range of the query list.  Pass 2 writes the entries,
+	// four recorders at a time, so that the four rank atomics of a group are in flight together.  (The first version
+	// took a counter atomic AND a rank atomic per recorder and waited for both before moving on: with 64 recorders 85 %
+	// of this kernel's stall samples sat on those two round trips, profiles/r2_ncu_c5_wf_shade_kernel.txt.) ----
+	if (p.n_rec > 0) {
+		__shared__ unsigned q_mask[8][256];   // [warp of the block][recorder] (n_rec <= 255)
+		const int wq = threadIdx.x >> 5;
+		int warp_total = 0;
+		if (shaded) lc.occlusion += (unsigned long long)p.n_rec;
+		for (int r = 0; r < p.n_rec; ++r) {
+			bool facing = false;
+			if (shaded) {
+				const float* x = p.rec[(size_t)c * p.n_rec + r].position;
+				// dot(lsdir, n) > 0 with lsdir = normalize(x - p) (src/Scene.cpp:202-209).  The sign is that of dot(x - p, n);
+				// normalising (three divisions by the rounded length) and the three roundings of the dot move the value by a
+				// few ulp of |x - p| at most, so the unnormalised dot decides whenever it is clearly away from zero and the
+				// exact expression is evaluated only in between.
+				const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
+				const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
+				const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
+				if (mesh_emit) facing = true;
+				else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;
+				else facing = vdot(vnormalized(seg), n) > 0.0f;
+			}
+			const unsigned mq = __ballot_sync(0xffffffffu, facing);
+			if (lane == 0) q_mask[wq][r] = mq;
+			warp_total += __popc(mq);
 		}
-		const unsigned mq = __ballot_sync(0xffffffffu, facing);
-		if (mq) {
-			int base = 0;
-			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
-			base = __shfl_sync(0xffffffffu, base, 0);
-			if (facing) {
-				if (pool.sort_queries) {
-					const uint32_t bin = (((uint32_t)r & 7u) << 12) | cell_key(pool, pnt.x, pnt.y, pnt.z);
-					const int at = base + __popc(mq & lt_mask);
-					st_stream(pool.q_rank + at, atomicAdd(pool.bins + kRayBins + bin, 1));
-					st_stream(pool.q_tmp + at,
-					          make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | (bin << 16) | ((uint32_t)(bounce & 1) << 31)));
-				} else {
-					st_stream(pool.q_list + base + __popc(mq & lt_mask),
-					          make_uint2((uint32_t)slot | ((uint32_t)r << pool.slot_bits), (uint32_t)c | ((uint32_t)(bounce & 1) << 31)));
+		__syncwarp();
+		if (warp_total) {   // warp-uniform
+			int run = 0;
+			if (lane == 0) run = atomicAdd(pool.counts + 1, warp_total);
+			run = __shfl_sync(0xffffffffu, run, 0);
+			const uint32_t cell = pool.sort_queries ? cell_key(pool, pnt.x, pnt.y, pnt.z) : 0u;
+			const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
+			constexpr int kGroup = 4;
+			for (int r0 = 0; r0 < p.n_rec; r0 += kGroup) {
+				int at[kGroup], rank[kGroup];
+				bool mine[kGroup];
+#pragma unroll
+				for (int g = 0; g < kGroup; ++g) {
+					const int r = r0 + g;
+					const unsigned mq = r < p.n_rec ? q_mask[wq][r] : 0u;
+					mine[g] = (mq >> lane) & 1u;
+					at[g] = run + __popc(mq & lt_mask);
+					run += __popc(mq);
+					rank[g] = 0;
+					if (mine[g] && pool.sort_queries) rank[g] = atomicAdd(pool.bins + kRayBins + ((((uint32_t)r & 7u) << 12) | cell), 1);
+				}
+#pragma unroll
+				for (int g = 0; g < kGroup; ++g) {
+					if (!mine[g]) continue;
+					const uint32_t r = (uint32_t)(r0 + g);
+					const uint32_t word_x = (uint32_t)slot | (r << pool.slot_bits);
+					if (pool.sort_queries) {
+						const uint32_t bin = ((r & 7u) << 12) | cell;
+						st_stream(pool.q_rank + at[g], rank[g]);
+						st_stream(pool.q_tmp + at[g], make_uint2(word_x, word_y | (bin << 16)));
+					} else {
+						st_stream(pool.q_list + at[g], make_uint2(word_x, word_y));
+					}
 				}
 			}
 		}
