@@ -546,6 +546,20 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	// four recorders at a time, so that the four rank atomics of a group are in flight together.  (The first version
 	// took a counter atomic AND a rank atomic per recorder and waited for both before moving on: with 64 recorders 85 %
 	// of this kernel's stall samples sat on those two round trips, profiles/r2_ncu_c5_wf_shade_kernel.txt.) ----
+	// K6's atomics (list position of the warp's live rays, rank of each ray inside its bin) are issued early, between the
+	// atomics of the query enqueue, so that the round trips overlap; their results are consumed at the end of the kernel
+	const unsigned live = __ballot_sync(0xffffffffu, alive);
+	const uint32_t my_ray_bin = alive ? ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z) : 0u;
+	int live_base = 0, live_rank = 0;
+	bool ray_atomics_issued = false;
+	auto issue_ray_atomics = [&]() {
+		if (ray_atomics_issued) return;
+		ray_atomics_issued = true;
+		if (live) {
+			if (lane == 0) live_base = atomicAdd(pool.counts + 0, __popc(live));
+			if (alive) live_rank = atomicAdd(pool.bins + my_ray_bin, 1);
+		}
+	};
 	if (p.n_rec > 0) {
 		__shared__ unsigned q_mask[8][256];   // [warp of the block][recorder] (n_rec <= 255)
 		const int wq = threadIdx.x >> 5;
@@ -574,12 +588,19 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		if (warp_total) {   // warp-uniform
 			int run = 0;
 			if (lane == 0) run = atomicAdd(pool.counts + 1, warp_total);
+			issue_ray_atomics();   // K6's two atomics go out before anything waits for the one above
 			run = __shfl_sync(0xffffffffu, run, 0);
 			const uint32_t cell = pool.sort_queries ? cell_key(pool, pnt.x, pnt.y, pnt.z) : 0u;
+			// The rays of a warp were fetched in bin order, so most of its hit points share a cell and their rank atomics
+			// hit the SAME counter (32-way same-address returning atomics: at C5 they were 85 % of this kernel, 184 of 218 ms
+			// per 3e6 rays).  Lanes with equal cells are grouped once; per recorder the first facing lane of a group takes
+			// one atomic for all of them.
+			const unsigned m_shaded = __ballot_sync(0xffffffffu, shaded);
+			const unsigned peers = (shaded && pool.sort_queries) ? __match_any_sync(m_shaded, cell) : 0u;
 			const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
 			constexpr int kGroup = 4;
-			for (int r0 = 0; r0 < p.n_rec; r0 += kGroup) {
-				int at[kGroup], rank[kGroup];
+			for (int r0 = 0; r0 < p.n_rec; r0 += kGroup) {   // warp-uniform
+				int at[kGroup], rank[kGroup], who[kGroup];     // who = leader lane | position inside the group << 8
 				bool mine[kGroup];
 #pragma unroll
 				for (int g = 0; g < kGroup; ++g) {
@@ -588,17 +609,23 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 					mine[g] = (mq >> lane) & 1u;
 					at[g] = run + __popc(mq & lt_mask);
 					run += __popc(mq);
-					rank[g] = 0;
-					if (mine[g] && pool.sort_queries) rank[g] = atomicAdd(pool.bins + kRayBins + ((((uint32_t)r & 7u) << 12) | cell), 1);
+					rank[g] = 0; who[g] = lane;
+					if (mine[g] && pool.sort_queries) {
+						const unsigned group = peers & mq;               // facing lanes of this recorder in my cell
+						const int leader = __ffs(group) - 1;
+						who[g] = leader | (__popc(group & lt_mask) << 8);
+						if (lane == leader) rank[g] = atomicAdd(pool.bins + kRayBins + ((((uint32_t)r & 7u) << 12) | cell), __popc(group));
+					}
 				}
 #pragma unroll
 				for (int g = 0; g < kGroup; ++g) {
+					const int first = __shfl_sync(0xffffffffu, rank[g], who[g] & 31);   // every lane takes part
 					if (!mine[g]) continue;
 					const uint32_t r = (uint32_t)(r0 + g);
 					const uint32_t word_x = (uint32_t)slot | (r << pool.slot_bits);
 					if (pool.sort_queries) {
 						const uint32_t bin = ((r & 7u) << 12) | cell;
-						st_stream(pool.q_rank + at[g], rank[g]);
+						st_stream(pool.q_rank + at[g], first + (who[g] >> 8));
 						st_stream(pool.q_tmp + at[g], make_uint2(word_x, word_y | (bin << 16)));
 					} else {
 						st_stream(pool.q_list + at[g], make_uint2(word_x, word_y));
@@ -612,16 +639,13 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	st_stream(pool.rm + slot, m);
 	if (alive) { st_stream(pool.ro + slot, ro); st_stream(pool.rd + slot, rd); }
 	// ---- K6 compaction: slots that need a closest-hit query next, binned by (direction octant, origin cell) ----
-	const unsigned live = __ballot_sync(0xffffffffu, alive);
+	issue_ray_atomics();
 	if (live) {
-		int base = 0;
-		if (lane == 0) base = atomicAdd(pool.counts + 0, __popc(live));
-		base = __shfl_sync(0xffffffffu, base, 0);
+		const int base = __shfl_sync(0xffffffffu, live_base, 0);
 		if (alive) {
-			const uint32_t bin = ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
 			const int at = base + __popc(live & lt_mask);
-			st_stream(pool.trav_rank + at, atomicAdd(pool.bins + bin, 1));
-			st_stream(pool.trav_tmp + at, make_uint2((uint32_t)slot, bin));
+			st_stream(pool.trav_rank + at, live_rank);
+			st_stream(pool.trav_tmp + at, make_uint2((uint32_t)slot, my_ray_bin));
 		}
 	}
 	// the launch loop stops when no slot holds a ray and the shard's queue is dry
