@@ -372,7 +372,7 @@ struct ear_b200_scene {
 	bool slots_forced = false;
 	int pool_generations = 0;       // 0: choose from the bounce cap; k: pool = work / k slots (EAR_B200_GENERATIONS)
 	int check_every = 8;            // iterations between host checks for completion
-	int sort_queries = 1;           // counting-sort the occlusion queries by (recorder, cell) (EAR_B200_SORT_QUERIES)
+	int sort_queries = -1;          // counting-sort the occlusion queries by (recorder, cell): -1 = for up to 4 recorders (EAR_B200_SORT_QUERIES=0/1)
 	int splat_mode = 0;             // 0: one RED per ramp sample; 1: shared-memory time-window privatisation (EAR_B200_SPLAT=window)
 	int grid_wave = 1;              // lookups / splat launch one wave of resident blocks (EAR_B200_GRID_WAVE)
 	int ray_key = 2;                // binning of closest-hit rays (EAR_B200_RAY_KEY, see ray_bin; 2 measured best)
@@ -928,7 +928,7 @@ static int32_t ensure_pool(ear_b200_scene* s, size_t slots, size_t queries) {
 	pl.slot_bits = kMaxSlotBits;   // harness calls: one implicit recorder
 	if (!pl.bins) CUDA_TRY(dev_alloc(&pl.bins, kBinsTotal * sizeof(int)));
 	pl.ray_key = s->ray_key;
-	pl.sort_queries = s->sort_queries;
+	pl.sort_queries = s->sort_queries != 0 ? 1 : 0;   // the render loop decides per call when the setting is -1
 	for (int k = 0; k < 3; ++k) {
 		pl.cell_origin[k] = s->lo[k];
 		const float ext = s->hi[k] - s->lo[k];
@@ -1204,6 +1204,11 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	pl.n_slots = (int)slots;
 	pl.slot_bits = slot_bits;
 	pl.q_count_idx = 1; pl.q_cursor_idx = 4;
+	// Query order.  Sorted by (recorder, cell of the hit point): neighbouring lookups read the same texel lists.  Unsorted:
+	// the shade kernel's order, a warp's queries for one recorder side by side.  One recorder (C4, per 4e7 rays): sorted
+	// 1027 ms, unsorted 1056.  64 recorders (C5, per 3e6 rays): sorted 1012 ms (sort 198, rank atomics in the shade kernel
+	// 140), unsorted 796 -- lookups 466 -> 620, but shade 175 -> 36, sort 198 -> 2, splat 99 -> 66.
+	if (s->sort_queries < 0) pl.sort_queries = p.n_rec <= 4 ? 1 : 0;
 	CUDA_TRY(cudaMemsetAsync(pl.rm, 0, (size_t)slots * sizeof(uint4), stream));
 	if ((size_t)p.n_ctx > s->log2af_cap) {
 		dev_free(s->pool.ctx_log2af);

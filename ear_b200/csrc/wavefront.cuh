@@ -560,7 +560,37 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 			if (alive) live_rank = atomicAdd(pool.bins + my_ray_bin, 1);
 		}
 	};
-	if (p.n_rec > 0) {
+	if (p.n_rec == 1) {
+		// one recorder: nothing to batch -- the single-pass form (two passes cost 4 % of this kernel here)
+		bool facing = false;
+		if (shaded) {
+			++lc.occlusion;
+			const float* x = p.rec[c].position;
+			const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
+			const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
+			const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
+			if (mesh_emit) facing = true;
+			else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;   // see the general form below
+			else facing = vdot(vnormalized(seg), n) > 0.0f;
+		}
+		const unsigned mq = __ballot_sync(0xffffffffu, facing);
+		if (mq) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (facing) {
+				const int at = base + __popc(mq & lt_mask);
+				const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
+				if (pool.sort_queries) {
+					const uint32_t bin = cell_key(pool, pnt.x, pnt.y, pnt.z);
+					st_stream(pool.q_rank + at, atomicAdd(pool.bins + kRayBins + bin, 1));
+					st_stream(pool.q_tmp + at, make_uint2((uint32_t)slot, word_y | (bin << 16)));
+				} else {
+					st_stream(pool.q_list + at, make_uint2((uint32_t)slot, word_y));
+				}
+			}
+		}
+	} else if (p.n_rec > 1) {
 		__shared__ unsigned q_mask[8][256];   // [warp of the block][recorder] (n_rec <= 255)
 		const int wq = threadIdx.x >> 5;
 		int warp_total = 0;
