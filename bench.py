@@ -251,11 +251,13 @@ def run_ours(args):
             print(f"[bench] rank {rank} e2e step: create {e2e_create_ms[-1]:.1f} ms, render {(w1 - wc) * 1e3:.1f} ms", file=sys.stderr)
             if os.environ.get("EAR_BENCH_VERBOSE") == "2":   # diagnosis only: the same render again on the now-warm scene
                 s3 = create_replicated_scene(verts, tri_mat, table, device=local)
-                for k in range(2):
+                for k in range(3):
+                    s3.stats(reset=True)
                     torch.cuda.synchronize(); wa = time.perf_counter()
                     render_sharded(s3, ctxs, recs, max_bounces=MAX_BOUNCES, seed=1234)
                     torch.cuda.synchronize()
-                    print(f"[bench] rank {rank} render #{k + 1} on one scene: {(time.perf_counter() - wa) * 1e3:.1f} ms", file=sys.stderr)
+                    print(f"[bench] rank {rank} render #{k + 1} on one scene: {(time.perf_counter() - wa) * 1e3:.1f} ms, "
+                          f"kernels {({n: round(v, 1) for n, v in s3.stats()['ms'].items()})}", file=sys.stderr)
                 s3.close()
     e2 = torch.tensor([sum(e2e_ms)], dtype=torch.float64, device=dev)
     es = torch.tensor([e2e_segments], dtype=torch.int64, device=dev)
