@@ -51,7 +51,7 @@ def select_workload(key, rays=None, tris=None):
     N_BANDS, N_RECORDERS = b, n
     TOTAL_RAYS = int(float(rays if rays is not None else os.environ.get("EAR_BENCH_RAYS", r)))
     what = "hall" if key == "c4" else "complex of 8 coupled halls"
-    WORKLOAD = (f"synthetic {N_TRIS}-triangle {what}, {N_BANDS} bands, {TOTAL_RAYS:.0e} rays, {MAX_BOUNCES} bounces, "
+    WORKLOAD = (f"synthetic {N_TRIS}-triangle {what}, {N_BANDS} bands, {TOTAL_RAYS:.3g} rays, {MAX_BOUNCES} bounces, "
                 f"{N_RECORDERS} mono recorder{'s' if N_RECORDERS > 1 else ''}")
     if TOTAL_RAYS != int(r) or N_TRIS != t:
         WORKLOAD += f" [REDUCED from the named {t} triangles / {r:.0e} rays]"

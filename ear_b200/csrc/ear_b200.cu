@@ -163,6 +163,7 @@ struct DevBuf {
 // ------------------------------------------------------------------------------------------
 // device-side parameter blocks
 // ------------------------------------------------------------------------------------------
+constexpr int kCounterParts = 256;   // partial rows of the shade kernel's counters (wavefront.cuh)
 struct RenderParams {
 	const ear_b200_context* ctx;     // [n_ctx]
 	const ear_b200_recorder* rec;    // [n_ctx][n_rec]
@@ -176,6 +177,7 @@ struct RenderParams {
 	float* hist;                     // [n_ctx][n_rec][tpr][n_bins]
 	uint32_t* range;                 // [n_ctx][n_rec][tpr][2] {first_sample, real_length}
 	unsigned long long* counters;    // [8]
+	unsigned long long* counter_parts;   // [kCounterParts][4] partial rows of counters 0..2 (shade kernel), folded at the end of a trace
 	unsigned long long* next_work;   // work-queue head
 	int32_t* hits;                   // parity harness: [rays][max_bounces] triangle hit per bounce (or null)
 	float* final_state;              // parity harness: [rays][8] (or null)
@@ -402,6 +404,7 @@ struct ear_b200_scene {
 	// scratch reused across calls
 	ear_b200_context* d_ctx = nullptr; ear_b200_recorder* d_rec = nullptr; long long* d_prefix = nullptr; float* d_ctx_area = nullptr;
 	unsigned long long* d_queue = nullptr;
+	unsigned long long* d_counter_parts = nullptr;   // [kCounterParts][4], all zero between calls
 	size_t ctx_cap = 0, rec_cap = 0;
 };
 
@@ -460,6 +463,8 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	s->sm_count = prop.multiProcessorCount;
 	CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
 	CUDA_TRY(dev_alloc(&s->d_queue, sizeof(unsigned long long)));
+	CUDA_TRY(dev_alloc(&s->d_counter_parts, kCounterParts * 4 * sizeof(unsigned long long)));
+	CUDA_TRY(cudaMemset(s->d_counter_parts, 0, kCounterParts * 4 * sizeof(unsigned long long)));
 	s->dev.nodes = s->d_nodes; s->dev.tris = s->d_tris; s->dev.materials = s->d_materials;
 	s->dev.n_tris = h.n_tris; s->dev.n_materials = h.n_materials; s->dev.n_bands = h.n_bands;
 	s->dev.s0 = h.s0;
@@ -676,7 +681,7 @@ extern "C" void ear_b200_scene_destroy(ear_b200_scene* s) {
 	cudaSetDevice(s->device);
 	cudaDeviceSynchronize();   // released blocks go back to the cache: nothing of this scene may still be in flight
 	dev_free(s->d_image); dev_free(s->d_spill); dev_free(s->d_emitters);
-	dev_free(s->d_ctx); dev_free(s->d_rec); dev_free(s->d_prefix); dev_free(s->d_queue); dev_free(s->d_ctx_area);
+	dev_free(s->d_ctx); dev_free(s->d_rec); dev_free(s->d_prefix); dev_free(s->d_queue); dev_free(s->d_counter_parts); dev_free(s->d_ctx_area);
 	dev_free(s->pool.ro); dev_free(s->pool.rd); dev_free(s->pool.rm); dev_free(s->pool.hit);
 	dev_free(s->pool.sh0); dev_free(s->pool.sh1); dev_free(s->pool.sh2); dev_free(s->pool.trav_list);
 	dev_free(s->pool.q_list); dev_free(s->pool.vis_list); dev_free(s->pool.counts);
@@ -873,6 +878,7 @@ static int32_t upload_params(ear_b200_scene* s, const ear_b200_context* ctx, int
 	p.first_ray = first;
 	p.total_work = prefix[n_ctx];
 	p.next_work = s->d_queue;
+	p.counter_parts = s->d_counter_parts;
 	return 0;
 }
 
@@ -1288,6 +1294,8 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 		if (n_mapped && s->vismap_sort < 0 && s->h_counts[1] > 4096 && (long long)s->h_counts[2] * 2 < s->h_counts[1])
 			if (int32_t rc = sort_vismaps(s, stream)) return rc;
 	}
+	wf_fold_counters_kernel<<<1, kCounterParts, 0, stream>>>(p);
+	CUDA_TRY(cudaGetLastError());
 	if (!finished) return fail("render: the wavefront loop hit its iteration bound with rays left (internal error)");
 	if (dbg) std::fprintf(stderr, "[ear_b200] wavefront loop: %.2f ms after set-up\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_loop).count());
 	return 0;
@@ -1295,6 +1303,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 
 static int32_t launch_trace(ear_b200_scene* s, RenderParams& p, cudaStream_t stream) {
 	CUDA_TRY(cudaMemsetAsync(s->d_queue, 0, sizeof(unsigned long long), stream));
+	CUDA_TRY(cudaMemsetAsync(s->d_counter_parts, 0, kCounterParts * 4 * sizeof(unsigned long long), stream));   // (a failed call may have left some)
 	if (p.total_work <= 0) return 0;
 	// every ray of the shard must have been emitted when the engine returns: the caller's `rays` counter (which may
 	// already hold earlier shards) has to advance by exactly total_work

@@ -679,11 +679,40 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 		}
 	}
 	// the launch loop stops when no slot holds a ray and the shard's queue is dry
+	// Counters: warp sums -> block sums in shared memory -> ONE atomic per counter and block, spread over kCounterParts
+	// partial rows (folded into p.counters when the wavefront loop ends).  The first version added every warp's sums
+	// straight to p.counters: 1.5 M same-address 64-bit atomics per launch of 16 Mi slots, and how fast the L2 retires
+	// those depended on where the caller's counter block happened to live (shade 400 ms per 1e8 rays through
+	// ear_b200_trace_device with a torch tensor, 530 ms through ear_b200_render: profiles/r2_ab_closest.txt).
+	__shared__ unsigned long long w_cnt[8][3];
 	const unsigned long long v0 = warp_sum(lc.rays), v1 = warp_sum(lc.segments), v2 = warp_sum(lc.occlusion);
-	if (lane == 0 && (v0 | v1 | v2)) {
-		if (v0) atomicAdd(p.counters + 0, v0);
-		if (v1) atomicAdd(p.counters + 1, v1);
-		if (v2) atomicAdd(p.counters + 2, v2);
+	if (lane == 0) { w_cnt[threadIdx.x >> 5][0] = v0; w_cnt[threadIdx.x >> 5][1] = v1; w_cnt[threadIdx.x >> 5][2] = v2; }
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		unsigned long long v = 0;
+#pragma unroll
+		for (int w = 0; w < 8; ++w) v += w_cnt[w][threadIdx.x];
+		if (v) atomicAdd(p.counter_parts + (size_t)(blockIdx.x % kCounterParts) * 4 + threadIdx.x, v);
+	}
+}
+
+// adds the partial rows of the shade kernel's counters (rays, segments, occlusion queries) to the call's counters and
+// clears them for the next call
+__global__ void __launch_bounds__(kCounterParts) wf_fold_counters_kernel(RenderParams p) {
+	__shared__ unsigned long long part[kCounterParts / 32][3];
+	unsigned long long v[3];
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		v[k] = p.counter_parts[(size_t)threadIdx.x * 4 + k];
+		p.counter_parts[(size_t)threadIdx.x * 4 + k] = 0;
+		v[k] = warp_sum(v[k]);
+	}
+	if ((threadIdx.x & 31) == 0) for (int k = 0; k < 3; ++k) part[threadIdx.x >> 5][k] = v[k];
+	__syncthreads();
+	if (threadIdx.x < 3) {
+		unsigned long long t = 0;
+		for (int w = 0; w < kCounterParts / 32; ++w) t += part[w][threadIdx.x];
+		if (t) atomicAdd(p.counters + threadIdx.x, t);
 	}
 }
 
