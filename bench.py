@@ -163,6 +163,8 @@ def run_ours(args):
     rng = torch.empty((n_tracks, 2), dtype=torch.int32, device=dev)
     counters = torch.zeros((8,), dtype=torch.int64, device=dev)
     flush = torch.empty((64 * 1024 * 1024,), dtype=torch.float32, device=dev)   # 256 MiB > 126 MB L2
+    if os.environ.get("EAR_BENCH_STREAM") == "new":     # diagnosis: the device-timed leg on a stream of its own
+        torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     stream = torch.cuda.current_stream()
     sp = C.c_void_p(stream.cuda_stream)
 

@@ -461,7 +461,12 @@ static int32_t scene_finish(ear_b200_scene* s, const ImageHeader& h) {
 	cudaDeviceProp prop;
 	CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
 	s->sm_count = prop.multiProcessorCount;
-	CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	{   // diagnosis knob: EAR_B200_STREAM=null runs the scene's own work on the legacy default stream, =blocking on a blocking stream
+		const char* sk = std::getenv("EAR_B200_STREAM");
+		if (sk && std::strcmp(sk, "null") == 0) s->stream = nullptr;
+		else if (sk && std::strcmp(sk, "blocking") == 0) CUDA_TRY(cudaStreamCreate(&s->stream));
+		else CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+	}
 	CUDA_TRY(dev_alloc(&s->d_queue, sizeof(unsigned long long)));
 	CUDA_TRY(dev_alloc(&s->d_counter_parts, kCounterParts * 4 * sizeof(unsigned long long)));
 	CUDA_TRY(cudaMemset(s->d_counter_parts, 0, kCounterParts * 4 * sizeof(unsigned long long)));
@@ -1249,8 +1254,7 @@ static int32_t launch_wavefront(ear_b200_scene* s, RenderParams& p, cudaStream_t
 	bool finished = false;
 	for (long long it = 0; it < max_iter;) {
 		for (int k = 0; k < s->check_every && it < max_iter; ++k, ++it) {
-			CUDA_TRY(cudaMemsetAsync(pl.counts, 0, 8 * sizeof(int), stream));
-			CUDA_TRY(cudaMemsetAsync(pl.bins, 0, kBinsTotal * sizeof(int), stream));
+			wf_clear_kernel<<<(kBinsTotal + 255) / 256, 256, 0, stream>>>(pl);
 			{ LaunchTimer t(s, stream, 0); wf_shade_kernel<<<shade_grid, 256, 0, stream>>>(s->dev, pl, p); }
 			{
 				LaunchTimer t(s, stream, 4);
