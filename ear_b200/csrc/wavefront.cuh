@@ -325,26 +325,14 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	// this launch frees its slot for the NEXT launch: one idle iteration per ~50, and emission shares the sampling
 	// loop with the bounces instead of running on one lane of the warp.) ----
 	const unsigned dead = __ballot_sync(0xffffffffu, !alive);
-	// one queue atomic per block (the warps' demands meet in shared memory), none once the queue is dry
-	__shared__ int want_of[8];
-	__shared__ unsigned long long queue_base;
-	if (lane == 0) want_of[threadIdx.x >> 5] = __popc(dead);
-	__syncthreads();
-	if (threadIdx.x == 0) {
-		int want = 0;
-#pragma unroll
-		for (int w = 0; w < 8; ++w) want += want_of[w];
+	if (dead) {
 		unsigned long long base = 0;
-		if (want) {
+		const int want = __popc(dead);
+		if (lane == 0) {
 			base = *(volatile unsigned long long*)p.next_work;
 			if ((long long)base < p.total_work) base = atomicAdd(p.next_work, (unsigned long long)want);
 		}
-		queue_base = base;
-	}
-	__syncthreads();
-	if (dead) {
-		unsigned long long base = queue_base;
-		for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += (unsigned long long)want_of[w];
+		base = __shfl_sync(0xffffffffu, base, 0);
 		const long long w = (long long)base + __popc(dead & lt_mask);
 		if (!alive && w < p.total_work) {
 			c = 0;
@@ -558,95 +546,122 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	// four recorders at a time, so that the four rank atomics of a group are in flight together.  (The first version
 	// took a counter atomic AND a rank atomic per recorder and waited for both before moving on: with 64 recorders 85 %
 	// of this kernel's stall samples sat on those two round trips, profiles/r2_ncu_c5_wf_shade_kernel.txt.) ----
-	// ---- list positions: ONE returning atomic per BLOCK for the queries and one for the live rays (the warps' totals meet
-	// in shared memory); a returning atomic per warp and list -- 2 x 524 288 on two addresses per launch of 16 Mi slots --
-	// was what the kernel's tail waited for.  The per-lane rank atomics go out before the barrier so that their round
-	// trips overlap it. ----
-	__shared__ int blk_tot[8][2];     // [warp][queries, live rays]
-	__shared__ int blk_base[2];
-	const int wq = threadIdx.x >> 5;
+	// (One position atomic per BLOCK instead of per warp -- warp totals meeting in shared memory behind two barriers -- was
+	// tried and lost: shade 181 -> 192 ms per 4e7 rays at C4, 36 -> 40 ms per 3e6 rays at C5.)
+	// K6's atomics (list position of the warp's live rays, rank of each ray inside its bin) are issued early, between the
+	// atomics of the query enqueue, so that the round trips overlap; their results are consumed at the end of the kernel
 	const unsigned live = __ballot_sync(0xffffffffu, alive);
 	const uint32_t my_ray_bin = alive ? ray_bin(pool, ro.x, ro.y, ro.z, rd.x, rd.y, rd.z) : 0u;
-	int live_rank = 0;
-	if (alive) live_rank = atomicAdd(pool.bins + my_ray_bin, 1);
-	// pass 1 over the recorders: Scene::Connect is called for every recorder (src/Scene.cpp:188-195); its answer is only
-	// used when dot(lsdir, n) > 0 (:209), so only those queries are traced.  The warp's facing ballot per recorder is kept
-	// (register for one recorder, shared memory for more).
-	__shared__ unsigned q_mask[8][256];   // [warp of the block][recorder] (n_rec <= 255)
-	unsigned mq_single = 0u;
-	int warp_total = 0;
-	if (shaded) lc.occlusion += (unsigned long long)p.n_rec;
-	for (int r = 0; r < p.n_rec; ++r) {
+	int live_base = 0, live_rank = 0;
+	bool ray_atomics_issued = false;
+	auto issue_ray_atomics = [&]() {
+		if (ray_atomics_issued) return;
+		ray_atomics_issued = true;
+		if (live) {
+			if (lane == 0) live_base = atomicAdd(pool.counts + 0, __popc(live));
+			if (alive) live_rank = atomicAdd(pool.bins + my_ray_bin, 1);
+		}
+	};
+	if (p.n_rec == 1) {
+		// one recorder: nothing to batch -- the single-pass form (two passes cost 4 % of this kernel here)
 		bool facing = false;
 		if (shaded) {
-			const float* x = p.rec[(size_t)c * p.n_rec + r].position;
-			// dot(lsdir, n) > 0 with lsdir = normalize(x - p) (src/Scene.cpp:202-209).  The sign is that of dot(x - p, n);
-			// normalising (three divisions by the rounded length) and the three roundings of the dot move the value by a
-			// few ulp of |x - p| at most, so the unnormalised dot decides whenever it is clearly away from zero and the
-			// exact expression is evaluated only in between.
+			++lc.occlusion;
+			const float* x = p.rec[c].position;
 			const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
 			const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
 			const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
 			if (mesh_emit) facing = true;
-			else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;
+			else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;   // see the general form below
 			else facing = vdot(vnormalized(seg), n) > 0.0f;
 		}
 		const unsigned mq = __ballot_sync(0xffffffffu, facing);
-		if (p.n_rec == 1) mq_single = mq;
-		else if (lane == 0) q_mask[wq][r] = mq;
-		warp_total += __popc(mq);
-	}
-	if (lane == 0) { blk_tot[wq][0] = warp_total; blk_tot[wq][1] = __popc(live); }
-	__syncthreads();
-	if (threadIdx.x < 2) {
-		int total = 0;
-#pragma unroll
-		for (int w = 0; w < 8; ++w) total += blk_tot[w][threadIdx.x];
-		blk_base[threadIdx.x] = total ? atomicAdd(pool.counts + (threadIdx.x == 0 ? 1 : 0), total) : 0;
-	}
-	__syncthreads();
-	int run = blk_base[0], live_base = blk_base[1];
-	for (int w = 0; w < wq; ++w) { run += blk_tot[w][0]; live_base += blk_tot[w][1]; }
-	// pass 2: the entries, four recorders at a time, so that the rank atomics of a group are in flight together
-	if (warp_total) {   // warp-uniform
-		const uint32_t cell = pool.sort_queries ? cell_key(pool, pnt.x, pnt.y, pnt.z) : 0u;
-		// Lanes whose hit points share a cell send their rank atomics to the SAME counter; they are grouped once and per
-		// recorder the first facing lane of a group takes one atomic for all of them.
-		const unsigned m_shaded = __ballot_sync(0xffffffffu, shaded);
-		const unsigned peers = (shaded && pool.sort_queries) ? __match_any_sync(m_shaded, cell) : 0u;
-		const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
-		constexpr int kGroup = 4;
-		for (int r0 = 0; r0 < p.n_rec; r0 += kGroup) {   // warp-uniform
-			int at[kGroup], rank[kGroup], who[kGroup];     // who = leader lane | position inside the group << 8
-			bool mine[kGroup];
-#pragma unroll
-			for (int g = 0; g < kGroup; ++g) {
-				const int r = r0 + g;
-				const unsigned mq = r >= p.n_rec ? 0u : (p.n_rec == 1 ? mq_single : q_mask[wq][r]);
-				mine[g] = (mq >> lane) & 1u;
-				at[g] = run + __popc(mq & lt_mask);
-				run += __popc(mq);
-				rank[g] = 0; who[g] = lane;
-				if (mine[g] && pool.sort_queries) {
-					const unsigned group = peers & mq;               // facing lanes of this recorder in my cell
-					const int leader = __ffs(group) - 1;
-					who[g] = leader | (__popc(group & lt_mask) << 8);
-					if (lane == leader) rank[g] = atomicAdd(pool.bins + kRayBins + ((((uint32_t)r & 7u) << 12) | cell), __popc(group));
+		if (mq) {
+			int base = 0;
+			if (lane == 0) base = atomicAdd(pool.counts + 1, __popc(mq));
+			base = __shfl_sync(0xffffffffu, base, 0);
+			if (facing) {
+				const int at = base + __popc(mq & lt_mask);
+				const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
+				if (pool.sort_queries) {
+					const uint32_t bin = cell_key(pool, pnt.x, pnt.y, pnt.z);
+					st_stream(pool.q_rank + at, atomicAdd(pool.bins + kRayBins + bin, 1));
+					st_stream(pool.q_tmp + at, make_uint2((uint32_t)slot, word_y | (bin << 16)));
+				} else {
+					st_stream(pool.q_list + at, make_uint2((uint32_t)slot, word_y));
 				}
 			}
+		}
+	} else if (p.n_rec > 1) {
+		__shared__ unsigned q_mask[8][256];   // [warp of the block][recorder] (n_rec <= 255)
+		const int wq = threadIdx.x >> 5;
+		int warp_total = 0;
+		if (shaded) lc.occlusion += (unsigned long long)p.n_rec;
+		for (int r = 0; r < p.n_rec; ++r) {
+			bool facing = false;
+			if (shaded) {
+				const float* x = p.rec[(size_t)c * p.n_rec + r].position;
+				// dot(lsdir, n) > 0 with lsdir = normalize(x - p) (src/Scene.cpp:202-209).  The sign is that of dot(x - p, n);
+				// normalising (three divisions by the rounded length) and the three roundings of the dot move the value by a
+				// few ulp of |x - p| at most, so the unnormalised dot decides whenever it is clearly away from zero and the
+				// exact expression is evaluated only in between.
+				const V3 seg = vsub(mk(x[0], x[1], x[2]), pnt);
+				const float du = fmaf(seg.x, n.x, fmaf(seg.y, n.y, seg.z * n.z));
+				const float mag = fabsf(seg.x) + fabsf(seg.y) + fabsf(seg.z);
+				if (mesh_emit) facing = true;
+				else if (fabsf(du) > 1e-4f * mag) facing = du > 0.0f;
+				else facing = vdot(vnormalized(seg), n) > 0.0f;
+			}
+			const unsigned mq = __ballot_sync(0xffffffffu, facing);
+			if (lane == 0) q_mask[wq][r] = mq;
+			warp_total += __popc(mq);
+		}
+		__syncwarp();
+		if (warp_total) {   // warp-uniform
+			int run = 0;
+			if (lane == 0) run = atomicAdd(pool.counts + 1, warp_total);
+			issue_ray_atomics();   // K6's two atomics go out before anything waits for the one above
+			run = __shfl_sync(0xffffffffu, run, 0);
+			const uint32_t cell = pool.sort_queries ? cell_key(pool, pnt.x, pnt.y, pnt.z) : 0u;
+			// The rays of a warp were fetched in bin order, so most of its hit points share a cell and their rank atomics
+			// hit the SAME counter (32-way same-address returning atomics: at C5 they were 85 % of this kernel, 184 of 218 ms
+			// per 3e6 rays).  Lanes with equal cells are grouped once; per recorder the first facing lane of a group takes
+			// one atomic for all of them.
+			const unsigned m_shaded = __ballot_sync(0xffffffffu, shaded);
+			const unsigned peers = (shaded && pool.sort_queries) ? __match_any_sync(m_shaded, cell) : 0u;
+			const uint32_t word_y = (uint32_t)c | ((uint32_t)(bounce & 1) << 31);
+			constexpr int kGroup = 4;
+			for (int r0 = 0; r0 < p.n_rec; r0 += kGroup) {   // warp-uniform
+				int at[kGroup], rank[kGroup], who[kGroup];     // who = leader lane | position inside the group << 8
+				bool mine[kGroup];
 #pragma unroll
-			for (int g = 0; g < kGroup; ++g) {
-				if (r0 + g >= p.n_rec) break;                                          // warp-uniform
-				const int first = __shfl_sync(0xffffffffu, rank[g], who[g] & 31);   // every lane takes part
-				if (!mine[g]) continue;
-				const uint32_t r = (uint32_t)(r0 + g);
-				const uint32_t word_x = (uint32_t)slot | (r << pool.slot_bits);
-				if (pool.sort_queries) {
-					const uint32_t bin = ((r & 7u) << 12) | cell;
-					st_stream(pool.q_rank + at[g], first + (who[g] >> 8));
-					st_stream(pool.q_tmp + at[g], make_uint2(word_x, word_y | (bin << 16)));
-				} else {
-					st_stream(pool.q_list + at[g], make_uint2(word_x, word_y));
+				for (int g = 0; g < kGroup; ++g) {
+					const int r = r0 + g;
+					const unsigned mq = r < p.n_rec ? q_mask[wq][r] : 0u;
+					mine[g] = (mq >> lane) & 1u;
+					at[g] = run + __popc(mq & lt_mask);
+					run += __popc(mq);
+					rank[g] = 0; who[g] = lane;
+					if (mine[g] && pool.sort_queries) {
+						const unsigned group = peers & mq;               // facing lanes of this recorder in my cell
+						const int leader = __ffs(group) - 1;
+						who[g] = leader | (__popc(group & lt_mask) << 8);
+						if (lane == leader) rank[g] = atomicAdd(pool.bins + kRayBins + ((((uint32_t)r & 7u) << 12) | cell), __popc(group));
+					}
+				}
+#pragma unroll
+				for (int g = 0; g < kGroup; ++g) {
+					const int first = __shfl_sync(0xffffffffu, rank[g], who[g] & 31);   // every lane takes part
+					if (!mine[g]) continue;
+					const uint32_t r = (uint32_t)(r0 + g);
+					const uint32_t word_x = (uint32_t)slot | (r << pool.slot_bits);
+					if (pool.sort_queries) {
+						const uint32_t bin = ((r & 7u) << 12) | cell;
+						st_stream(pool.q_rank + at[g], first + (who[g] >> 8));
+						st_stream(pool.q_tmp + at[g], make_uint2(word_x, word_y | (bin << 16)));
+					} else {
+						st_stream(pool.q_list + at[g], make_uint2(word_x, word_y));
+					}
 				}
 			}
 		}
@@ -656,10 +671,14 @@ __global__ void __launch_bounds__(256, EARB_SHADE_MIN_BLOCKS) wf_shade_kernel(Sc
 	st_stream(pool.rm + slot, m);
 	if (alive) { st_stream(pool.ro + slot, ro); st_stream(pool.rd + slot, rd); }
 	// ---- K6 compaction: slots that need a closest-hit query next, binned by (direction octant, origin cell) ----
-	if (alive) {
-		const int at = live_base + __popc(live & lt_mask);
-		st_stream(pool.trav_rank + at, live_rank);
-		st_stream(pool.trav_tmp + at, make_uint2((uint32_t)slot, my_ray_bin));
+	issue_ray_atomics();
+	if (live) {
+		const int base = __shfl_sync(0xffffffffu, live_base, 0);
+		if (alive) {
+			const int at = base + __popc(live & lt_mask);
+			st_stream(pool.trav_rank + at, live_rank);
+			st_stream(pool.trav_tmp + at, make_uint2((uint32_t)slot, my_ray_bin));
+		}
 	}
 	// the launch loop stops when no slot holds a ray and the shard's queue is dry
 	// Counters: warp sums -> block sums in shared memory -> ONE atomic per counter and block, spread over kCounterParts

@@ -20,4 +20,4 @@ cap c4_n2 c4 5e7 "wf_traverse_kernel<.bool.0" 100 1
 cap c4_n4 c4 2.5e7 "wf_traverse_kernel<.bool.0" 100 1
 cap c4_n8 c4 1.25e7 "wf_traverse_kernel<.bool.0" 30 1
 fi
-cap c5_n1 c5 1e7 "wf_vismap_kernel|wf_traverse_kernel<.bool.1" 40 2
+cap c5_n1 c5 1e7 "wf_vismap_kernel" 40 1

@@ -3,4 +3,4 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/traffic_*.csv gpurun_out/traffic_*.log
 bash scripts/capture_traffic.sh all
-bash scripts/profile_r2.sh
+bash scripts/profile_r2_final.sh
