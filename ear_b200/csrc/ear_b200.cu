@@ -66,8 +66,17 @@ static void trim_locked(size_t keep) {
 		g_free.erase(it);
 	}
 }
+// blocks below this size are not cached (EAR_B200_CACHE_MIN_KB): they hold the hot words of the engine (list counters, queue
+// head, context tables), cost microseconds to allocate, and the shade kernel ran up to 30 % slower when they sat in recycled
+// blocks (profiles/r2_ab_closest.txt, diag3-diag6)
+static size_t min_cached() {
+	static size_t v = ~(size_t)0;
+	if (v == ~(size_t)0) { const char* e = std::getenv("EAR_B200_CACHE_MIN_KB"); v = (size_t)(e ? std::max(0, std::atoi(e)) : 1024) << 10; }
+	return v;
+}
 static cudaError_t alloc(void** out, size_t bytes) {
 	bytes = std::max<size_t>((bytes + 255) / 256 * 256, 256);
+	if (bytes < min_cached()) return cudaMalloc(out, bytes);   // release() finds it unknown and hands it to cudaFree
 	int dev = 0;
 	cudaGetDevice(&dev);
 	std::lock_guard<std::mutex> g(g_lock);
