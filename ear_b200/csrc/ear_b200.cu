@@ -135,11 +135,19 @@ static void* take(size_t bytes, size_t* got) {
 	*got = bytes;
 	return p;
 }
+static size_t byte_limit() {   // page-locked memory is a scarce host resource: EAR_B200_HOST_CACHE_MB (default 8192)
+	static size_t v = 0;
+	if (!v) { const char* e = std::getenv("EAR_B200_HOST_CACHE_MB"); v = ((size_t)(e ? std::max(0, std::atoi(e)) : 8192) << 20) + 1; }
+	return v;
+}
 static void give(void* p, size_t bytes) {
 	if (!p) return;
 	std::lock_guard<std::mutex> g(g_lock);
 	g_free.push_back(Block{p, bytes});
-	while (g_free.size() > kHostCacheBlocks) {   // drop the oldest
+	size_t held = 0;
+	for (const auto& b : g_free) held += b.bytes;
+	while (!g_free.empty() && (g_free.size() > kHostCacheBlocks || held > byte_limit())) {   // drop the oldest
+		held -= g_free.front().bytes;
 		cudaFreeHost(g_free.front().p);
 		g_free.erase(g_free.begin());
 	}
